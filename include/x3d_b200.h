@@ -1,0 +1,260 @@
+/*
+ * x3d_b200.h — C ABI of the B200-native hot path for Xcompact3d.
+ *
+ * Every entry point below replaces one procedure of the reference
+ * (xcompact3d/Incompact3d v5.0, paths relative to the reference tree); the
+ * file:line of the interface it replaces is cited beside it.  The ABI is what
+ * an ISO_C_BINDING `interface ... bind(C)` block binds to (see
+ * incompact3d_b200/fortran/x3d_gpu.f90 and INTEGRATION.md):
+ *
+ *   - plain pointers and sizes only, no C++/torch types;
+ *   - operator entry points keep the reference's argument list and order and
+ *     take scalars BY REFERENCE (Fortran convention), preceded by the context
+ *     handle (passed by value);
+ *   - arrays are column-major (i fastest), real(8) / complex(8) / integer(4);
+ *   - every pointer argument may be a HOST pointer or a DEVICE pointer; the
+ *     library classifies it (cudaPointerGetAttributes).  Host fields are staged
+ *     through device scratch (drop-in mode); device fields are used in place;
+ *   - every function returns 0 on success, non-zero on error and never aborts;
+ *     x3d_last_error() gives the message (the Fortran shim calls
+ *     decomp_2d_abort, the reference's convention, src/schemes.f90:472-473).
+ *
+ * There is NO CPU fallback: without a CUDA device x3d_create fails.
+ */
+#ifndef X3D_B200_H
+#define X3D_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct x3d_ctx x3d_ctx;
+
+/* ---- lifecycle ------------------------------------------------------- */
+int x3d_create(x3d_ctx **ctx, int device);
+int x3d_destroy(x3d_ctx *ctx);
+const char *x3d_last_error(void);
+int x3d_version(void);
+/* number of kernels of this library launched since context creation */
+long long x3d_launch_count(const x3d_ctx *ctx);
+/* blocks until all work queued on the context's stream has finished */
+int x3d_sync(x3d_ctx *ctx);
+/* the cudaStream_t the context launches on (as an integer handle) */
+unsigned long long x3d_stream(x3d_ctx *ctx);
+
+/* ---- hidden module state made explicit -------------------------------
+ * The reference operators read stencil scalars from modules derivX/Y/Z
+ * (src/module_param.f90:559-617), filter scalars from parfiX/Y/Z
+ * (src/module_param.f90:621-656) and flags from module param
+ * (iibm src/derive.f90:23, istret :409, iimplicit :2166, nclx/y/z :3816).   */
+typedef struct x3d_deriv_coeffs {
+  /* first derivative, src/schemes.f90:443-520 */
+  double alfa1, af1, bf1, cf1, df1, alfa2, af2;
+  double alfan, afn, bfn, cfn, dfn, alfam, afm;
+  double alfai, afi, bfi;
+  /* second derivative, src/schemes.f90:602-740 */
+  double alsa1, as1, bs1, cs1, ds1, alsa2, as2;
+  double alsan, asn, bsn, csn, dsn, alsam, asm_;
+  double alsa3, as3, bs3, alsat, ast, bst;
+  double alsa4, as4, bs4, cs4, alsatt, astt, bstt, cstt;
+  double alsai, asi, bsi, csi, dsi;
+  /* staggered derivative / interpolation, src/schemes.f90:860-931 */
+  double alcai6, aci6, bci6;
+  double ailcai6, aici6, bici6, cici6, dici6;
+} x3d_deriv_coeffs;
+
+typedef struct x3d_filter_coeffs { /* src/filters.f90:62-138 */
+  double fial1, fia1, fib1, fic1, fid1;
+  double fial2, fia2, fib2, fic2, fid2;
+  double fial3, fia3, fib3, fic3, fid3, fie3, fif3;
+  double fialn, fian, fibn, ficn, fidn;
+  double fialm, fiam, fibm, ficm, fidm;
+  double fialp, fiap, fibp, ficp, fidp, fiep, fifp;
+  double fiali, fiai, fibi, fici, fidi;
+} x3d_filter_coeffs;
+
+/* axis: 0 = x, 1 = y, 2 = z */
+int x3d_set_deriv_coeffs(x3d_ctx *ctx, int axis, const x3d_deriv_coeffs *c);
+int x3d_set_filter_coeffs(x3d_ctx *ctx, int axis, const x3d_filter_coeffs *c);
+/* module param flags; nclx/ncly/nclz are the LOGICALs (1 = periodic)       */
+int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit,
+                  int nclx, int ncly, int nclz);
+
+/* ---- compact operators ------------------------------------------------
+ * abstract interfaces DERIVATIVE_X/Y/Z, src/module_param.f90:136-167 and
+ * FILTER_X/Y/Z :203-226.  t is output; u input; r,s caller scratch (ignored:
+ * the Sherman-Morrison vector is precomputed per coefficient set); ff,fs,fw
+ * the LU arrays from prepare(), src/schemes.f90:413-439 (host pointers).     */
+#define X3D_DECL_DERX(name)                                                    \
+  int x3d_##name(x3d_ctx *ctx, double *tx, const double *ux, double *rx,       \
+                 double *sx, const double *ffx, const double *fsx,             \
+                 const double *fwx, const int *nx, const int *ny,              \
+                 const int *nz, const int *npaire, const double *lind)
+#define X3D_DECL_DERY(name)                                                    \
+  int x3d_##name(x3d_ctx *ctx, double *ty, const double *uy, double *ry,       \
+                 double *sy, const double *ffy, const double *fsy,             \
+                 const double *fwy, const double *ppy, const int *nx,          \
+                 const int *ny, const int *nz, const int *npaire,              \
+                 const double *lind)
+/* src/derive.f90:7,68,141,211,281 */
+X3D_DECL_DERX(derx_00); X3D_DECL_DERX(derx_11); X3D_DECL_DERX(derx_12);
+X3D_DECL_DERX(derx_21); X3D_DECL_DERX(derx_22);
+/* src/derive.f90:325,423,545,664,783 */
+X3D_DECL_DERY(dery_00); X3D_DECL_DERY(dery_11); X3D_DECL_DERY(dery_12);
+X3D_DECL_DERY(dery_21); X3D_DECL_DERY(dery_22);
+/* src/derive.f90:858,951,1064,1176,1288 */
+X3D_DECL_DERX(derz_00); X3D_DECL_DERX(derz_11); X3D_DECL_DERX(derz_12);
+X3D_DECL_DERX(derz_21); X3D_DECL_DERX(derz_22);
+/* src/derive.f90:1354,1481,1666,1822,1978 */
+X3D_DECL_DERX(derxx_00); X3D_DECL_DERX(derxx_11); X3D_DECL_DERX(derxx_12);
+X3D_DECL_DERX(derxx_21); X3D_DECL_DERX(derxx_22);
+/* src/derive.f90:2052,2207,2433,2631,2829 (no ppy argument) */
+X3D_DECL_DERX(deryy_00); X3D_DECL_DERX(deryy_11); X3D_DECL_DERX(deryy_12);
+X3D_DECL_DERX(deryy_21); X3D_DECL_DERX(deryy_22);
+/* src/derive.f90:2923,3082,3307,3503,3699 */
+X3D_DECL_DERX(derzz_00); X3D_DECL_DERX(derzz_11); X3D_DECL_DERX(derzz_12);
+X3D_DECL_DERX(derzz_21); X3D_DECL_DERX(derzz_22);
+/* src/filters.f90:221,292,384,470,558 / 605.. / 990.. */
+X3D_DECL_DERX(filx_00); X3D_DECL_DERX(filx_11); X3D_DECL_DERX(filx_12);
+X3D_DECL_DERX(filx_21); X3D_DECL_DERX(filx_22);
+X3D_DECL_DERX(fily_00); X3D_DECL_DERX(fily_11); X3D_DECL_DERX(fily_12);
+X3D_DECL_DERX(fily_21); X3D_DECL_DERX(fily_22);
+X3D_DECL_DERX(filz_00); X3D_DECL_DERX(filz_11); X3D_DECL_DERX(filz_12);
+X3D_DECL_DERX(filz_21); X3D_DECL_DERX(filz_22);
+
+/* staggered operators (velocity mesh <-> pressure mesh).  Argument lists as in
+ * the reference; note the order of (n, nm) differs between vp and pv.        */
+/* src/derive.f90:3796 derxvp, :3911 interxvp */
+int x3d_derxvp(x3d_ctx *ctx, double *tx, const double *ux, double *rx,
+               double *sx, const double *cfx6, const double *csx6,
+               const double *cwx6, const int *nx, const int *nxm,
+               const int *ny, const int *nz, const int *npaire);
+int x3d_interxvp(x3d_ctx *ctx, double *tx, const double *ux, double *rx,
+                 double *sx, const double *cifx6, const double *cisx6,
+                 const double *ciwx6, const int *nx, const int *nxm,
+                 const int *ny, const int *nz, const int *npaire);
+/* src/derive.f90:4041 derxpv, :4126 interxpv */
+int x3d_derxpv(x3d_ctx *ctx, double *tx, const double *ux, double *rx,
+               double *sx, const double *cfi6, const double *csi6,
+               const double *cwi6, const double *cfx6, const double *csx6,
+               const double *cwx6, const int *nxm, const int *nx,
+               const int *ny, const int *nz, const int *npaire);
+int x3d_interxpv(x3d_ctx *ctx, double *tx, const double *ux, double *rx,
+                 double *sx, const double *cifi6, const double *cisi6,
+                 const double *ciwi6, const double *cifx6, const double *cisx6,
+                 const double *ciwx6, const int *nxm, const int *nx,
+                 const int *ny, const int *nz, const int *npaire);
+/* src/derive.f90:4265 interyvp, :4442 deryvp, :4587 interypv, :4775 derypv */
+int x3d_interyvp(x3d_ctx *ctx, double *ty, const double *uy, double *ry,
+                 double *sy, const double *cify6, const double *cisy6,
+                 const double *ciwy6, const int *nx, const int *ny,
+                 const int *nym, const int *nz, const int *npaire);
+int x3d_deryvp(x3d_ctx *ctx, double *ty, const double *uy, double *ry,
+               double *sy, const double *cfy6, const double *csy6,
+               const double *cwy6, const double *ppyi, const int *nx,
+               const int *ny, const int *nym, const int *nz,
+               const int *npaire);
+int x3d_interypv(x3d_ctx *ctx, double *ty, const double *uy, double *ry,
+                 double *sy, const double *cifi6y, const double *cisi6y,
+                 const double *ciwi6y, const double *cify6, const double *cisy6,
+                 const double *ciwy6, const int *nx, const int *nym,
+                 const int *ny, const int *nz, const int *npaire);
+int x3d_derypv(x3d_ctx *ctx, double *ty, const double *uy, double *ry,
+               double *sy, const double *cfi6y, const double *csi6y,
+               const double *cwi6y, const double *cfy6, const double *csy6,
+               const double *cwy6, const double *ppy, const int *nx,
+               const int *nym, const int *ny, const int *nz,
+               const int *npaire);
+/* src/derive.f90:4920 derzvp, :5105 interzvp, :5287 derzpv, :5426 interzpv */
+int x3d_derzvp(x3d_ctx *ctx, double *tz, const double *uz, double *rz,
+               double *sz, const double *cfz6, const double *csz6,
+               const double *cwz6, const int *nx, const int *ny, const int *nz,
+               const int *nzm, const int *npaire);
+int x3d_interzvp(x3d_ctx *ctx, double *tz, const double *uz, double *rz,
+                 double *sz, const double *cifz6, const double *cisz6,
+                 const double *ciwz6, const int *nx, const int *ny,
+                 const int *nz, const int *nzm, const int *npaire);
+int x3d_derzpv(x3d_ctx *ctx, double *tz, const double *uz, double *rz,
+               double *sz, const double *cfiz6, const double *csiz6,
+               const double *cwiz6, const double *cfz6, const double *csz6,
+               const double *cwz6, const int *nx, const int *ny,
+               const int *nzm, const int *nz, const int *npaire);
+int x3d_interzpv(x3d_ctx *ctx, double *tz, const double *uz, double *rz,
+                 double *sz, const double *cifiz6, const double *cisiz6,
+                 const double *ciwiz6, const double *cifz6, const double *cisz6,
+                 const double *ciwz6, const int *nx, const int *ny,
+                 const int *nzm, const int *nz, const int *npaire);
+
+/* ---- 2DECOMP&FFT pencil decomposition (external library v2.0.4) ---------
+ * decomp_2d_init (call site src/xcompact3d.f90:191) and decomp_info_init
+ * (:197-201, src/poisson.f90:132-133).  A decomposition handle plays the role
+ * of TYPE(DECOMP_INFO); id 0 is the main (nx,ny,nz) decomposition.           */
+typedef struct x3d_decomp_info {
+  int xst[3], xen[3], xsz[3]; /* 1-based inclusive, as in DECOMP_INFO */
+  int yst[3], yen[3], ysz[3];
+  int zst[3], zen[3], zsz[3];
+} x3d_decomp_info;
+/* nranks = p_row*p_col, rank in [0,nranks). Single-process contexts use
+ * nranks = 1.  nccl_unique_id: 128 opaque bytes shared by all ranks (may be
+ * NULL when nranks == 1).                                                    */
+int x3d_decomp_init(x3d_ctx *ctx, int nx, int ny, int nz, int p_row, int p_col,
+                    int rank, int nranks, const void *nccl_unique_id);
+int x3d_nccl_unique_id(void *out128);
+int x3d_decomp_info_init(x3d_ctx *ctx, int nx, int ny, int nz, int *decomp_id);
+int x3d_decomp_info_get(x3d_ctx *ctx, int decomp_id, x3d_decomp_info *out);
+/* transpose_x_to_y etc. (call sites src/transeq.f90:163,236,318,437); the
+ * complex variants are used on the spectral decomposition sp
+ * (src/poisson.f90:759).  Bit-exact data movement.                           */
+int x3d_transpose_x_to_y(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_y_to_z(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_z_to_y(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_y_to_x(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_x_to_y_complex(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_y_to_z_complex(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_z_to_y_complex(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+int x3d_transpose_y_to_x_complex(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
+
+/* ---- spectral Poisson solver -------------------------------------------
+ * decomp_2d_poisson_init src/poisson.f90:73 and the `poisson` procedure
+ * pointer :63 (poisson_000 :298, _100 :413, _010 :665, _11x :1019).          */
+typedef struct x3d_poisson_params {
+  int nx, ny, nz;          /* velocity-mesh node counts (nx_global ...)     */
+  int bcx, bcy, bcz;       /* 0 periodic, 1 otherwise (src/poisson.f90:79-93)*/
+  double xlx, yly, zlz;    /* domain lengths                                */
+  int istret;              /* stretched-mesh option                         */
+  double alpha, beta;      /* mod_stret parameters (src/stretching.f90)     */
+} x3d_poisson_params;
+int x3d_poisson_init(x3d_ctx *ctx, const x3d_poisson_params *p);
+/* rhs: z-pencil of the pressure mesh (ph%zsz), in place */
+int x3d_poisson(x3d_ctx *ctx, double *rhs);
+
+/* ---- device-resident solver -------------
+ * momentum_rhs_eq src/transeq.f90:73, intt src/time_integrators.f90:18,
+ * pre_correc/divergence/gradp/cor_vel src/navier.f90:502,257,386,206,
+ * init_tgv / postprocess_tgv src/Case-TGV.f90:25,189.                        */
+typedef struct x3d_solver_params {
+  int nx, ny, nz;                 /* nodes */
+  int nclx1, nclxn, ncly1, nclyn, nclz1, nclzn;
+  double xlx, yly, zlz;
+  double re, dt;
+  int ifirstder, isecondder, ipinter, itimescheme; /* 5 = RK3 */
+  int istret; double beta;
+  double nu0nu, cnu;
+  int p_row, p_col;
+} x3d_solver_params;
+int x3d_solver_init(x3d_ctx *ctx, const x3d_solver_params *p);
+int x3d_solver_init_tgv(x3d_ctx *ctx);
+/* set / get the x-pencil velocity fields (host or device pointers) */
+int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, const double *uz);
+int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz);
+/* advance nsteps full time steps (iadvance_time sub-steps each) */
+int x3d_solver_step(x3d_ctx *ctx, int nsteps);
+/* out5 = (eek, eps, eps2, enst, divmax) as postprocess_tgv writes them      */
+int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5);
+/* DIV U max / mean of the current velocity (divergence nlock=2)             */
+int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X3D_B200_H */
