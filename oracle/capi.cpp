@@ -1,0 +1,95 @@
+// capi.cpp -- C entry points of the oracle for ctypes (TEST INFRASTRUCTURE).
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include "x3d_oracle.hpp"
+
+using namespace x3do;
+
+static thread_local std::string g_err;
+
+static vec *axis_array(AxisScheme *a, const std::string &nm) {
+#define A(x) if (nm == #x) return &a->x;
+  A(ff) A(fs) A(fw) A(ffp) A(fsp) A(fwp) A(sf) A(ss) A(sw) A(sfp) A(ssp) A(swp)
+  A(cfx6) A(ccx6) A(cbx6) A(cfxp6) A(csxp6) A(cwxp6) A(csx6) A(cwx6)
+  A(cifx6) A(cicx6) A(cibx6) A(cifxp6) A(cisxp6) A(ciwxp6) A(cisx6) A(ciwx6)
+  A(cfi6) A(cci6) A(cbi6) A(cfip6) A(csip6) A(cwip6) A(csi6) A(cwi6)
+  A(cifi6) A(cici6) A(cibi6) A(cifip6) A(cisip6) A(ciwip6) A(cisi6) A(ciwi6)
+  A(fiff) A(fifs) A(fifw) A(fiffp) A(fifsp) A(fifwp)
+#undef A
+  return nullptr;
+}
+
+// parse "derx_11", "deryy_00", "filz_22", "derxvp", "interzpv" ...
+static bool parse_op(const char *name, OpKind &kind, int &axis, int &ncl1, int &ncln) {
+  std::string s(name);
+  auto ax = [](char ch) { return ch == 'x' ? 0 : ch == 'y' ? 1 : ch == 'z' ? 2 : -1; };
+  ncl1 = ncln = -1;
+  if (s.size() >= 6 && (s.substr(s.size() - 2) == "vp" || s.substr(s.size() - 2) == "pv")) {
+    const bool vp = s.substr(s.size() - 2) == "vp";
+    const bool inter = s.rfind("inter", 0) == 0;
+    axis = ax(s[inter ? 5 : 3]);
+    kind = inter ? (vp ? IVP : IPV) : (vp ? DVP : DPV);
+    return axis >= 0;
+  }
+  auto us = s.find('_');
+  if (us == std::string::npos || s.size() != us + 3) return false;
+  ncl1 = s[us + 1] - '0';
+  ncln = s[us + 2] - '0';
+  std::string head = s.substr(0, us);
+  if (head.rfind("fil", 0) == 0 && head.size() == 4) { kind = FIL; axis = ax(head[3]); return axis >= 0; }
+  if (head.rfind("der", 0) == 0 && head.size() == 4) { kind = D1; axis = ax(head[3]); return axis >= 0; }
+  if (head.rfind("der", 0) == 0 && head.size() == 5 && head[3] == head[4]) { kind = D2; axis = ax(head[3]); return axis >= 0; }
+  return false;
+}
+
+extern "C" {
+
+const char *x3do_last_error() { return g_err.c_str(); }
+
+void *x3do_axis_create(int n, int ncl1, int ncln, double len, int ifirstder, int isecondder, int ipinter,
+                       double nu0nu, double cnu) {
+  try {
+    SchemeOptions o;
+    o.ifirstder = ifirstder; o.isecondder = isecondder; o.ipinter = ipinter; o.nu0nu = nu0nu; o.cnu = cnu;
+    return new AxisScheme(make_axis(n, ncl1, ncln, len, o));
+  } catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void x3do_axis_destroy(void *a) { delete static_cast<AxisScheme *>(a); }
+void x3do_axis_set_filter(void *a, double af) { set_filter_coefficients(*static_cast<AxisScheme *>(a), af); }
+int x3do_axis_nm(void *a) { return static_cast<AxisScheme *>(a)->nm; }
+double x3do_axis_d(void *a) { return static_cast<AxisScheme *>(a)->d; }
+int x3do_axis_get_array(void *a, const char *name, double *out, int cap) {
+  vec *v = axis_array(static_cast<AxisScheme *>(a), name);
+  if (!v) return -1;
+  const int n = static_cast<int>(v->size());
+  if (out && cap >= n) std::memcpy(out, v->data(), n * sizeof(double));
+  return n;
+}
+void x3do_axis_get_coeffs(void *a, x3d_deriv_coeffs *c, x3d_filter_coeffs *fc) {
+  auto *s = static_cast<AxisScheme *>(a);
+  if (c) *c = s->c;
+  if (fc) *fc = s->fc;
+}
+
+// the reference operator interface: caller passes LU arrays and module scalars
+int x3do_op(const char *name, const int *dims_in, int npaire, const double *u, double *t, const double *f,
+            const double *s, const double *w, const double *post, const x3d_deriv_coeffs *c,
+            const x3d_filter_coeffs *fc, int periodic, int rhs_only) {
+  try {
+    OpDesc op{};
+    int axis;
+    if (!parse_op(name, op.kind, axis, op.ncl1, op.ncln)) { g_err = std::string("unknown operator ") + name; return 1; }
+    op.periodic = periodic != 0;
+    op.npaire = npaire;
+    op.f = f; op.s = s; op.w = w; op.c = c; op.fc = fc; op.post = post; op.rhs_only = rhs_only != 0;
+    const int ext = dims_in[axis];
+    if (op.kind == DVP || op.kind == IVP) { op.n = ext; op.nm = op.periodic ? ext : ext - 1; }
+    else if (op.kind == DPV || op.kind == IPV) { op.nm = ext; op.n = op.periodic ? ext : ext + 1; }
+    else { op.n = ext; op.nm = ext; }
+    apply_op(op, axis, dims_in, u, t);
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 2; }
+}
+
+}  // extern "C"
