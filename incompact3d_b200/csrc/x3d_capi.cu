@@ -1,0 +1,228 @@
+// x3d_capi.cu -- extern "C" entry points declared in include/x3d_b200.h.
+#include <cstring>
+#include "x3d_ctx.cuh"
+
+using namespace x3d;
+
+struct x3d_ctx {
+  Ctx c;
+};
+
+static thread_local std::string g_last_error;
+
+template <class F>
+static int guard(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    return 1;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return 2;
+  }
+}
+
+extern "C" {
+
+const char *x3d_last_error(void) { return g_last_error.c_str(); }
+int x3d_version(void) { return 100; }
+
+int x3d_create(x3d_ctx **out, int device) {
+  return guard([&] {
+    if (!out) throw Error("x3d_create: null output");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(std::string("x3d_create: no CUDA device (") + cudaGetErrorString(e) +
+                  "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) throw Error("x3d_create: bad device index");
+    X3D_CUDA(cudaSetDevice(device));
+    auto *h = new x3d_ctx();
+    h->c.device = device;
+    cudaDeviceProp prop{};
+    X3D_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->c.sm_count = prop.multiProcessorCount;
+    X3D_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    *out = h;
+  });
+}
+int x3d_destroy(x3d_ctx *ctx) {
+  return guard([&] {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    delete ctx;
+  });
+}
+long long x3d_launch_count(const x3d_ctx *ctx) { return ctx ? ctx->c.launches : -1; }
+int x3d_sync(x3d_ctx *ctx) {
+  return guard([&] {
+    X3D_CUDA(cudaSetDevice(ctx->c.device));
+    X3D_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+unsigned long long x3d_stream(x3d_ctx *ctx) { return reinterpret_cast<unsigned long long>(ctx->c.stream); }
+
+int x3d_set_deriv_coeffs(x3d_ctx *ctx, int axis, const x3d_deriv_coeffs *c) {
+  return guard([&] {
+    if (axis < 0 || axis > 2 || !c) throw Error("x3d_set_deriv_coeffs: bad argument");
+    ctx->c.dc[axis] = *c;
+    ctx->c.have_dc[axis] = true;
+  });
+}
+int x3d_set_filter_coeffs(x3d_ctx *ctx, int axis, const x3d_filter_coeffs *c) {
+  return guard([&] {
+    if (axis < 0 || axis > 2 || !c) throw Error("x3d_set_filter_coeffs: bad argument");
+    ctx->c.fc[axis] = *c;
+    ctx->c.have_fc[axis] = true;
+  });
+}
+int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit, int nclx, int ncly, int nclz) {
+  return guard([&] {
+    if (iibm == 2 || iibm == 3)
+      throw Error("iibm=2/3 (lagpol/cubspl pre-pass inside the operators, src/derive.f90:23-24) is not implemented");
+    ctx->c.iibm = iibm; ctx->c.istret = istret; ctx->c.iimplicit = iimplicit;
+    ctx->c.ncl[0] = nclx != 0; ctx->c.ncl[1] = ncly != 0; ctx->c.ncl[2] = nclz != 0;
+  });
+}
+
+// ---- collocated operators --------------------------------------------------------
+static int colloc(x3d_ctx *ctx, Kind kind, int axis, int ncl1, int ncln, double *t, const double *u, const double *f,
+                  const double *s, const double *w, const double *pp, int nx, int ny, int nz, int npaire) {
+  return guard([&] {
+    if (!ctx) throw Error("null context");
+    OpCall call{};
+    call.kind = kind; call.axis = axis; call.ncl1 = ncl1; call.ncln = ncln;
+    call.periodic = (ncl1 == 0 && ncln == 0);
+    call.npaire = npaire;
+    call.dims_in[0] = nx; call.dims_in[1] = ny; call.dims_in[2] = nz;
+    call.n = call.nm = call.dims_in[axis];
+    call.f = f; call.s = s; call.w = w;
+    // dery_*: ty = ty*ppy when istret /= 0 (src/derive.f90:409-417)
+    call.post = (kind == D1 && axis == 1 && ctx->c.istret != 0) ? pp : nullptr;
+    // deryy_*: return after the RHS when iimplicit >= 1 (src/derive.f90:2166)
+    call.rhs_only = (kind == D2 && axis == 1 && ctx->c.iimplicit >= 1);
+    run_op(ctx->c, call, u, t);
+  });
+}
+
+#define X3D_DEF_X(name, kind, axis, a, b)                                                                     \
+  int x3d_##name(x3d_ctx *ctx, double *tx, const double *ux, double *rx, double *sx, const double *ffx,       \
+                 const double *fsx, const double *fwx, const int *nx, const int *ny, const int *nz,           \
+                 const int *npaire, const double *lind) {                                                     \
+    (void)rx; (void)sx; (void)lind;                                                                           \
+    return colloc(ctx, kind, axis, a, b, tx, ux, ffx, fsx, fwx, nullptr, *nx, *ny, *nz, *npaire);             \
+  }
+#define X3D_DEF_Y(name, kind, axis, a, b)                                                                     \
+  int x3d_##name(x3d_ctx *ctx, double *ty, const double *uy, double *ry, double *sy, const double *ffy,       \
+                 const double *fsy, const double *fwy, const double *ppy, const int *nx, const int *ny,       \
+                 const int *nz, const int *npaire, const double *lind) {                                      \
+    (void)ry; (void)sy; (void)lind;                                                                           \
+    return colloc(ctx, kind, axis, a, b, ty, uy, ffy, fsy, fwy, ppy, *nx, *ny, *nz, *npaire);                 \
+  }
+#define X3D_FIVE(M, stem, kind, axis) \
+  M(stem##_00, kind, axis, 0, 0) M(stem##_11, kind, axis, 1, 1) M(stem##_12, kind, axis, 1, 2) \
+  M(stem##_21, kind, axis, 2, 1) M(stem##_22, kind, axis, 2, 2)
+
+X3D_FIVE(X3D_DEF_X, derx, D1, 0)
+X3D_FIVE(X3D_DEF_Y, dery, D1, 1)
+X3D_FIVE(X3D_DEF_X, derz, D1, 2)
+X3D_FIVE(X3D_DEF_X, derxx, D2, 0)
+X3D_FIVE(X3D_DEF_X, deryy, D2, 1)
+X3D_FIVE(X3D_DEF_X, derzz, D2, 2)
+X3D_FIVE(X3D_DEF_X, filx, FIL, 0)
+X3D_FIVE(X3D_DEF_X, fily, FIL, 1)
+X3D_FIVE(X3D_DEF_X, filz, FIL, 2)
+
+// ---- staggered operators ------------------------------------------------------------
+static int stag(x3d_ctx *ctx, Kind kind, int axis, double *t, const double *u, const double *f, const double *s,
+                const double *w, const double *pp, int d0, int d1, int d2, int n, int nm, int npaire) {
+  return guard([&] {
+    if (!ctx) throw Error("null context");
+    OpCall call{};
+    call.kind = kind; call.axis = axis; call.ncl1 = call.ncln = -1;
+    call.periodic = ctx->c.ncl[axis];
+    call.npaire = npaire;
+    call.n = n; call.nm = nm;
+    call.dims_in[0] = d0; call.dims_in[1] = d1; call.dims_in[2] = d2;
+    call.f = f; call.s = s; call.w = w;
+    call.post = (ctx->c.istret != 0) ? pp : nullptr;  // deryvp*ppyi, derypv*ppy (derive.f90:4572,4905)
+    run_op(ctx->c, call, u, t);
+  });
+}
+
+int x3d_derxvp(x3d_ctx *ctx, double *tx, const double *ux, double *, double *, const double *cfx6, const double *csx6,
+               const double *cwx6, const int *nx, const int *nxm, const int *ny, const int *nz, const int *npaire) {
+  return stag(ctx, DVP, 0, tx, ux, cfx6, csx6, cwx6, nullptr, *nx, *ny, *nz, *nx, *nxm, *npaire);
+}
+int x3d_interxvp(x3d_ctx *ctx, double *tx, const double *ux, double *, double *, const double *cifx6,
+                 const double *cisx6, const double *ciwx6, const int *nx, const int *nxm, const int *ny, const int *nz,
+                 const int *npaire) {
+  return stag(ctx, IVP, 0, tx, ux, cifx6, cisx6, ciwx6, nullptr, *nx, *ny, *nz, *nx, *nxm, *npaire);
+}
+// pv operators: the periodic branch sweeps with the second LU triple (cfx6..), the other with the first
+int x3d_derxpv(x3d_ctx *ctx, double *tx, const double *ux, double *, double *, const double *cfi6, const double *csi6,
+               const double *cwi6, const double *cfx6, const double *csx6, const double *cwx6, const int *nxm,
+               const int *nx, const int *ny, const int *nz, const int *npaire) {
+  const bool per = ctx && ctx->c.ncl[0];
+  return stag(ctx, DPV, 0, tx, ux, per ? cfx6 : cfi6, per ? csx6 : csi6, per ? cwx6 : cwi6, nullptr, *nxm, *ny, *nz, *nx,
+              *nxm, *npaire);
+}
+int x3d_interxpv(x3d_ctx *ctx, double *tx, const double *ux, double *, double *, const double *cifi6,
+                 const double *cisi6, const double *ciwi6, const double *cifx6, const double *cisx6,
+                 const double *ciwx6, const int *nxm, const int *nx, const int *ny, const int *nz, const int *npaire) {
+  const bool per = ctx && ctx->c.ncl[0];
+  return stag(ctx, IPV, 0, tx, ux, per ? cifx6 : cifi6, per ? cisx6 : cisi6, per ? ciwx6 : ciwi6, nullptr, *nxm, *ny, *nz,
+              *nx, *nxm, *npaire);
+}
+int x3d_interyvp(x3d_ctx *ctx, double *ty, const double *uy, double *, double *, const double *cify6,
+                 const double *cisy6, const double *ciwy6, const int *nx, const int *ny, const int *nym, const int *nz,
+                 const int *npaire) {
+  return stag(ctx, IVP, 1, ty, uy, cify6, cisy6, ciwy6, nullptr, *nx, *ny, *nz, *ny, *nym, *npaire);
+}
+int x3d_deryvp(x3d_ctx *ctx, double *ty, const double *uy, double *, double *, const double *cfy6, const double *csy6,
+               const double *cwy6, const double *ppyi, const int *nx, const int *ny, const int *nym, const int *nz,
+               const int *npaire) {
+  return stag(ctx, DVP, 1, ty, uy, cfy6, csy6, cwy6, ppyi, *nx, *ny, *nz, *ny, *nym, *npaire);
+}
+int x3d_interypv(x3d_ctx *ctx, double *ty, const double *uy, double *, double *, const double *cifi6y,
+                 const double *cisi6y, const double *ciwi6y, const double *cify6, const double *cisy6,
+                 const double *ciwy6, const int *nx, const int *nym, const int *ny, const int *nz, const int *npaire) {
+  const bool per = ctx && ctx->c.ncl[1];
+  return stag(ctx, IPV, 1, ty, uy, per ? cify6 : cifi6y, per ? cisy6 : cisi6y, per ? ciwy6 : ciwi6y, nullptr, *nx, *nym,
+              *nz, *ny, *nym, *npaire);
+}
+int x3d_derypv(x3d_ctx *ctx, double *ty, const double *uy, double *, double *, const double *cfi6y,
+               const double *csi6y, const double *cwi6y, const double *cfy6, const double *csy6, const double *cwy6,
+               const double *ppy, const int *nx, const int *nym, const int *ny, const int *nz, const int *npaire) {
+  const bool per = ctx && ctx->c.ncl[1];
+  return stag(ctx, DPV, 1, ty, uy, per ? cfy6 : cfi6y, per ? csy6 : csi6y, per ? cwy6 : cwi6y, ppy, *nx, *nym, *nz, *ny,
+              *nym, *npaire);
+}
+int x3d_derzvp(x3d_ctx *ctx, double *tz, const double *uz, double *, double *, const double *cfz6, const double *csz6,
+               const double *cwz6, const int *nx, const int *ny, const int *nz, const int *nzm, const int *npaire) {
+  return stag(ctx, DVP, 2, tz, uz, cfz6, csz6, cwz6, nullptr, *nx, *ny, *nz, *nz, *nzm, *npaire);
+}
+int x3d_interzvp(x3d_ctx *ctx, double *tz, const double *uz, double *, double *, const double *cifz6,
+                 const double *cisz6, const double *ciwz6, const int *nx, const int *ny, const int *nz, const int *nzm,
+                 const int *npaire) {
+  return stag(ctx, IVP, 2, tz, uz, cifz6, cisz6, ciwz6, nullptr, *nx, *ny, *nz, *nz, *nzm, *npaire);
+}
+int x3d_derzpv(x3d_ctx *ctx, double *tz, const double *uz, double *, double *, const double *cfiz6,
+               const double *csiz6, const double *cwiz6, const double *cfz6, const double *csz6, const double *cwz6,
+               const int *nx, const int *ny, const int *nzm, const int *nz, const int *npaire) {
+  const bool per = ctx && ctx->c.ncl[2];
+  return stag(ctx, DPV, 2, tz, uz, per ? cfz6 : cfiz6, per ? csz6 : csiz6, per ? cwz6 : cwiz6, nullptr, *nx, *ny, *nzm,
+              *nz, *nzm, *npaire);
+}
+int x3d_interzpv(x3d_ctx *ctx, double *tz, const double *uz, double *, double *, const double *cifiz6,
+                 const double *cisiz6, const double *ciwiz6, const double *cifz6, const double *cisz6,
+                 const double *ciwz6, const int *nx, const int *ny, const int *nzm, const int *nz, const int *npaire) {
+  const bool per = ctx && ctx->c.ncl[2];
+  return stag(ctx, IPV, 2, tz, uz, per ? cifz6 : cifiz6, per ? cisz6 : cisiz6, per ? ciwz6 : ciwiz6, nullptr, *nx, *ny,
+              *nzm, *nz, *nzm, *npaire);
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// x3d_ctx.cuh -- the library context (opaque x3d_ctx of the C ABI).
+#pragma once
+#include "x3d_common.cuh"
+
+namespace x3d {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  void reserve(size_t n) {
+    if (n <= bytes) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    X3D_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct PoissonState;
+struct DecompState;
+struct SolverState;
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  long long launches = 0;
+  // module state made explicit (x3d_set_deriv_coeffs / x3d_set_filter_coeffs / x3d_set_flags)
+  x3d_deriv_coeffs dc[3]{};
+  x3d_filter_coeffs fc[3]{};
+  bool have_dc[3] = {false, false, false}, have_fc[3] = {false, false, false};
+  int iibm = 0, istret = 0, iimplicit = 0;
+  bool ncl[3] = {true, true, true};
+  // caches
+  std::map<uint64_t, std::unique_ptr<TriTable>> tri_cache;
+  // staging for host-pointer (drop-in) calls
+  DevBuf stage_in, stage_out;
+  // sub-systems
+  std::unique_ptr<DecompState> decomp;
+  std::unique_ptr<PoissonState> poisson;
+  std::unique_ptr<SolverState> solver;
+  Ctx();
+  ~Ctx();
+};
+
+// device pointer classification: true if p is device (or managed) memory
+bool is_device_ptr(const void *p);
+
+// LU arrays (host) -> cached device table for chunk length L
+const TriTable &get_tri(Ctx &ctx, const double *f, const double *s, const double *w, int n, int L, bool periodic,
+                        double alpha, const double *post);
+
+// launchers (device pointers)
+void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double *d_u, double *d_t);
+// full operator call with host-or-device pointers
+void run_op(Ctx &ctx, OpCall &call, const double *u, double *t);
+
+}  // namespace x3d
