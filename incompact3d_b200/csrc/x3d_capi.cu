@@ -1,4 +1,5 @@
 // x3d_capi.cu -- extern "C" entry points declared in include/x3d_b200.h.
+#include <cstdlib>
 #include <cstring>
 #include "x3d_ctx.cuh"
 
@@ -45,6 +46,8 @@ int x3d_create(x3d_ctx **out, int device) {
     X3D_CUDA(cudaGetDeviceProperties(&prop, device));
     h->c.sm_count = prop.multiProcessorCount;
     X3D_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("X3D_STRIDED_VARIANT")) h->c.strided_variant = atoi(e);
+    if (const char *e = getenv("X3D_CONTIG_VARIANT")) h->c.contig_variant = atoi(e);
     *out = h;
   });
 }

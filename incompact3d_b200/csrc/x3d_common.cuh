@@ -87,7 +87,7 @@ int op_n_in(const OpCall &c);
 int op_n_out(const OpCall &c);
 
 // chunk length policy
-int pick_L_strided(int n);
+int pick_L_strided(int n, int variant);
 int pick_L_contig(int n);
 
 }  // namespace x3d

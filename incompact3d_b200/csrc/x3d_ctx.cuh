@@ -27,6 +27,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   long long launches = 0;
+  // kernel variants (tuning knobs; X3D_STRIDED_VARIANT / X3D_CONTIG_VARIANT override)
+  int strided_variant = 2, contig_variant = 1;
   // module state made explicit (x3d_set_deriv_coeffs / x3d_set_filter_coeffs / x3d_set_flags)
   x3d_deriv_coeffs dc[3]{};
   x3d_filter_coeffs fc[3]{};

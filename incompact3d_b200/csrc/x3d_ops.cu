@@ -28,9 +28,10 @@ bool is_device_ptr(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-int pick_L_strided(int n) {
+int pick_L_strided(int n, int variant) {
   if (n <= 128) return 8;
   if (n <= 256) return 16;
+  if (n <= 512 && variant >= 2) return 16;
   return 32;
 }
 int pick_L_contig(int n) {
@@ -75,7 +76,7 @@ static LineGeom make_geom(const OpCall &call, int n_in, int n_out) {
 void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double *d_u, double *d_t) {
   const int n_in = op.n_in, n_out = op.n_out;
   LineGeom g = make_geom(call, n_in, n_out);
-  const int L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out);
+  const int L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out, ctx.strided_variant);
   if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 1056)");
   const TriTable &T = get_tri(ctx, call.f, call.s, call.w, n_out, L, op.periodic != 0, op.alpha, call.post);
   switch (op.kind) {

@@ -59,8 +59,8 @@ __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterp
 // ===========================================================================
 // y / z lines
 // ===========================================================================
-template <int KIND, int NT, int L, int LX, int NCMAX>
-__global__ void __launch_bounds__(LX *NCMAX)
+template <int KIND, int NT, int L, int LX, int NCMAX, int MINB>
+__global__ void __launch_bounds__(LX *NCMAX, MINB)
     k_strided(const __grid_constant__ DevOp op, const double *__restrict__ u, double *__restrict__ t,
               const double *__restrict__ rows, const double *__restrict__ chunkp, int nc, int n1, long long sin,
               long long sout, long long oin, long long oout) {
@@ -167,73 +167,141 @@ __global__ void __launch_bounds__(LX *NCMAX)
 // ===========================================================================
 // x lines
 // ===========================================================================
-// shared memory layout (doubles):  coefficient columns [7][NP] | per-warp line buffers [WPB][NBUF]
-template <int KIND, int NT, int L, int WPB>
-__global__ void __launch_bounds__(32 * WPB)
+// PTX helpers: mbarrier + bulk async copy (TMA, 1-D).  SASS: UBLKCP / SYNCS.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "X3D_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra X3D_WAIT_DONE;\n"
+      "bra X3D_WAIT_LOOP;\n"
+      "X3D_WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared memory layout (doubles):
+//   coefficient columns [7][NP] | per-warp: NB line buffers [NBUF] + boundary rows [8] | mbarriers
+// Element q of a line sits at buf[HALO + q]; ghosts / padding around it stay finite.
+// TMA = true : lines are moved HBM<->shared by 1-D bulk async copies (cp.async.bulk + mbarrier),
+//              NB-deep per-warp ring, so the load of line k+1 and the store of line k-1 overlap
+//              the arithmetic of line k.  Needs n_in, n_out even (16-byte rows).
+// TMA = false: plain coalesced LDG/STG through the same buffers (any n).
+template <int KIND, int NT, int L, int WPB, int NB, int MINB, bool TMA>
+__global__ void __launch_bounds__(32 * WPB, MINB)
     k_contig(const __grid_constant__ DevOp op, const double *__restrict__ u, double *__restrict__ t,
              const double *__restrict__ rows, const double *__restrict__ scan, int nc, long long nlines, int NP,
-             int NBUF) {
+             int NBUF, int COEF) {
   constexpr int NWIN = L + 2 * HALO;
-  extern __shared__ double smem[];
-  double *coef = smem;                       // [7][NP]
+  extern __shared__ __align__(16) double smem[];
+  double *coef = smem;  // [7][NP], COEF doubles reserved (even)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *buf = smem + 7 * NP + warp * NBUF;  // [NBUF], element q at buf[HALO + q]
+  const int WSTRIDE = NB * NBUF + 8;
+  double *wbase = smem + COEF + warp * WSTRIDE;
+  double *sb = wbase + NB * NBUF;  // [8] explicit boundary rows of the current line
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + COEF + WPB * WSTRIDE) + warp * NB;
   const int n_in = op.n_in, n_out = op.n_out;
-  // stage the coefficient table (SoA so that lane-strided reads are conflict free)
   for (int idx = threadIdx.x; idx < NP * TRI_W; idx += blockDim.x) {
     const int r = idx / TRI_W, col = idx % TRI_W;
     if (col < 7) coef[col * NP + r] = __ldg(rows + idx);
   }
+  for (int q = lane; q < WSTRIDE; q += 32) wbase[q] = 0.0;
+  if (TMA && lane == 0) {
+    X3D_UNROLL
+    for (int b = 0; b < NB; ++b) mbar_init(bars + b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (TMA) fence_proxy_async();
   __syncthreads();
   const int c = lane;
   const int cl = c < nc ? c : nc - 1;  // idle lanes shadow the last chunk (results discarded)
   const int q0 = cl * L;
   const bool live = c < nc;
-  // Kogge-Stone multipliers of this lane
-  double mf[5], mb[5];
-  X3D_UNROLL
-  for (int lev = 0; lev < 5; ++lev) { mf[lev] = __ldg(scan + lev * 32 + lane); mb[lev] = __ldg(scan + (5 + lev) * 32 + lane); }
-
-  if (lane < HALO) buf[lane] = 0.0;
-  for (long long line = static_cast<long long>(blockIdx.x) * WPB + warp; line < nlines;
-       line += static_cast<long long>(gridDim.x) * WPB) {
-    const double *up = u + line * n_in;
-    double *tp = t + line * n_out;
-    // ---- coalesced load of the line into shared memory ----------------------
-    for (int q = lane; q < NBUF - 2 * HALO; q += 32) buf[HALO + q] = q < n_in ? up[q] : 0.0;
-    __syncwarp();
-    if (op.periodic && lane < 2 * HALO) {  // wrap ghosts
-      const int k = lane < HALO ? lane : lane - HALO;  // k = 0..3
-      if (lane < HALO) buf[HALO - 1 - k] = up[n_in - 1 - k]; else buf[HALO + n_in + k] = up[k];
-    }
-    __syncwarp();
-    double win[NWIN];
-    X3D_UNROLL
-    for (int j = 0; j < NWIN; ++j) win[j] = buf[q0 + j];
-    double x[L];
-    X3D_UNROLL
-    for (int m = 0; m < L; ++m) {
-      const int row = q0 + m;
-      double v = rhs_interior<KIND, NT, NWIN>(op, win, m);
-      if (op.nb) {
-        if (row < NBROW) {
-          v = 0.0;
-#pragma unroll 1
-          for (int q = 0; q < NBCOL; ++q) v += op.wstart[row][q] * buf[HALO + q];
-        } else if (row >= n_out - NBROW) {
-          v = 0.0;
-          if (row < n_out) {
-#pragma unroll 1
-            for (int q = 0; q < NBCOL; ++q) v += op.wend[row - (n_out - NBROW)][q] * buf[HALO + n_in - NBCOL + q];
-          }
+  const double *cS = coef + T_S * NP + q0, *cPF = coef + T_PF * NP + q0, *cW = coef + T_W * NP + q0,
+               *cFW = coef + T_FW * NP + q0, *cPB = coef + T_PB * NP + q0, *cRS = coef + T_RS * NP + q0,
+               *cPO = coef + T_POST * NP + q0;
+  const long long first = static_cast<long long>(blockIdx.x) * WPB + warp;
+  const long long step = static_cast<long long>(gridDim.x) * WPB;
+  const unsigned in_bytes = static_cast<unsigned>(n_in) * 8u, out_bytes = static_cast<unsigned>(n_out) * 8u;
+  if (TMA && lane == 0 && first < nlines) {
+    mbar_expect_tx(bars + 0, in_bytes);
+    bulk_g2s(wbase + HALO, u + first * n_in, in_bytes, bars + 0);
+  }
+  int it = 0;
+  for (long long line = first; line < nlines; line += step, ++it) {
+    const int b = it % NB;
+    double *buf = wbase + b * NBUF;
+    if constexpr (TMA) {
+      // prefetch the next line into the next ring slot (its previous store must have left shared memory)
+      const long long nxt = line + step;
+      if (nxt < nlines) {
+        const int bn = (it + 1) % NB;
+        if (lane == 0) {
+          bulk_wait_read<NB - 2>();
+          mbar_expect_tx(bars + bn, in_bytes);
+          bulk_g2s(wbase + bn * NBUF + HALO, u + nxt * n_in, in_bytes, bars + bn);
         }
       }
-      x[m] = (live && row < n_out) ? v : 0.0;
+      mbar_wait(bars + b, (it / NB) & 1);
+    } else {
+      const double *up = u + line * n_in;
+      for (int q = lane; q < n_in; q += 32) buf[HALO + q] = up[q];
+      __syncwarp();
+    }
+    if (op.periodic) {  // wrap ghosts
+      if (lane < HALO) buf[HALO - 1 - lane] = buf[HALO + n_in - 1 - lane];
+      else if (lane < 2 * HALO) buf[HALO + n_in + (lane - HALO)] = buf[HALO + (lane - HALO)];
+      __syncwarp();
+    } else if (op.nb) {  // explicit closure rows, one lane per row
+      if (lane < 2 * NBROW) {
+        const bool end = lane >= NBROW;
+        const double *wr = end ? op.wend[lane - NBROW] : op.wstart[lane];
+        const double *src = buf + HALO + (end ? n_in - NBCOL : 0);
+        double v = 0.0;
+        X3D_UNROLL
+        for (int q = 0; q < NBCOL; ++q) v = fma(wr[q], src[q], v);
+        sb[lane] = v;
+      }
+      __syncwarp();
+    }
+    double x[L];
+    {
+      double win[NWIN];
+      X3D_UNROLL
+      for (int j = 0; j < NWIN; ++j) win[j] = buf[q0 + j];
+      X3D_UNROLL
+      for (int m = 0; m < L; ++m) {
+        const int row = q0 + m;
+        double v = rhs_interior<KIND, NT, NWIN>(op, win, m);
+        if (op.nb) {
+          if (row < NBROW) v = sb[row];
+          else if (row >= n_out - NBROW && row < n_out) v = sb[NBROW + row - (n_out - NBROW)];
+        }
+        x[m] = (live && row < n_out) ? v : 0.0;
+      }
     }
     if (!op.rhs_only) {
-      const double *cS = coef + T_S * NP + q0, *cPF = coef + T_PF * NP + q0, *cW = coef + T_W * NP + q0,
-                   *cFW = coef + T_FW * NP + q0, *cPB = coef + T_PB * NP + q0, *cRS = coef + T_RS * NP + q0,
-                   *cPO = coef + T_POST * NP + q0;
       X3D_UNROLL
       for (int m = 1; m < L; ++m) x[m] = fma(-x[m - 1], cS[m], x[m]);
       // chunk-end values: v(c) = e(c) + Af(c) v(c-1)  -> Kogge-Stone over lanes
@@ -241,7 +309,7 @@ __global__ void __launch_bounds__(32 * WPB)
       X3D_UNROLL
       for (int lev = 0; lev < 5; ++lev) {
         const double o = __shfl_up_sync(0xffffffffu, v, 1 << lev);
-        v = fma(mf[lev], o, v);
+        v = fma(__ldg(scan + lev * 32 + lane), o, v);
       }
       double cin = __shfl_up_sync(0xffffffffu, v, 1);
       if (lane == 0) cin = 0.0;
@@ -258,7 +326,7 @@ __global__ void __launch_bounds__(32 * WPB)
       X3D_UNROLL
       for (int lev = 0; lev < 5; ++lev) {
         const double o = __shfl_down_sync(0xffffffffu, v, 1 << lev);
-        v = fma(mb[lev], o, v);
+        v = fma(__ldg(scan + (5 + lev) * 32 + lane), o, v);
       }
       double cb = __shfl_down_sync(0xffffffffu, v, 1);
       if (lane >= nc - 1) cb = 0.0;
@@ -280,16 +348,24 @@ __global__ void __launch_bounds__(32 * WPB)
         for (int m = 0; m < L; ++m) x[m] *= cPO[m];
       }
     }
-    __syncwarp();
+    __syncwarp();  // every lane has read its window
     if (live) {
       X3D_UNROLL
       for (int m = 0; m < L; ++m)
         if (q0 + m < n_out) buf[HALO + q0 + m] = x[m];
     }
-    __syncwarp();
-    for (int q = lane; q < n_out; q += 32) tp[q] = buf[HALO + q];
-    __syncwarp();
+    if constexpr (TMA) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) bulk_s2g(t + line * n_out, buf + HALO, out_bytes);
+    } else {
+      __syncwarp();
+      double *tp = t + line * n_out;
+      for (int q = lane; q < n_out; q += 32) tp[q] = buf[HALO + q];
+      __syncwarp();
+    }
   }
+  if (TMA && lane == 0) bulk_wait_read<0>();
 }
 
 }  // namespace x3d

@@ -92,4 +92,88 @@ int x3do_op(const char *name, const int *dims_in, int npaire, const double *u, d
   } catch (std::exception &e) { g_err = e.what(); return 2; }
 }
 
+
+// ---- Poisson -----------------------------------------------------------------------
+struct PoissonBox {
+  AxisScheme X, Y, Z;
+  Poisson po;
+};
+void *x3do_poisson_create(int nx, int ny, int nz, const int *ncl6, double xlx, double yly, double zlz, int ifirstder,
+                          int ipinter) {
+  try {
+    SchemeOptions o; o.ifirstder = ifirstder; o.ipinter = ipinter;
+    auto *b = new PoissonBox();
+    b->X = make_axis(nx, ncl6[0], ncl6[1], xlx, o);
+    b->Y = make_axis(ny, ncl6[2], ncl6[3], yly, o);
+    b->Z = make_axis(nz, ncl6[4], ncl6[5], zlz, o);
+    b->po.init(b->X, b->Y, b->Z, nullptr);
+    return b;
+  } catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void x3do_poisson_destroy(void *p) { delete static_cast<PoissonBox *>(p); }
+int x3do_poisson_solve(void *p, double *rhs) {
+  try { static_cast<PoissonBox *>(p)->po.solve(rhs); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// kxyz as (nx,ny,nz/2+1) complex; returns element count
+long x3do_poisson_kxyz(void *p, double *out_re_im) {
+  auto &po = static_cast<PoissonBox *>(p)->po;
+  if (out_re_im) std::memcpy(out_re_im, po.kxyz.data(), po.kxyz.size() * sizeof(cplx));
+  return static_cast<long>(po.kxyz.size());
+}
+void x3do_poisson_dims(void *p, int *d3) { auto &po = static_cast<PoissonBox *>(p)->po; d3[0] = po.nx; d3[1] = po.ny; d3[2] = po.nz; }
+
+// ---- solver ---------------------------------------------------------------------------
+void *x3do_solver_create(int nx, int ny, int nz, const int *ncl6, double xlx, double yly, double zlz, double re, double dt,
+                         int itimescheme, int ifirstder, int isecondder, int ipinter, int istret, double beta) {
+  try {
+    auto *s = new Solver();
+    s->p.nx = nx; s->p.ny = ny; s->p.nz = nz;
+    for (int a = 0; a < 3; ++a) { s->p.ncl[a][0] = ncl6[2 * a]; s->p.ncl[a][1] = ncl6[2 * a + 1]; }
+    s->p.xlx = xlx; s->p.yly = yly; s->p.zlz = zlz; s->p.re = re; s->p.dt = dt; s->p.itimescheme = itimescheme;
+    s->p.opt.ifirstder = ifirstder; s->p.opt.isecondder = isecondder; s->p.opt.ipinter = ipinter;
+    s->p.istret = istret; s->p.beta = beta;
+    s->init();
+    return s;
+  } catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void x3do_solver_destroy(void *s) { delete static_cast<Solver *>(s); }
+void x3do_solver_init_tgv(void *s) { static_cast<Solver *>(s)->init_tgv(); }
+int x3do_solver_step(void *s, int nsteps) {
+  try { for (int i = 0; i < nsteps; ++i) static_cast<Solver *>(s)->step(); return 0; }
+  catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_postprocess_tgv(void *s, double *out4) {
+  try { static_cast<Solver *>(s)->postprocess_tgv(out4); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_divergence(void *sv, double *tmax, double *tmoy) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    std::vector<double> dv(s->pp3.size());
+    s->divergence(dv.data(), 2, tmax, tmoy);
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void x3do_solver_get_velocity(void *sv, double *ux, double *uy, double *uz) {
+  auto *s = static_cast<Solver *>(sv);
+  std::memcpy(ux, s->ux.data(), s->ux.size() * 8); std::memcpy(uy, s->uy.data(), s->uy.size() * 8); std::memcpy(uz, s->uz.data(), s->uz.size() * 8);
+}
+void x3do_solver_set_velocity(void *sv, const double *ux, const double *uy, const double *uz) {
+  auto *s = static_cast<Solver *>(sv);
+  std::memcpy(s->ux.data(), ux, s->ux.size() * 8); std::memcpy(s->uy.data(), uy, s->uy.size() * 8); std::memcpy(s->uz.data(), uz, s->uz.size() * 8);
+}
+// pieces of one sub-step, for stage-by-stage parity tests
+int x3do_solver_momentum_rhs(void *sv, double *dux, double *duy, double *duz) {
+  try { static_cast<Solver *>(sv)->momentum_rhs_eq(dux, duy, duz); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_divergence_of(void *sv, double *pp3, int nlock) {
+  try { static_cast<Solver *>(sv)->divergence(pp3, nlock, nullptr, nullptr); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_gradp(void *sv, double *px, double *py, double *pz, const double *pp3) {
+  try { static_cast<Solver *>(sv)->gradp(px, py, pz, pp3); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_poisson(void *sv, double *pp3) {
+  try { static_cast<Solver *>(sv)->po.solve(pp3); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void x3do_solver_pdims(void *sv, int *d3) { auto *s = static_cast<Solver *>(sv); d3[0] = s->nxm; d3[1] = s->nym; d3[2] = s->nzm; }
+
 }  // extern "C"

@@ -1,0 +1,327 @@
+// solver.cpp -- oracle restatement of the time step on one rank (TEST INFRASTRUCTURE):
+// src/xcompact3d.f90:29-102 (loop), src/transeq.f90:73-591 (momentum_rhs_eq),
+// src/time_integrators.f90:18-187 (intt), src/navier.f90:206-499,502-789 (cor_vel, divergence,
+// gradp, pre_correc), src/Case-TGV.f90:25-107,189-380 (init_tgv, postprocess_tgv),
+// src/variables.f90:1388-1399 (RK3 coefficients), src/parameters.f90:273-304.
+#include <cmath>
+#include <stdexcept>
+#include "x3d_oracle.hpp"
+
+namespace x3do {
+
+double *Solver::W(int i, size_t n) {
+  if (static_cast<int>(work.size()) <= i) work.resize(i + 1);
+  if (work[i].size() < n) work[i].assign(n, 0.0);
+  return work[i].data();
+}
+
+namespace {
+OpDesc mk(OpKind kind, const AxisScheme &A, int npaire, const vec &f, const vec &s, const vec &w, const double *post = nullptr) {
+  OpDesc op{};
+  op.kind = kind; op.ncl1 = A.ncl1; op.ncln = A.ncln; op.periodic = A.periodic; op.npaire = npaire;
+  op.n = A.n; op.nm = A.nm; op.f = f.data(); op.s = s.data(); op.w = w.data();
+  op.c = &A.c; op.fc = &A.fc; op.post = post; op.rhs_only = false;
+  return op;
+}
+// first / second derivative with the coefficient set the call sites pair with npaire (transeq.f90:125-130,442-444)
+void der1(const AxisScheme &A, int axis, const int d[3], const double *u, double *t, int npaire, const double *post) {
+  OpDesc op = npaire == 1 ? mk(D1, A, 1, A.ffp, A.fsp, A.fwp, post) : mk(D1, A, 0, A.ff, A.fs, A.fw, post);
+  apply_op(op, axis, d, u, t);
+}
+void der2(const AxisScheme &A, int axis, const int d[3], const double *u, double *t, int npaire) {
+  OpDesc op = npaire == 1 ? mk(D2, A, 1, A.sfp, A.ssp, A.swp) : mk(D2, A, 0, A.sf, A.ss, A.sw);
+  apply_op(op, axis, d, u, t);
+}
+}  // namespace
+
+void Solver::init() {
+  X = make_axis(p.nx, p.ncl[0][0], p.ncl[0][1], p.xlx, p.opt);
+  Y = make_axis(p.ny, p.ncl[1][0], p.ncl[1][1], p.yly, p.opt);
+  Z = make_axis(p.nz, p.ncl[2][0], p.ncl[2][1], p.zlz, p.opt);
+  nxm = X.nm; nym = Y.nm; nzm = Z.nm;
+  xnu = 1.0 / p.re;  // parameters.f90:302
+  st.istret = p.istret;
+  if (p.istret != 0) {
+    st.beta = p.beta; st.yly = p.yly;
+    stretching(st, p.ny, nym, p.ncl[1][0], p.ncl[1][1], Y.periodic);
+  }
+  const double dt = p.dt;
+  if (p.itimescheme == 5) {  // variables.f90:1388-1399
+    iadvance_time = 3;
+    adt[0] = (8.0 / 15.0) * dt; bdt[0] = 0.0; gdt[0] = adt[0];
+    adt[1] = (5.0 / 12.0) * dt; bdt[1] = (-17.0 / 60.0) * dt; gdt[1] = adt[1] + bdt[1];
+    adt[2] = (3.0 / 4.0) * dt; bdt[2] = (-5.0 / 12.0) * dt; gdt[2] = adt[2] + bdt[2];
+    ntime = 2;
+  } else if (p.itimescheme == 1) {  // Euler, variables.f90:1343-1349
+    iadvance_time = 1; adt[0] = dt; bdt[0] = 0.0; gdt[0] = adt[0] + bdt[0]; ntime = 1;
+  } else {
+    throw std::runtime_error("oracle solver: itimescheme 1 (Euler) and 5 (RK3) are restated");
+  }
+  po.init(X, Y, Z, p.istret ? &st : nullptr);
+  const size_t n = static_cast<size_t>(p.nx) * p.ny * p.nz;
+  ux.assign(n, 0.0); uy.assign(n, 0.0); uz.assign(n, 0.0);
+  px.assign(n, 0.0); py.assign(n, 0.0); pz.assign(n, 0.0);
+  pp3.assign(static_cast<size_t>(nxm) * nym * nzm, 0.0);
+  for (int q = 0; q < ntime; ++q) { dux[q].assign(n, 0.0); duy[q].assign(n, 0.0); duz[q].assign(n, 0.0); }
+  itime = 0;
+}
+
+// Case-TGV.f90:58-100 (iin=1, no noise)
+void Solver::init_tgv() {
+  const double dx = X.d, dy = Y.d, dz = Z.d;
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j) {
+      const double z = static_cast<double>(k) * dz, y = static_cast<double>(j) * dy;
+      for (int i = 0; i < nx; ++i) {
+        const double x = static_cast<double>(i) * dx;
+        const size_t id = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
+        ux[id] = +std::sin(x) * std::cos(y) * std::cos(z);
+        uy[id] = -std::cos(x) * std::sin(y) * std::cos(z);
+        uz[id] = 0.0;
+      }
+    }
+}
+
+// transeq.f90:73-591, incompressible, iimplicit=0, no LES / scalar / forcing
+void Solver::momentum_rhs_eq(double *dux1, double *duy1, double *duz1) {
+  const int d[3] = {p.nx, p.ny, p.nz};
+  const size_t n = static_cast<size_t>(p.nx) * p.ny * p.nz;
+  double *ta = W(0, n), *tb = W(1, n), *tc = W(2, n), *td = W(3, n), *te = W(4, n), *tf = W(5, n);
+  double *tg1 = W(6, n), *th1 = W(7, n), *ti1 = W(8, n);
+  double *tg2 = W(9, n), *th2 = W(10, n), *ti2 = W(11, n);
+  double *tg3 = W(12, n), *th3 = W(13, n), *ti3 = W(14, n), *tj = W(15, n);
+  const double *u = ux.data(), *v = uy.data(), *w = uz.data();
+  const double *ppy = p.istret ? st.ppy.data() : nullptr;
+  const double half = 0.5;
+  // ---- x pencils, :114-146
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { ta[q] = u[q] * u[q]; tb[q] = u[q] * v[q]; tc[q] = u[q] * w[q]; }
+  der1(X, 0, d, ta, td, 1, nullptr); der1(X, 0, d, tb, te, 0, nullptr); der1(X, 0, d, tc, tf, 0, nullptr);
+  der1(X, 0, d, u, ta, 0, nullptr); der1(X, 0, d, v, tb, 1, nullptr); der1(X, 0, d, w, tc, 1, nullptr);
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { tg1[q] = td[q] + u[q] * ta[q]; th1[q] = te[q] + u[q] * tb[q]; ti1[q] = tf[q] + u[q] * tc[q]; }
+  // ---- y pencils, :188-219
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { td[q] = u[q] * v[q]; te[q] = v[q] * v[q]; tf[q] = w[q] * v[q]; }
+  der1(Y, 1, d, td, tg2, 0, ppy); der1(Y, 1, d, te, th2, 1, ppy); der1(Y, 1, d, tf, ti2, 0, ppy);
+  der1(Y, 1, d, u, td, 1, ppy); der1(Y, 1, d, v, te, 0, ppy); der1(Y, 1, d, w, tf, 1, ppy);
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { tg2[q] = tg2[q] + v[q] * td[q]; th2[q] = th2[q] + v[q] * te[q]; ti2[q] = ti2[q] + v[q] * tf[q]; }
+  // ---- z pencils, :249-314
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { td[q] = u[q] * w[q]; te[q] = v[q] * w[q]; tf[q] = w[q] * w[q]; }
+  der1(Z, 2, d, td, tg3, 0, nullptr); der1(Z, 2, d, te, th3, 0, nullptr); der1(Z, 2, d, tf, ti3, 1, nullptr);
+  der1(Z, 2, d, u, td, 1, nullptr); der1(Z, 2, d, v, te, 1, nullptr); der1(Z, 2, d, w, tf, 0, nullptr);
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { td[q] = tg3[q] + w[q] * td[q]; te[q] = th3[q] + w[q] * te[q]; tf[q] = ti3[q] + w[q] * tf[q]; }
+  der2(Z, 2, d, u, ta, 1); der2(Z, 2, d, v, tb, 1); der2(Z, 2, d, w, tc, 0);
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) {
+    td[q] = xnu * ta[q] - half * td[q]; te[q] = xnu * tb[q] - half * te[q]; tf[q] = xnu * tc[q] - half * tf[q];
+    // back in y pencils, :323-325
+    tg2[q] = td[q] - half * tg2[q]; th2[q] = te[q] - half * th2[q]; ti2[q] = tf[q] - half * ti2[q];
+  }
+  // ---- diffusive terms in y, :336-372
+  der2(Y, 1, d, u, td, 1); der2(Y, 1, d, v, te, 0); der2(Y, 1, d, w, tf, 1);
+  if (p.istret != 0) {
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    der1(Y, 1, d, u, tj, 1, ppy);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
+      td[q] = td[q] * st.pp2y[j] - st.pp4y[j] * tj[q];
+    }
+    der1(Y, 1, d, v, tj, 0, ppy);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
+      te[q] = te[q] * st.pp2y[j] - st.pp4y[j] * tj[q];
+    }
+    der1(Y, 1, d, w, tj, 1, ppy);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
+      tf[q] = tf[q] * st.pp2y[j] - st.pp4y[j] * tj[q];
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { ta[q] = xnu * td[q] + tg2[q]; tb[q] = xnu * te[q] + th2[q]; tc[q] = xnu * tf[q] + ti2[q]; }  // :431-433
+  // ---- diffusive terms in x and final sum, :442-470
+  der2(X, 0, d, u, td, 0); der2(X, 0, d, v, te, 1); der2(X, 0, d, w, tf, 1);
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) {
+    td[q] = xnu * td[q]; te[q] = xnu * te[q]; tf[q] = xnu * tf[q];
+    dux1[q] = ta[q] - half * tg1[q] + td[q];
+    duy1[q] = tb[q] - half * th1[q] + te[q];
+    duz1[q] = tc[q] - half * ti1[q] + tf[q];
+  }
+}
+
+// time_integrators.f90:71-74 (Euler), :151-157 (RK3)
+void Solver::intt(std::vector<double> &var, std::vector<double> *dvar) {
+  const size_t n = var.size();
+  double *v = var.data();
+  const double *d1 = dvar[0].data();
+  if (p.itimescheme == 1) {
+    const double g = gdt[itr - 1];
+#pragma omp parallel for schedule(static)
+    for (size_t q = 0; q < n; ++q) v[q] = g * d1[q] + v[q];
+    return;
+  }
+  double *d2 = dvar[1].data();
+  if (itr == 1) {
+    const double g = gdt[0];
+#pragma omp parallel for schedule(static)
+    for (size_t q = 0; q < n; ++q) { v[q] = g * d1[q] + v[q]; d2[q] = d1[q]; }
+  } else {
+    const double a = adt[itr - 1], b = bdt[itr - 1];
+#pragma omp parallel for schedule(static)
+    for (size_t q = 0; q < n; ++q) { v[q] = a * d1[q] + b * d2[q] + v[q]; d2[q] = d1[q]; }
+  }
+}
+
+// navier.f90:502-789 -- only the free-slip (ncl=1) planes matter for the restated cases; Dirichlet
+// planes of TGV-type boxes would need the case's b?? arrays (Channel/Cylinder glue)
+void Solver::pre_correc() {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  auto id = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
+  for (int a = 0; a < 3; ++a)
+    for (int e = 0; e < 2; ++e)
+      if (p.ncl[a][e] == 2) throw std::runtime_error("oracle pre_correc: Dirichlet planes need case boundary data");
+  if (p.ncl[0][0] == 1) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) ux[id(0, j, k)] = 0.0;        // :600-606
+  if (p.ncl[0][1] == 1) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) ux[id(nx - 1, j, k)] = 0.0;   // :607-613
+  if (p.ncl[1][0] == 1) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) uy[id(i, 0, k)] = 0.0;        // :693-701
+  if (p.ncl[1][1] == 1) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) uy[id(i, ny - 1, k)] = 0.0;   // :703-711
+  if (p.ncl[2][0] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, 0)] = 0.0;        // :751-759
+  if (p.ncl[2][1] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, nz - 1)] = 0.0;   // :761-769
+}
+
+// navier.f90:257-372
+void Solver::divergence(double *pp3out, int nlock, double *tmax_out, double *tmoy_out) {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  const size_t n1 = static_cast<size_t>(nxm) * ny * nz, n2 = static_cast<size_t>(nxm) * nym * nz;
+  const size_t n3 = static_cast<size_t>(nxm) * nym * nzm;
+  double *pp1 = W(20, n1), *pgy1 = W(21, n1), *pgz1 = W(22, n1);
+  double *upi2 = W(23, n2), *duydypi2 = W(24, n2), *po3 = W(25, n3);
+  const int dx1[3] = {nx, ny, nz};
+  apply_op(mk(DVP, X, 0, X.cfx6, X.csx6, X.cwx6), 0, dx1, ux.data(), pp1);        // :297
+  apply_op(mk(IVP, X, 1, X.cifxp6, X.cisxp6, X.ciwxp6), 0, dx1, uy.data(), pgy1);  // :313
+  apply_op(mk(IVP, X, 1, X.cifxp6, X.cisxp6, X.ciwxp6), 0, dx1, uz.data(), pgz1);  // :314
+  const int dy2[3] = {nxm, ny, nz};
+  const double *ppyi = p.istret ? st.ppyi.data() : nullptr;
+  apply_op(mk(IVP, Y, 1, Y.cifxp6, Y.cisxp6, Y.ciwxp6), 1, dy2, pp1, upi2);           // :321
+  apply_op(mk(DVP, Y, 0, Y.cfx6, Y.csx6, Y.cwx6, ppyi), 1, dy2, pgy1, duydypi2);       // :322
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n2; ++q) duydypi2[q] = duydypi2[q] + upi2[q];                 // :325
+  apply_op(mk(IVP, Y, 1, Y.cifxp6, Y.cisxp6, Y.ciwxp6), 1, dy2, pgz1, upi2);           // :327
+  const int dz3[3] = {nxm, nym, nz};
+  apply_op(mk(IVP, Z, 1, Z.cifxp6, Z.cisxp6, Z.ciwxp6), 2, dz3, duydypi2, pp3out);     // :333
+  apply_op(mk(DVP, Z, 0, Z.cfx6, Z.csx6, Z.cwx6), 2, dz3, upi2, po3);                  // :335
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n3; ++q) pp3out[q] = pp3out[q] + po3[q];                      // :339
+  if (nlock == 2) {                                                                     // :341-347
+    const double pres_ref = pp3out[static_cast<size_t>(nxm) * nym * (nzm - 1)];
+    for (size_t q = 0; q < n3; ++q) pp3out[q] = pp3out[q] - pres_ref;
+  }
+  double tmax = -1609.0, tmoy = 0.0;                                                    // :349-359
+  for (size_t q = 0; q < n3; ++q) { if (pp3out[q] > tmax) tmax = pp3out[q]; tmoy += std::fabs(pp3out[q]); }
+  tmoy = tmoy / static_cast<double>(n3);
+  if (tmax_out) *tmax_out = tmax;
+  if (tmoy_out) *tmoy_out = tmoy;
+}
+
+// navier.f90:386-431
+void Solver::gradp(double *px1, double *py1, double *pz1, const double *pp3in) {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  const size_t n3 = static_cast<size_t>(nxm) * nym * nz, n2 = static_cast<size_t>(nxm) * ny * nz;
+  double *ppi3 = W(30, n3), *pgz3 = W(31, n3), *ppi2 = W(32, n2), *pgy2 = W(33, n2), *pgzi2 = W(34, n2);
+  auto pv = [&](OpKind k, const AxisScheme &A, const double *post) {
+    const bool inter = (k == IPV);
+    if (A.periodic) return inter ? mk(k, A, 1, A.cifx6, A.cisx6, A.ciwx6, post) : mk(k, A, 1, A.cfx6, A.csx6, A.cwx6, post);
+    return inter ? mk(k, A, 1, A.cifip6, A.cisip6, A.ciwip6, post) : mk(k, A, 1, A.cfip6, A.csip6, A.cwip6, post);
+  };
+  const int dz[3] = {nxm, nym, nzm};
+  apply_op(pv(IPV, Z, nullptr), 2, dz, pp3in, ppi3);  // :404
+  apply_op(pv(DPV, Z, nullptr), 2, dz, pp3in, pgz3);  // :406
+  const int dy[3] = {nxm, nym, nz};
+  const double *ppy = p.istret ? st.ppy.data() : nullptr;
+  apply_op(pv(IPV, Y, nullptr), 1, dy, ppi3, ppi2);   // :413
+  apply_op(pv(DPV, Y, ppy), 1, dy, ppi3, pgy2);       // :415
+  apply_op(pv(IPV, Y, nullptr), 1, dy, pgz3, pgzi2);  // :417
+  const int dxx[3] = {nxm, ny, nz};
+  apply_op(pv(DPV, X, nullptr), 0, dxx, ppi2, px1);   // :426
+  apply_op(pv(IPV, X, nullptr), 0, dxx, pgy2, py1);   // :428
+  apply_op(pv(IPV, X, nullptr), 0, dxx, pgzi2, pz1);  // :430
+}
+
+// navier.f90:242-244
+void Solver::cor_vel() {
+  const size_t n = ux.size();
+#pragma omp parallel for schedule(static)
+  for (size_t q = 0; q < n; ++q) { ux[q] = ux[q] - px[q]; uy[q] = uy[q] - py[q]; uz[q] = uz[q] - pz[q]; }
+}
+
+// xcompact3d.f90:29-102
+void Solver::step() {
+  itime += 1;
+  for (itr = 1; itr <= iadvance_time; ++itr) {
+    momentum_rhs_eq(dux[0].data(), duy[0].data(), duz[0].data());
+    intt(ux, dux); intt(uy, duy); intt(uz, duz);
+    pre_correc();
+    divergence(pp3.data(), 1, nullptr, nullptr);  // solve_poisson, navier.f90:76
+    po.solve(pp3.data());                          // :99
+    gradp(px.data(), py.data(), pz.data(), pp3.data());  // :107
+    cor_vel();
+  }
+}
+
+// Case-TGV.f90:189-380
+void Solver::postprocess_tgv(double out[4]) {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  const int d[3] = {nx, ny, nz};
+  const size_t n = static_cast<size_t>(nx) * ny * nz;
+  const int xs1 = (p.ncl[0][0] == 1) ? nx - 1 : nx, xs2 = (p.ncl[1][0] == 1) ? ny - 1 : ny, xs3 = (p.ncl[2][0] == 1) ? nz - 1 : nz;
+  const int nxc = (p.ncl[0][0] == 1) ? nxm : nx, nyc = (p.ncl[1][0] == 1) ? nym : ny, nzc = (p.ncl[2][0] == 1) ? nzm : nz;
+  double *ta1 = W(40, n), *tb1 = W(41, n), *tc1 = W(42, n), *td1 = W(43, n), *te1 = W(44, n), *tf1 = W(45, n);
+  double *tg1 = W(46, n), *th1 = W(47, n), *ti1 = W(48, n);
+  const double *u = ux.data(), *v = uy.data(), *w = uz.data();
+  const double *ppy = p.istret ? st.ppy.data() : nullptr;
+  der1(X, 0, d, u, ta1, 0, nullptr); der1(X, 0, d, v, tb1, 1, nullptr); der1(X, 0, d, w, tc1, 1, nullptr);  // :261-263
+  der1(Y, 1, d, u, td1, 1, ppy); der1(Y, 1, d, v, te1, 0, ppy); der1(Y, 1, d, w, tf1, 1, ppy);              // :265-267
+  der1(Z, 2, d, u, tg1, 1, nullptr); der1(Z, 2, d, v, th1, 1, nullptr); der1(Z, 2, d, w, ti1, 0, nullptr);  // :269-271
+  double enst = 0.0, eps = 0.0, eek = 0.0, eps2 = 0.0;
+  auto ID = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
+  // the reference accumulates serially in (k,j,i) order (:287-296); keep that order
+  for (int k = 0; k < xs3; ++k) for (int j = 0; j < xs2; ++j) for (int i = 0; i < xs1; ++i) {
+    const size_t q = ID(i, j, k);
+    const double a = tf1[q] - th1[q], b = tg1[q] - tc1[q], c = tb1[q] - td1[q];
+    enst = enst + 0.5 * (a * a + b * b + c * c);
+  }
+  enst = enst / (static_cast<double>(nxc) * nyc * nzc);
+  for (int k = 0; k < xs3; ++k) for (int j = 0; j < xs2; ++j) for (int i = 0; i < xs1; ++i) {
+    const size_t q = ID(i, j, k);
+    auto sq = [](double x) { return x * x; };
+    eps = eps + 0.5 * xnu * (sq(2.0 * ta1[q]) + sq(2.0 * te1[q]) + sq(2.0 * ti1[q]) + 2.0 * sq(td1[q] + tb1[q]) +
+                             2.0 * sq(tg1[q] + tc1[q]) + 2.0 * sq(th1[q] + tf1[q]));
+  }
+  eps = eps / (static_cast<double>(nxc) * nyc * nzc);
+  for (int k = 0; k < xs3; ++k) for (int j = 0; j < xs2; ++j) for (int i = 0; i < xs1; ++i) {
+    const size_t q = ID(i, j, k);
+    eek = eek + 0.5 * (u[q] * u[q] + v[q] * v[q] + w[q] * w[q]);
+  }
+  eek = eek / (static_cast<double>(nxc) * nyc * nzc);
+  der2(X, 0, d, u, ta1, 0); der2(X, 0, d, v, tb1, 1); der2(X, 0, d, w, tc1, 1);  // :332-334
+  der2(Y, 1, d, u, td1, 1); der2(Y, 1, d, v, te1, 0); der2(Y, 1, d, w, tf1, 1);  // :336-338
+  der2(Z, 2, d, u, tg1, 1); der2(Z, 2, d, v, th1, 1); der2(Z, 2, d, w, ti1, 0);  // :340-342
+  for (int k = 0; k < xs3; ++k) for (int j = 0; j < xs2; ++j) for (int i = 0; i < xs1; ++i) {
+    const size_t q = ID(i, j, k);
+    const double di = (-xnu) * (u[q] * (ta1[q] + td1[q] + tg1[q]) + v[q] * (tb1[q] + te1[q] + th1[q]) + w[q] * (tc1[q] + tf1[q] + ti1[q]));
+    eps2 = eps2 + di;
+  }
+  eps2 = eps2 / (static_cast<double>(nxc) * nyc * nzc);
+  out[0] = eek; out[1] = eps; out[2] = eps2; out[3] = enst;
+}
+
+}  // namespace x3do

@@ -65,7 +65,7 @@ def product_op(x3d, name, u, A, npaire, post=None, t=None):
     fam, ax, bc = parse(name)
     axis = "xyz".index(ax)
     lu = lu_arrays(A, fam, npaire)
-    shape = list(u.shape)
+    shape = list(u.shape) if isinstance(u, np.ndarray) else list(reversed(u.shape))
     n, nm = A.n, A.nm
     if fam in ("dvp", "ivp"):
         shape[axis] = nm

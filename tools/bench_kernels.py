@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--ops", default="derx_00,dery_00,derz_00,derxx_00,deryy_00,derzz_00,"
                     "interxvp,deryvp,derzpv,derx_11,dery_11,derz_11")
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     from incompact3d_b200 import X3D
@@ -58,7 +59,7 @@ def main():
             if fam in ("dpv", "ipv") and not A.periodic:
                 continue
             npaire = 1 if fam != "dvp" else 0
-            for _ in range(3):
+            for _ in range(args.warmup):
                 H.product_op(x3d, name, uin, A, npaire, t=t)
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
