@@ -254,6 +254,14 @@ int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5);
 /* DIV U max / mean of the current velocity (divergence nlock=2)             */
 int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean);
 
+/* ---- schemes() for hosts that are not the reference's Fortran (src/schemes.f90:443-1066) ------
+ * CPU-only helper: stencil scalars of one direction and one prepared LU triple.
+ * which: 0 ff,fs,fw | 1 ffp.. | 2 sf,ss,sw | 3 sfp.. | 4 cfx6.. | 5 cfxp6.. | 6 cifx6.. | 7 cifxp6.. |
+ *        8 cfi6.. | 9 cfip6.. | 10 cifi6.. | 11 cifip6..   (arrays 4-7 have nm entries, the others n) */
+int x3d_schemes_axis(int n, int ncl1, int ncln, double len, int ifirstder, int isecondder, int ipinter,
+                     double nu0nu, double cnu, x3d_deriv_coeffs *coeffs, int which, double *f, double *s,
+                     double *w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,8 +87,11 @@ def symbols_declared_in_header():
     hdr = os.path.join(HERE, "..", "include", "x3d_b200.h")
     txt = open(hdr).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    stems = re.findall(r"X3D_DECL_DER[XY]\((\w+)\)", txt)
+    txt = re.sub(r"#define[^\n]*(\\\n[^\n]*)*", "", txt)  # drop macro bodies
     names = set(re.findall(r"\b(x3d_[a-z0-9_]+)\s*\(", txt))
-    for stem in re.findall(r"X3D_DECL_DER[XY]\((\w+)\)", txt):
-        names.add("x3d_" + stem)
+    for stem in stems:
+        if stem != "name":
+            names.add("x3d_" + stem)
     names.discard("x3d_")
     return sorted(n for n in names if not n.endswith("_"))

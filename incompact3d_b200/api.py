@@ -93,6 +93,8 @@ class X3D:
 
     # -- module state -------------------------------------------------------------
     def set_deriv_coeffs(self, axis: int, c: DerivCoeffs):
+        if not isinstance(c, DerivCoeffs):
+            raise TypeError("set_deriv_coeffs expects incompact3d_b200.DerivCoeffs")
         self._check(self._L.x3d_set_deriv_coeffs(self._h, axis, C.byref(c)))
 
     def set_filter_coeffs(self, axis: int, c: FilterCoeffs):
@@ -153,3 +155,172 @@ for _n, _k, _pp in (("derxvp", 3, False), ("interxvp", 3, False), ("derxpv", 6, 
                     ("interyvp", 3, False), ("deryvp", 3, True), ("interypv", 6, False), ("derypv", 6, True),
                     ("derzvp", 3, False), ("interzvp", 3, False), ("derzpv", 6, False), ("interzpv", 6, False)):
     setattr(X3D, _n, _make_stag(_n, _k, _pp))
+
+
+# ---------------------------------------------------------------------------------------
+# schemes() for Python hosts, Poisson solver, decomposition, device-resident solver
+# ---------------------------------------------------------------------------------------
+_LU_NAMES = {"d1": 0, "d1p": 1, "d2": 2, "d2p": 3, "vp": 4, "vpp": 5, "ivp": 6, "ivpp": 7,
+             "pv": 8, "pvp": 9, "ipv": 10, "ipvp": 11}
+
+
+class AxisSchemes:
+    """Coefficients of one direction as `schemes()` builds them (src/schemes.f90): `c` holds the
+    derivX/Y/Z scalars, `lu(name)` the prepared (f, s, w) arrays:
+    d1/d1p = ffx../ffxp.., d2/d2p = sfx../sfxp.., vp/vpp = cfx6../cfxp6.., ivp/ivpp = cifx6../cifxp6..,
+    pv/pvp = cfi6../cfip6.., ipv/ipvp = cifi6../cifip6.. .  Host-side, CPU only."""
+
+    def __init__(self, n, ncl1, ncln, length, ifirstder=4, isecondder=4, ipinter=3, nu0nu=4.0, cnu=0.44):
+        self._L = _lib.load()
+        self.n, self.ncl1, self.ncln, self.length = int(n), int(ncl1), int(ncln), float(length)
+        self.periodic = ncl1 == 0 and ncln == 0
+        self.nm = self.n if self.periodic else self.n - 1
+        self.d = self.length / self.nm
+        self._opts = (int(ifirstder), int(isecondder), int(ipinter), float(nu0nu), float(cnu))
+        self.c = DerivCoeffs()
+        self._cache = {}
+        self.lu("d1")
+
+    def lu(self, name):
+        if name not in self._cache:
+            which = _LU_NAMES[name]
+            m = self.nm if 4 <= which <= 7 else self.n
+            f, s, w = (np.zeros(m) for _ in range(3))
+            fn = self._L.x3d_schemes_axis
+            fn.restype = C.c_int
+            rc = fn(C.c_int(self.n), C.c_int(self.ncl1), C.c_int(self.ncln), C.c_double(self.length),
+                    C.c_int(self._opts[0]), C.c_int(self._opts[1]), C.c_int(self._opts[2]),
+                    C.c_double(self._opts[3]), C.c_double(self._opts[4]), C.byref(self.c), C.c_int(which),
+                    C.c_void_p(f.ctypes.data), C.c_void_p(s.ctypes.data), C.c_void_p(w.ctypes.data))
+            if rc:
+                raise X3DError(self._L.x3d_last_error().decode())
+            self._cache[name] = (f, s, w)
+        return self._cache[name]
+
+
+def _poisson_init(self, nx, ny, nz, bcx, bcy, bcz, xlx, yly, zlz, istret=0, alpha=0.0, beta=0.0):
+    """decomp_2d_poisson_init (src/poisson.f90:73); nx,ny,nz are the velocity-mesh node counts"""
+    p = _lib.PoissonParams(int(nx), int(ny), int(nz), int(bcx), int(bcy), int(bcz), float(xlx), float(yly), float(zlz),
+                           int(istret), float(alpha), float(beta))
+    fn = self._L.x3d_poisson_init
+    fn.argtypes = [C.c_void_p, C.POINTER(_lib.PoissonParams)]
+    self._check(fn(self._h, C.byref(p)))
+
+
+def _poisson(self, rhs):
+    """`poisson(rhs)` (src/poisson.f90:63): rhs is the z-pencil of the pressure mesh, solved in place"""
+    keep = []
+    fn = self._L.x3d_poisson
+    fn.argtypes = [C.c_void_p, C.c_void_p]
+    self._check(fn(self._h, _addr(rhs, keep)))
+
+
+def _decomp_init(self, nx, ny, nz, p_row=1, p_col=1, rank=0, nranks=1, nccl_id=None):
+    fn = self._L.x3d_decomp_init
+    fn.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+    buf = None if nccl_id is None else C.create_string_buffer(bytes(nccl_id), 128)
+    self._check(fn(self._h, nx, ny, nz, p_row, p_col, rank, nranks, buf))
+
+
+def _decomp_info_init(self, nx, ny, nz):
+    out = C.c_int()
+    fn = self._L.x3d_decomp_info_init
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    self._check(fn(self._h, nx, ny, nz, C.byref(out)))
+    return out.value
+
+
+def _decomp_info(self, decomp_id=0):
+    info = _lib.DecompInfo()
+    fn = self._L.x3d_decomp_info_get
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(_lib.DecompInfo)]
+    self._check(fn(self._h, decomp_id, C.byref(info)))
+    return {k: list(getattr(info, k)) for k, _ in _lib.DecompInfo._fields_}
+
+
+def _make_transpose(name):
+    def f(self, src, dst, decomp_id=0):
+        keep = []
+        cplx = isinstance(src, np.ndarray) and src.dtype == np.complex128
+        if hasattr(src, "is_complex") and src.is_complex():
+            cplx = True
+        fn = getattr(self._L, "x3d_" + name + ("_complex" if cplx else ""))
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self._check(fn(self._h, _addr(src, keep), _addr(dst, keep), int(decomp_id)))
+    f.__name__ = name
+    f.__doc__ = f"2DECOMP&FFT `{name}(src, dst[, decomp])`; real or complex arrays"
+    return f
+
+
+def _solver_init(self, nx, ny, nz, ncl=(0, 0, 0, 0, 0, 0), xlx=2 * np.pi, yly=2 * np.pi, zlz=2 * np.pi, re=1600.0,
+                 dt=0.005, ifirstder=4, isecondder=4, ipinter=3, itimescheme=5, istret=0, beta=0.0, nu0nu=4.0,
+                 cnu=0.44, p_row=1, p_col=1):
+    p = _lib.SolverParams(int(nx), int(ny), int(nz), *[int(v) for v in ncl], float(xlx), float(yly), float(zlz),
+                          float(re), float(dt), int(ifirstder), int(isecondder), int(ipinter), int(itimescheme),
+                          int(istret), float(beta), float(nu0nu), float(cnu), int(p_row), int(p_col))
+    fn = self._L.x3d_solver_init
+    fn.argtypes = [C.c_void_p, C.POINTER(_lib.SolverParams)]
+    self._check(fn(self._h, C.byref(p)))
+    self._solver_shape = (int(nx), int(ny), int(nz))
+
+
+def _solver_init_tgv(self):
+    fn = self._L.x3d_solver_init_tgv
+    fn.argtypes = [C.c_void_p]
+    self._check(fn(self._h))
+
+
+def _solver_step(self, nsteps=1):
+    fn = self._L.x3d_solver_step
+    fn.argtypes = [C.c_void_p, C.c_int]
+    self._check(fn(self._h, int(nsteps)))
+
+
+def _solver_diag(self):
+    """-> dict(eek, eps, eps2, enst, divmax) as postprocess_tgv / divergence(nlock=2) report them"""
+    out = (C.c_double * 5)()
+    fn = self._L.x3d_solver_diagnostics_tgv
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    self._check(fn(self._h, out))
+    return dict(eek=out[0], eps=out[1], eps2=out[2], enst=out[3], divmax=out[4])
+
+
+def _solver_divergence(self):
+    a, b = C.c_double(), C.c_double()
+    fn = self._L.x3d_solver_divergence
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    self._check(fn(self._h, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _solver_set_velocity(self, ux, uy, uz):
+    keep = []
+    fn = self._L.x3d_solver_set_velocity
+    fn.argtypes = [C.c_void_p] * 4
+    self._check(fn(self._h, _addr(ux, keep), _addr(uy, keep), _addr(uz, keep)))
+
+
+def _solver_get_velocity(self, ux=None, uy=None, uz=None):
+    if ux is None:
+        ux, uy, uz = (np.zeros(self._solver_shape, order="F") for _ in range(3))
+    keep = []
+    fn = self._L.x3d_solver_get_velocity
+    fn.argtypes = [C.c_void_p] * 4
+    self._check(fn(self._h, _addr(ux, keep), _addr(uy, keep), _addr(uz, keep)))
+    return ux, uy, uz
+
+
+X3D.poisson_init = _poisson_init
+X3D.poisson = _poisson
+X3D.decomp_init = _decomp_init
+X3D.decomp_info_init = _decomp_info_init
+X3D.decomp_info = _decomp_info
+for _n in ("transpose_x_to_y", "transpose_y_to_z", "transpose_z_to_y", "transpose_y_to_x"):
+    setattr(X3D, _n, _make_transpose(_n))
+X3D.solver_init = _solver_init
+X3D.solver_init_tgv = _solver_init_tgv
+X3D.solver_step = _solver_step
+X3D.solver_diagnostics_tgv = _solver_diag
+X3D.solver_divergence = _solver_divergence
+X3D.solver_set_velocity = _solver_set_velocity
+X3D.solver_get_velocity = _solver_get_velocity

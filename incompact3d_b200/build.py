@@ -20,7 +20,7 @@ NVCC = os.environ.get("X3D_NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = os.environ.get("X3D_CXX", "/usr/bin/g++")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOSTCXX,
-          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+          "-Xptxas", "-v", "--expt-relaxed-constexpr", "--extended-lambda"]
 
 
 def _newer(src, obj, deps):

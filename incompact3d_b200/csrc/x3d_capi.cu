@@ -3,7 +3,26 @@
 #include <cstring>
 #include "x3d_ctx.cuh"
 
+#include "x3d_schemes.cuh"
+
 using namespace x3d;
+
+namespace x3d {
+void poisson_init(Ctx &ctx, const x3d_poisson_params &p);
+void poisson_solve_device(Ctx &ctx, double *d_rhs);
+void poisson_dims(Ctx &ctx, int d[3]);
+void solver_init(Ctx &ctx, const x3d_solver_params &p);
+void solver_init_tgv(Ctx &ctx);
+void solver_step(Ctx &ctx, int nsteps);
+void solver_diagnostics_tgv(Ctx &ctx, double *out5);
+void solver_divergence(Ctx &ctx, double *divmax, double *divmean);
+void solver_set_velocity(Ctx &ctx, const double *ux, const double *uy, const double *uz);
+void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz);
+void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id);
+int decomp_info_init(Ctx &ctx, int nx, int ny, int nz);
+void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out);
+void transpose(Ctx &ctx, int which, const double *src, double *dst, int id, int elem);
+}
 
 struct x3d_ctx {
   Ctx c;
@@ -226,6 +245,87 @@ int x3d_interzpv(x3d_ctx *ctx, double *tz, const double *uz, double *, double *,
   const bool per = ctx && ctx->c.ncl[2];
   return stag(ctx, IPV, 2, tz, uz, per ? cifz6 : cifiz6, per ? cisz6 : cisiz6, per ? ciwz6 : ciwiz6, nullptr, *nx, *ny,
               *nzm, *nz, *nzm, *npaire);
+}
+
+
+// ---- decomposition / transposes ----------------------------------------------------------
+int x3d_decomp_init(x3d_ctx *ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *id) {
+  return guard([&] { decomp_init(ctx->c, nx, ny, nz, p_row, p_col, rank, nranks, id); });
+}
+int x3d_nccl_unique_id(void *out128) {
+  return guard([&] { (void)out128; throw Error("x3d_nccl_unique_id: NCCL path not wired yet"); });
+}
+int x3d_decomp_info_init(x3d_ctx *ctx, int nx, int ny, int nz, int *decomp_id) {
+  return guard([&] { *decomp_id = decomp_info_init(ctx->c, nx, ny, nz); });
+}
+int x3d_decomp_info_get(x3d_ctx *ctx, int decomp_id, x3d_decomp_info *out) {
+  return guard([&] { decomp_info_get(ctx->c, decomp_id, out); });
+}
+#define X3D_DEF_TR(name, which)                                                                            \
+  int x3d_transpose_##name(x3d_ctx *ctx, const double *src, double *dst, int id) {                         \
+    return guard([&] { transpose(ctx->c, which, src, dst, id, 1); });                                      \
+  }                                                                                                        \
+  int x3d_transpose_##name##_complex(x3d_ctx *ctx, const double *src, double *dst, int id) {               \
+    return guard([&] { transpose(ctx->c, which, src, dst, id, 2); });                                      \
+  }
+X3D_DEF_TR(x_to_y, 0)
+X3D_DEF_TR(y_to_z, 1)
+X3D_DEF_TR(z_to_y, 2)
+X3D_DEF_TR(y_to_x, 3)
+
+// ---- Poisson ---------------------------------------------------------------------------------
+int x3d_poisson_init(x3d_ctx *ctx, const x3d_poisson_params *p) {
+  return guard([&] { if (!p) throw Error("null params"); poisson_init(ctx->c, *p); });
+}
+int x3d_poisson(x3d_ctx *ctx, double *rhs) {
+  return guard([&] {
+    Ctx &c = ctx->c;
+    X3D_CUDA(cudaSetDevice(c.device));
+    if (is_device_ptr(rhs)) { poisson_solve_device(c, rhs); return; }
+    int d[3];
+    poisson_dims(c, d);
+    const size_t bytes = static_cast<size_t>(d[0]) * d[1] * d[2] * sizeof(double);
+    c.stage_in.reserve(bytes);
+    X3D_CUDA(cudaMemcpyAsync(c.stage_in.p, rhs, bytes, cudaMemcpyHostToDevice, c.stream));
+    poisson_solve_device(c, static_cast<double *>(c.stage_in.p));
+    X3D_CUDA(cudaMemcpyAsync(rhs, c.stage_in.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+    X3D_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// ---- device-resident solver -----------------------------------------------------------------------
+int x3d_solver_init(x3d_ctx *ctx, const x3d_solver_params *p) {
+  return guard([&] { if (!p) throw Error("null params"); solver_init(ctx->c, *p); });
+}
+int x3d_solver_init_tgv(x3d_ctx *ctx) { return guard([&] { solver_init_tgv(ctx->c); }); }
+int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, const double *uz) {
+  return guard([&] { solver_set_velocity(ctx->c, ux, uy, uz); });
+}
+int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz) {
+  return guard([&] { solver_get_velocity(ctx->c, ux, uy, uz); });
+}
+int x3d_solver_step(x3d_ctx *ctx, int nsteps) { return guard([&] { solver_step(ctx->c, nsteps); }); }
+int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5) { return guard([&] { solver_diagnostics_tgv(ctx->c, out5); }); }
+int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean) {
+  return guard([&] { solver_divergence(ctx->c, divmax, divmean); });
+}
+
+// ---- schemes() for non-Fortran hosts (src/schemes.f90); CPU only, no context needed -----------------
+// which: 0 first derivative (ff,fs,fw), 1 its p-variant, 2 second derivative, 3 p-variant, 4 cfx6.., 5 cfxp6..,
+//        6 cifx6.., 7 cifxp6.., 8 cfi6.., 9 cfip6.., 10 cifi6.., 11 cifip6..
+int x3d_schemes_axis(int n, int ncl1, int ncln, double len, int ifirstder, int isecondder, int ipinter, double nu0nu,
+                     double cnu, x3d_deriv_coeffs *coeffs, int which, double *f, double *s, double *w) {
+  return guard([&] {
+    SchemeOpts o; o.ifirstder = ifirstder; o.isecondder = isecondder; o.ipinter = ipinter; o.nu0nu = nu0nu; o.cnu = cnu;
+    AxisCoeffs A = make_axis_coeffs(n, ncl1, ncln, len, o);
+    if (coeffs) *coeffs = A.c;
+    const LU3 *t[12] = {&A.d1, &A.d1p, &A.d2, &A.d2p, &A.vp, &A.vpp, &A.ivp, &A.ivpp, &A.pv, &A.pvp, &A.ipv, &A.ipvp};
+    if (which < 0 || which > 11) throw Error("x3d_schemes_axis: bad selector");
+    const LU3 &L = *t[which];
+    if (f) std::copy(L.f.begin(), L.f.end(), f);
+    if (s) std::copy(L.s.begin(), L.s.end(), s);
+    if (w) std::copy(L.w.begin(), L.w.end(), w);
+  });
 }
 
 }  // extern "C"

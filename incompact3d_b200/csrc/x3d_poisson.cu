@@ -1,0 +1,383 @@
+// x3d_poisson.cu -- spectral Poisson solver (src/poisson.f90) on one GPU.
+//
+//   rhs (z-pencil, pressure mesh)  ->  [even/odd reorder of every non-periodic axis, one gather]
+//   -> 1-D r2c FFTs along z (stride nx*ny) -> c2c along y and x            (decomp_2d_fft_3d, :330)
+//   -> fused spectral kernels: normalise, half-sample phase rotations / DCT post-processing with
+//      the mirrored partner, division by the modified wavenumbers, inverse post-processing
+//   -> inverse FFTs -> inverse reorder.
+// The 1-D FFT passes are cuFFT plans (library code, like calling cuBLAS); everything around
+// them is hand written.  kxyz (src/poisson.f90:1733-1738,1787-1800) is NOT stored: it is
+// rebuilt per mode from three 1-D tables (squared modified wavenumbers and interpolator
+// transfer functions), which removes a 16 B/mode read and 1 GB of HBM at 512^3.
+#include <cufft.h>
+#include <cmath>
+#include "x3d_state.cuh"
+
+namespace x3d {
+
+#define X3D_CUFFT(call)                                                                         \
+  do {                                                                                          \
+    cufftResult r_ = (call);                                                                    \
+    if (r_ != CUFFT_SUCCESS)                                                                    \
+      throw ::x3d::Error(std::string(#call) + ": cuFFT error " + std::to_string((int)r_));      \
+  } while (0)
+
+struct PoissonImpl : PoissonState {
+  x3d_poisson_params p{};
+  int nx = 0, ny = 0, nz = 0, nzh = 0;  // pressure mesh
+  int bcx = 0, bcy = 0, bcz = 0;
+  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_xy = 0;
+  bool plans = false;
+  DevBuf cw, cwb, rwork, tables, fftwork, maps;
+  int *d_map[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [backward][axis]
+  // device table layout (doubles): ax,bx[nx] ay,by[ny] az,bz[nzh] | xk2[nx] yk2[ny] zk2[nzh][2] | tx[nx] ty[ny] tz[nzh][2]
+  double *d_ax = nullptr, *d_bx = nullptr, *d_ay = nullptr, *d_by = nullptr, *d_az = nullptr, *d_bz = nullptr;
+  double *d_xk2 = nullptr, *d_yk2 = nullptr, *d_zk2 = nullptr, *d_tx = nullptr, *d_ty = nullptr, *d_tz = nullptr;
+  ~PoissonImpl() override {
+    if (plans) { cufftDestroy(plan_r2c); cufftDestroy(plan_c2r); cufftDestroy(plan_xy); }
+  }
+};
+
+namespace {
+
+constexpr double EPS = 1.e-16;  // src/poisson.f90:25
+
+struct SpecArgs {
+  int nx, ny, nzh, nz;
+  int bcx, bcy, bcz;
+  double norm_x, norm_y, norm_z;
+  const double *ax, *bx, *ay, *by, *az, *bz;
+  const double *xk2, *yk2, *zk2, *tx, *ty, *tz;
+};
+
+// modified wavenumber of mode (i,j,k): (re,im) pair, src/poisson.f90:1733-1738 / :1787-1800
+__device__ __forceinline__ double2 kxyz_of(const SpecArgs &a, int i, int j, int k) {
+  const double fx = a.tx[i], fy = a.ty[j];
+  const double fzr = a.tz[2 * k], fzi = a.tz[2 * k + 1];
+  const double xk = a.xk2[i], yk = a.yk2[j];
+  const double zkr = a.zk2[2 * k], zki = a.zk2[2 * k + 1];
+  const double fxy2 = (fx * fy) * (fx * fy);
+  double2 r;
+  r.x = xk * ((fy * fzr) * (fy * fzr)) + yk * ((fx * fzr) * (fx * fzr)) + zkr * fxy2;
+  r.y = xk * ((fy * fzi) * (fy * fzi)) + yk * ((fx * fzi) * (fx * fzi)) + zki * fxy2;
+  return r;
+}
+__device__ __forceinline__ double2 rot_fwd(double2 c, double a, double b) { return make_double2(c.x * b + c.y * a, c.y * b - c.x * a); }
+__device__ __forceinline__ double2 rot_bwd(double2 c, double a, double b) { return make_double2(c.x * b - c.y * a, c.y * b + c.x * a); }
+__device__ __forceinline__ double2 neg(double2 c) { return make_double2(-c.x, -c.y); }
+__device__ __forceinline__ double2 divide4(double2 c, double2 kk) {  // src/poisson.f90:545-559
+  const bool z1 = fabs(kk.x) < EPS, z2 = fabs(kk.y) < EPS;
+  return make_double2(z1 ? 0.0 : c.x / (-kk.x), z2 ? 0.0 : c.y / (-kk.y));
+}
+// half-sample DCT post-/pre-processing with the mirrored partner, src/poisson.f90:508-528,571-591
+__device__ __forceinline__ double2 dct_post(double2 c, double2 p, double a, double b) {
+  return make_double2(0.5 * (c.x * b + c.y * a + p.x * b - p.y * a), 0.5 * (-c.x * a + c.y * b + p.x * a + p.y * b));
+}
+__device__ __forceinline__ double2 dct_pre(double2 c, double2 p, double a, double b) {
+  return make_double2(c.x * b - c.y * a + p.x * a + p.y * b, c.x * a + c.y * b - p.x * b + p.y * a);
+}
+
+// poisson_000, src/poisson.f90:336-402: everything between the two FFTs in one pass
+__global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
+  const long long tot = static_cast<long long>(a.nx) * a.ny * a.nzh;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < tot;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % a.nx);
+    const int j = static_cast<int>((idx / a.nx) % a.ny);
+    const int k = static_cast<int>(idx / (static_cast<long long>(a.nx) * a.ny));
+    double2 c = cw[idx];
+    c.x = c.x / a.norm_x / a.norm_y / a.norm_z;
+    c.y = c.y / a.norm_x / a.norm_y / a.norm_z;
+    c = rot_fwd(c, a.az[k], a.bz[k]);
+    c = rot_fwd(c, a.ay[j], a.by[j]);
+    if (j + 1 > a.ny / 2 + 1) c = neg(c);
+    c = rot_fwd(c, a.ax[i], a.bx[i]);
+    if (i + 1 > a.nx / 2 + 1) c = neg(c);
+    const double2 kk = kxyz_of(a, i, j, k);
+    if (kk.x < EPS || kk.y < EPS) c = make_double2(0.0, 0.0);  // :366
+    else c = make_double2(c.x / (-kk.x), c.y / (-kk.y));
+    c = make_double2(c.x * a.bz[k] - c.y * a.az[k], -c.y * a.bz[k] - c.x * a.az[k]);  // :381-384
+    c = make_double2(c.x * a.by[j] + c.y * a.ay[j], c.y * a.by[j] - c.x * a.ay[j]);   // :387-391
+    if (j + 1 > a.ny / 2 + 1) c = neg(c);
+    c = make_double2(c.x * a.bx[i] + c.y * a.ax[i], -c.y * a.bx[i] + c.x * a.ax[i]);  // :394-398
+    if (i + 1 > a.nx / 2 + 1) c = neg(c);
+    cw[idx] = c;
+  }
+}
+
+// Generic staged kernels for the non-periodic variants.  Each stage is out-of-place because the
+// DCT steps read the mirrored partner.  MODE bits select what a stage does, in this order:
+//   NORM, ROTZ_F, ROTY_F(+sign), ROTX_F(+sign), POSTY, POSTX, DIVIDE, ZERO010, PREX, PREY, ROTX_B(+sign), ROTY_B(+sign), ROTZ_B
+enum : unsigned { S_NORM = 1, S_ROTZ_F = 2, S_ROTY_F = 4, S_ROTX_F = 8, S_POSTY = 16, S_POSTX = 32, S_DIVIDE = 64,
+                  S_ZERO010 = 128, S_PREX = 256, S_PREY = 512, S_ROTX_B = 1024, S_ROTY_B = 2048, S_ROTZ_B = 4096 };
+
+__device__ __forceinline__ double2 pointwise_fwd(const SpecArgs &a, unsigned mode, double2 c, int i, int j, int k) {
+  if (mode & S_NORM) { c.x = c.x / a.norm_x / a.norm_y / a.norm_z; c.y = c.y / a.norm_x / a.norm_y / a.norm_z; }
+  if (mode & S_ROTZ_F) c = rot_fwd(c, a.az[k], a.bz[k]);
+  if (mode & S_ROTY_F) { c = rot_fwd(c, a.ay[j], a.by[j]); if (j + 1 > a.ny / 2 + 1) c = neg(c); }
+  if (mode & S_ROTX_F) { c = rot_fwd(c, a.ax[i], a.bx[i]); if (i + 1 > a.nx / 2 + 1) c = neg(c); }
+  return c;
+}
+
+__global__ void k_spec_stage(SpecArgs a, unsigned mode, const double2 *__restrict__ in, double2 *__restrict__ out) {
+  const long long tot = static_cast<long long>(a.nx) * a.ny * a.nzh;
+  const long long sxy = static_cast<long long>(a.nx) * a.ny;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < tot;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % a.nx);
+    const int j = static_cast<int>((idx / a.nx) % a.ny);
+    const int k = static_cast<int>(idx / sxy);
+    // the pointwise forward part is applied to the value AND to its partner before a POST step
+    double2 c = pointwise_fwd(a, mode, in[idx], i, j, k);
+    if (mode & S_POSTY) {
+      if (j > 0) {
+        const int jp = a.ny - j;
+        const double2 p = pointwise_fwd(a, mode, in[i + a.nx * static_cast<long long>(jp) + sxy * k], i, jp, k);
+        c = dct_post(c, p, a.ay[j], a.by[j]);
+      }
+    }
+    if (mode & S_POSTX) {
+      if (i > 0) {
+        const int ip = a.nx - i;
+        const double2 p = pointwise_fwd(a, mode, in[ip + a.nx * static_cast<long long>(j) + sxy * k], ip, j, k);
+        c = dct_post(c, p, a.ax[i], a.bx[i]);
+      }
+    }
+    if (mode & S_DIVIDE) c = divide4(c, kxyz_of(a, i, j, k));
+    if (mode & S_ZERO010) { if (i + 1 == a.nx / 2 + 1 && k + 1 == a.nz / 2 + 1) c = make_double2(0.0, 0.0); }  // :902-908
+    if (mode & S_PREX) {
+      if (i > 0) c = dct_pre(c, in[(a.nx - i) + a.nx * static_cast<long long>(j) + sxy * k], a.ax[i], a.bx[i]);
+    }
+    if (mode & S_PREY) {
+      if (j > 0) c = dct_pre(c, in[i + a.nx * static_cast<long long>(a.ny - j) + sxy * k], a.ay[j], a.by[j]);
+    }
+    if (mode & S_ROTX_B) { c = rot_bwd(c, a.ax[i], a.bx[i]); if (i + 1 > a.nx / 2 + 1) c = neg(c); }
+    if (mode & S_ROTY_B) { c = rot_bwd(c, a.ay[j], a.by[j]); if (j + 1 > a.ny / 2 + 1) c = neg(c); }
+    if (mode & S_ROTZ_B) c = rot_bwd(c, a.az[k], a.bz[k]);
+    out[idx] = c;
+  }
+}
+
+// even/odd reordering of the non-periodic axes, all axes in one gather driven by host-built
+// index maps (src/poisson.f90:435-444, 1047-1101 forward; :643-652, 1422-1458 backward)
+__global__ void k_reorder(const double *__restrict__ in, double *__restrict__ out, int nx, int ny, int nz,
+                          const int *__restrict__ mx, const int *__restrict__ my, const int *__restrict__ mz) {
+  const long long tot = static_cast<long long>(nx) * ny * nz;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < tot;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % nx);
+    const int j = static_cast<int>((idx / nx) % ny);
+    const int k = static_cast<int>(idx / (static_cast<long long>(nx) * ny));
+    out[idx] = in[mx[i] + static_cast<long long>(nx) * (my[j] + static_cast<long long>(ny) * mz[k])];
+  }
+}
+
+// ---- host tables (src/poisson.f90:1469-1526 abxyz, :1530-1810 waves) -----------------------
+struct AxisTables {
+  std::vector<double> a, b;    // sin/cos twiddles
+  std::vector<double> k2;      // squared modified wavenumber (re[,im])
+  std::vector<double> tf;      // interpolator transfer function (re[,im])
+};
+
+// one direction; n = pressure-mesh points (nm), nv = velocity nodes, per = periodic,
+// half = true for z (only n/2+1 modes; non-periodic z carries two wavenumbers per mode)
+AxisTables axis_tables(int nm, int nv, bool per, double len, const x3d_deriv_coeffs &c, bool half) {
+  AxisTables T;
+  const double pi = std::acos(-1.0), twopi = 2.0 * std::acos(-1.0);
+  const double d = len / static_cast<double>(nm);
+  const int na = half ? nm / 2 + 1 : nm;
+  T.a.resize(half ? na : nm); T.b.resize(half ? na : nm);
+  for (int i = 0; i < static_cast<int>(T.a.size()); ++i) {
+    const double arg = per ? static_cast<double>(i) * pi / static_cast<double>(nm) : static_cast<double>(i) * pi * 0.5 / static_cast<double>(nm);
+    T.a[i] = std::sin(arg); T.b[i] = std::cos(arg);
+  }
+  auto kmod = [&](double w) {  // modified wavenumber of the staggered derivative, :1569-1570
+    double wp = c.aci6 * 2.0 * d * std::sin(w * 0.5) + (c.bci6 * 2.0 * d) * std::sin(3.0 * 0.5 * w);
+    return wp / (1.0 + 2.0 * c.alcai6 * std::cos(w));
+  };
+  auto transfer = [&](double e) {  // (ytt1+ytt)/yt1 with e = exs*dx, :1716-1731
+    const double tt = 2.0 * (c.bici6 * std::cos(e * 1.5) + c.cici6 * std::cos(e * 2.5) + c.dici6 * std::cos(e * 3.5));
+    const double tt1 = 2.0 * c.aici6 * std::cos(e * 0.5);
+    const double t1 = 1.0 + 2.0 * c.ailcai6 * std::cos(e);
+    return (tt1 + tt) / t1;
+  };
+  const int w2 = half ? 2 : 1;
+  T.k2.assign(static_cast<size_t>(na) * w2, 0.0);
+  T.tf.assign(static_cast<size_t>(na) * w2, 0.0);
+  std::vector<double> es(static_cast<size_t>(na) * w2, 0.0);
+  if (!half) {
+    if (per) {
+      for (int i = 0; i <= nm / 2; ++i) {
+        const double w = twopi * i / nv;
+        const double v = nv * kmod(w) / len;
+        T.k2[i] = v * v; es[i] = nv * w / len;
+      }
+      for (int i = nm / 2 + 1; i < nm; ++i) { T.k2[i] = T.k2[nm - i]; es[i] = es[nm - i]; }
+    } else {
+      for (int i = 1; i < nm; ++i) {
+        const double w = twopi * 0.5 * i / nm;
+        const double v = nm * kmod(w) / len;
+        T.k2[i] = v * v; es[i] = nm * w / len;
+      }
+    }
+    for (int i = 0; i < nm; ++i) T.tf[i] = transfer(es[i] * d);
+  } else {
+    for (int k = 0; k < na; ++k) {
+      if (per) {
+        const double w = twopi * k / nv;
+        const double v = nv * kmod(w) / len;
+        T.k2[2 * k] = T.k2[2 * k + 1] = v * v;
+        es[2 * k] = es[2 * k + 1] = nv * w / len;
+      } else {  // :1646-1657: real part = mode k, imaginary part = mode nzm-k
+        const double w = pi * k / nm, w1 = pi * (nm - k) / nm;
+        const double v = nm * kmod(w) / len, v1 = nm * kmod(w1) / len;
+        T.k2[2 * k] = v * v; T.k2[2 * k + 1] = v1 * v1;
+        es[2 * k] = nm * w / len; es[2 * k + 1] = nm * w1 / len;
+      }
+      T.tf[2 * k] = transfer(es[2 * k] * d);
+      T.tf[2 * k + 1] = transfer(es[2 * k + 1] * d);
+    }
+  }
+  return T;
+}
+
+// source index of output point q: forward  out(i) = in(2(i-1)+1) | in(2n-2i+2)   (1-based, :438-441)
+//                                   backward out(2i-1) = in(i), out(2i) = in(n-i+1)   (:646-649)
+std::vector<int> reorder_map(int n, bool active, bool backward) {
+  std::vector<int> m(n);
+  for (int q = 0; q < n; ++q) {
+    if (!active) m[q] = q;
+    else if (!backward) m[q] = (q < n / 2) ? 2 * q : 2 * n - 2 * q - 1;
+    else m[q] = (q % 2 == 0) ? q / 2 : n - 1 - (q - 1) / 2;
+  }
+  return m;
+}
+
+int grid_for(long long n, int sm) {
+  long long b = (n + 255) / 256;
+  const long long cap = static_cast<long long>(sm) * 16;
+  return static_cast<int>(b < cap ? b : cap);
+}
+
+}  // namespace
+
+void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  if (p.istret != 0) throw Error("x3d_poisson_init: stretched-mesh Poisson (matrice_refinement/inversion5) not implemented yet");
+  for (int a = 0; a < 3; ++a)
+    if (!ctx.have_dc[a]) throw Error("x3d_poisson_init: call x3d_set_deriv_coeffs for the three axes first (waves() reads derivX/Y/Z)");
+  auto P = std::make_unique<PoissonImpl>();
+  P->p = p;
+  P->bcx = p.bcx; P->bcy = p.bcy; P->bcz = p.bcz;
+  const bool ok = (p.bcx == 0 && p.bcy == 0 && p.bcz == 0) || (p.bcx == 1 && p.bcy == 0 && p.bcz == 0) ||
+                  (p.bcx == 0 && p.bcy == 1 && p.bcz == 0) || (p.bcx == 1 && p.bcy == 1);
+  if (!ok) throw Error("boundary condition not supported (src/poisson.f90:107)");
+  P->nx = p.bcx ? p.nx - 1 : p.nx; P->ny = p.bcy ? p.ny - 1 : p.ny; P->nz = p.bcz ? p.nz - 1 : p.nz;
+  P->nzh = P->nz / 2 + 1;
+  const int nx = P->nx, ny = P->ny, nz = P->nz, nzh = P->nzh;
+  if ((p.bcx && nx % 2) || (p.bcy && ny % 2) || (p.bcz && nz % 2)) throw Error("non-periodic pressure mesh extents must be even");
+  AxisTables TX = axis_tables(nx, p.nx, p.bcx == 0, p.xlx, ctx.dc[0], false);
+  AxisTables TY = axis_tables(ny, p.ny, p.bcy == 0, p.yly, ctx.dc[1], false);
+  AxisTables TZ = axis_tables(nz, p.nz, p.bcz == 0, p.zlz, ctx.dc[2], true);
+  std::vector<double> h;
+  auto put = [&](const std::vector<double> &v) { size_t o = h.size(); h.insert(h.end(), v.begin(), v.end()); return o; };
+  const size_t o_ax = put(TX.a), o_bx = put(TX.b), o_ay = put(TY.a), o_by = put(TY.b), o_az = put(TZ.a), o_bz = put(TZ.b);
+  const size_t o_xk = put(TX.k2), o_yk = put(TY.k2), o_zk = put(TZ.k2), o_tx = put(TX.tf), o_ty = put(TY.tf), o_tz = put(TZ.tf);
+  P->tables.reserve(h.size() * sizeof(double));
+  X3D_CUDA(cudaMemcpyAsync(P->tables.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  double *base = static_cast<double *>(P->tables.p);
+  P->d_ax = base + o_ax; P->d_bx = base + o_bx; P->d_ay = base + o_ay; P->d_by = base + o_by; P->d_az = base + o_az; P->d_bz = base + o_bz;
+  P->d_xk2 = base + o_xk; P->d_yk2 = base + o_yk; P->d_zk2 = base + o_zk; P->d_tx = base + o_tx; P->d_ty = base + o_ty; P->d_tz = base + o_tz;
+  {  // reorder index maps
+    std::vector<int> hm;
+    size_t off[2][3];
+    const int nn[3] = {nx, ny, nz};
+    const int bcs[3] = {p.bcx, p.bcy, p.bcz};
+    for (int bw = 0; bw < 2; ++bw)
+      for (int a = 0; a < 3; ++a) {
+        std::vector<int> m = reorder_map(nn[a], bcs[a] != 0, bw == 1);
+        off[bw][a] = hm.size();
+        hm.insert(hm.end(), m.begin(), m.end());
+      }
+    P->maps.reserve(hm.size() * sizeof(int));
+    X3D_CUDA(cudaMemcpyAsync(P->maps.p, hm.data(), hm.size() * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+    X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (int bw = 0; bw < 2; ++bw)
+      for (int a = 0; a < 3; ++a) P->d_map[bw][a] = static_cast<int *>(P->maps.p) + off[bw][a];
+  }
+  // FFT plans
+  int nzv[1] = {nz};
+  int inembed[1] = {nz}, onembed[1] = {nzh};
+  const int nxy = nx * ny;
+  size_t ws = 0, wmax = 0;
+  X3D_CUFFT(cufftCreate(&P->plan_r2c)); X3D_CUFFT(cufftCreate(&P->plan_c2r)); X3D_CUFFT(cufftCreate(&P->plan_xy));
+  P->plans = true;
+  X3D_CUFFT(cufftSetAutoAllocation(P->plan_r2c, 0)); X3D_CUFFT(cufftSetAutoAllocation(P->plan_c2r, 0)); X3D_CUFFT(cufftSetAutoAllocation(P->plan_xy, 0));
+  X3D_CUFFT(cufftMakePlanMany(P->plan_r2c, 1, nzv, inembed, nxy, 1, onembed, nxy, 1, CUFFT_D2Z, nxy, &ws)); wmax = std::max(wmax, ws);
+  X3D_CUFFT(cufftMakePlanMany(P->plan_c2r, 1, nzv, onembed, nxy, 1, inembed, nxy, 1, CUFFT_Z2D, nxy, &ws)); wmax = std::max(wmax, ws);
+  int nyx[2] = {ny, nx};
+  X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nxy, nullptr, 1, nxy, CUFFT_Z2Z, nzh, &ws)); wmax = std::max(wmax, ws);
+  P->fftwork.reserve(wmax ? wmax : 16);
+  X3D_CUFFT(cufftSetWorkArea(P->plan_r2c, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_c2r, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_xy, P->fftwork.p));
+  X3D_CUFFT(cufftSetStream(P->plan_r2c, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_c2r, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_xy, ctx.stream));
+  const size_t nsp = static_cast<size_t>(nx) * ny * nzh;
+  P->cw.reserve(nsp * 16);
+  if (p.bcx || p.bcy) P->cwb.reserve(nsp * 16);
+  if (p.bcx || p.bcy || p.bcz) P->rwork.reserve(static_cast<size_t>(nx) * ny * nz * 8);
+  ctx.poisson = std::move(P);
+}
+
+void poisson_solve_device(Ctx &ctx, double *d_rhs) {
+  auto *P = dynamic_cast<PoissonImpl *>(ctx.poisson.get());
+  if (!P) throw Error("x3d_poisson: x3d_poisson_init has not been called");
+  const int nx = P->nx, ny = P->ny, nz = P->nz, nzh = P->nzh;
+  const long long nr = static_cast<long long>(nx) * ny * nz, nsp = static_cast<long long>(nx) * ny * nzh;
+  SpecArgs a{nx, ny, nzh, nz, P->bcx, P->bcy, P->bcz, static_cast<double>(nx), static_cast<double>(ny), static_cast<double>(nz),
+             P->d_ax, P->d_bx, P->d_ay, P->d_by, P->d_az, P->d_bz, P->d_xk2, P->d_yk2, P->d_zk2, P->d_tx, P->d_ty, P->d_tz};
+  double2 *cw = static_cast<double2 *>(P->cw.p), *cwb = static_cast<double2 *>(P->cwb.p);
+  double *rw = static_cast<double *>(P->rwork.p);
+  const int gr = grid_for(nr, ctx.sm_count), gs = grid_for(nsp, ctx.sm_count);
+  const bool any = P->bcx || P->bcy || P->bcz;
+  double *fft_in = d_rhs;
+  if (any) {
+    k_reorder<<<gr, 256, 0, ctx.stream>>>(d_rhs, rw, nx, ny, nz, P->d_map[0][0], P->d_map[0][1], P->d_map[0][2]);
+    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+    fft_in = rw;
+  }
+  X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cw)));
+  X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_FORWARD));
+  auto stage = [&](unsigned mode, const double2 *in, double2 *out) {
+    k_spec_stage<<<gs, 256, 0, ctx.stream>>>(a, mode, in, out);
+    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  };
+  if (!any) {
+    k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
+    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  } else if (P->bcx == 1 && P->bcy == 0) {  // poisson_100, :472-635
+    stage(S_NORM | S_ROTZ_F | S_ROTY_F | S_POSTX | S_DIVIDE, cw, cwb);
+    stage(S_PREX | S_ROTY_B | S_ROTZ_B, cwb, cw);
+  } else if (P->bcx == 0 && P->bcy == 1) {  // poisson_010, :724-991
+    stage(S_NORM | S_ROTZ_F | S_ROTX_F | S_POSTY | S_DIVIDE | S_ZERO010, cw, cwb);
+    stage(S_PREY | S_ROTX_B | S_ROTZ_B, cwb, cw);
+  } else {  // poisson_11x, :1118-1407
+    stage(S_NORM | S_ROTZ_F | S_POSTY, cw, cwb);
+    stage(S_POSTX | S_DIVIDE, cwb, cw);
+    stage(S_PREX, cw, cwb);
+    stage(S_PREY | S_ROTZ_B, cwb, cw);
+  }
+  X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_INVERSE));
+  X3D_CUFFT(cufftExecZ2D(P->plan_c2r, reinterpret_cast<cufftDoubleComplex *>(cw), any ? rw : d_rhs));
+  if (any) {
+    k_reorder<<<gr, 256, 0, ctx.stream>>>(rw, d_rhs, nx, ny, nz, P->d_map[1][0], P->d_map[1][1], P->d_map[1][2]);
+    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  }
+}
+
+void poisson_dims(Ctx &ctx, int d[3]) {
+  auto *P = dynamic_cast<PoissonImpl *>(ctx.poisson.get());
+  if (!P) throw Error("x3d_poisson: not initialised");
+  d[0] = P->nx; d[1] = P->ny; d[2] = P->nz;
+}
+
+}  // namespace x3d

@@ -1,0 +1,503 @@
+// x3d_solver.cu -- device-resident time step: the reference's
+// momentum_rhs_eq (src/transeq.f90:73-591), intt (src/time_integrators.f90:18-187), pre_correc /
+// divergence / gradp / cor_vel (src/navier.f90:502,257,386,206), init_tgv and postprocess_tgv
+// (src/Case-TGV.f90:25,189) chained on one GPU.  Fields never leave HBM; on a single rank every
+// pencil transpose of the reference is the identity and is not executed.
+#include <cmath>
+#include "x3d_schemes.cuh"
+#include "x3d_state.cuh"
+
+namespace x3d {
+
+void poisson_init(Ctx &ctx, const x3d_poisson_params &p);
+void poisson_solve_device(Ctx &ctx, double *d_rhs);
+
+namespace {
+
+template <class F>
+__global__ void k_map(long long n, F f) {
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n;
+       q += static_cast<long long>(gridDim.x) * blockDim.x)
+    f(q);
+}
+
+// block-level sum / max reduction into per-block partials, then one final block
+template <int NV, class F>
+__global__ void k_reduce_partial(long long n, F f, double *__restrict__ partial) {
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n;
+       q += static_cast<long long>(gridDim.x) * blockDim.x)
+    f(q, acc);
+  __shared__ double sh[NV][32];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double x = acc[v];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sh[v][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double x = threadIdx.x < (blockDim.x >> 5) ? sh[v][threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (threadIdx.x == 0) partial[static_cast<long long>(v) * gridDim.x + blockIdx.x] = x;
+    }
+  }
+}
+template <int NV>
+__global__ void k_reduce_final(int nblocks, const double *__restrict__ partial, double *__restrict__ out) {
+  __shared__ double sh[NV][32];
+  for (int v = 0; v < NV; ++v) {
+    double x = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) x += partial[static_cast<long long>(v) * nblocks + b];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sh[v][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    for (int v = 0; v < NV; ++v) {
+      double x = threadIdx.x < (blockDim.x >> 5) ? sh[v][threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (threadIdx.x == 0) out[v] = x;
+    }
+  }
+}
+__global__ void k_max_partial(long long n, const double *__restrict__ a, double *__restrict__ partial) {
+  double m = -1609.0;  // navier.f90:349
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n;
+       q += static_cast<long long>(gridDim.x) * blockDim.x)
+    m = fmax(m, a[q]);
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double x = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : -1609.0;
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
+    if (threadIdx.x == 0) partial[blockIdx.x] = x;
+  }
+}
+__global__ void k_max_final(int nblocks, const double *__restrict__ partial, double *__restrict__ out) {
+  double m = -1609.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) m = fmax(m, partial[b]);
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = sh[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) x = fmax(x, sh[w]);
+    out[0] = x;
+  }
+}
+
+}  // namespace
+
+struct PreOp {
+  DevOp op{};
+  OpCall call{};
+  bool ready = false;
+};
+
+struct SolverImpl : SolverState {
+  x3d_solver_params p{};
+  AxisCoeffs A[3];
+  int nxm = 0, nym = 0, nzm = 0;
+  double xnu = 0, adt[3]{}, bdt[3]{}, gdt[3]{};
+  int iadvance = 1, ntime = 1;
+  long long itime = 0;
+  size_t n = 0, n3 = 0;
+  // fields
+  DevBuf ux, uy, uz, px, py, pz, pp3, dux[2], duy[2], duz[2];
+  DevBuf w[16];
+  DevBuf red_partial, red_out;
+  double *h_red = nullptr;  // pinned
+  // prepared operators
+  PreOp d1[3][2], d2[3][2];                 // [axis][npaire]
+  PreOp dvp[3], ivp[3], dpv[3], ipv[3];
+  ~SolverImpl() override { if (h_red) cudaFreeHost(h_red); }
+};
+
+namespace {
+
+double *B(DevBuf &b) { return static_cast<double *>(b.p); }
+
+void prep(Ctx &ctx, PreOp &P, Kind kind, int axis, const AxisCoeffs &A, int npaire, const LU3 &lu, const int dims_in[3]) {
+  OpCall &c = P.call;
+  c = OpCall{};
+  c.kind = kind; c.axis = axis; c.ncl1 = A.ncl1; c.ncln = A.ncln; c.periodic = A.periodic; c.npaire = npaire;
+  c.n = A.n; c.nm = A.nm;
+  for (int d = 0; d < 3; ++d) c.dims_in[d] = dims_in[d];
+  c.f = lu.f.data(); c.s = lu.s.data(); c.w = lu.w.data();
+  c.post = nullptr; c.rhs_only = false;
+  build_devop(ctx, c, P.op);
+  if (P.op.untouched) throw Error("solver: operator variant not implemented by the reference");
+  P.ready = true;
+}
+void run(Ctx &ctx, const PreOp &P, const double *u, double *t) { launch_line_op(ctx, P.op, P.call, u, t); }
+
+int gridn(const Ctx &ctx, long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = static_cast<long long>(ctx.sm_count) * 16;
+  return static_cast<int>(b < cap ? b : cap);
+}
+template <class F>
+void map(Ctx &ctx, long long n, F f) {
+  k_map<<<gridn(ctx, n), 256, 0, ctx.stream>>>(n, f);
+  X3D_CUDA(cudaGetLastError());
+  ctx.launches++;
+}
+
+}  // namespace
+
+void solver_init(Ctx &ctx, const x3d_solver_params &p) {
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  if (p.p_row > 1 || p.p_col > 1) throw Error("x3d_solver_init: multi-rank solver goes through x3d_decomp_init (not wired yet)");
+  if (p.istret != 0) throw Error("x3d_solver_init: stretched meshes not implemented in the device solver yet");
+  auto S = std::make_unique<SolverImpl>();
+  S->p = p;
+  SchemeOpts o;
+  o.ifirstder = p.ifirstder; o.isecondder = p.isecondder; o.ipinter = p.ipinter; o.nu0nu = p.nu0nu; o.cnu = p.cnu;
+  const int nn[3] = {p.nx, p.ny, p.nz};
+  const int ncl[3][2] = {{p.nclx1, p.nclxn}, {p.ncly1, p.nclyn}, {p.nclz1, p.nclzn}};
+  const double len[3] = {p.xlx, p.yly, p.zlz};
+  for (int a = 0; a < 3; ++a) {
+    S->A[a] = make_axis_coeffs(nn[a], ncl[a][0], ncl[a][1], len[a], o);
+    ctx.dc[a] = S->A[a].c;
+    ctx.have_dc[a] = true;
+    ctx.ncl[a] = S->A[a].periodic;
+    for (int e = 0; e < 2; ++e)
+      if (ncl[a][e] == 2) throw Error("x3d_solver_init: Dirichlet faces need the case boundary data (Channel/Cylinder glue, SURVEY 8f-3)");
+  }
+  ctx.iibm = 0; ctx.istret = 0; ctx.iimplicit = 0;
+  S->nxm = S->A[0].nm; S->nym = S->A[1].nm; S->nzm = S->A[2].nm;
+  S->xnu = 1.0 / p.re;  // parameters.f90:302
+  const double dt = p.dt;
+  if (p.itimescheme == 5) {  // variables.f90:1388-1399
+    S->iadvance = 3; S->ntime = 2;
+    S->adt[0] = (8.0 / 15.0) * dt; S->bdt[0] = 0.0; S->gdt[0] = S->adt[0];
+    S->adt[1] = (5.0 / 12.0) * dt; S->bdt[1] = (-17.0 / 60.0) * dt; S->gdt[1] = S->adt[1] + S->bdt[1];
+    S->adt[2] = (3.0 / 4.0) * dt; S->bdt[2] = (-5.0 / 12.0) * dt; S->gdt[2] = S->adt[2] + S->bdt[2];
+  } else if (p.itimescheme == 1) {
+    S->iadvance = 1; S->ntime = 1; S->adt[0] = dt; S->gdt[0] = dt;
+  } else {
+    throw Error("x3d_solver_init: itimescheme 1 (Euler) and 5 (RK3) are implemented");
+  }
+  S->n = static_cast<size_t>(p.nx) * p.ny * p.nz;
+  S->n3 = static_cast<size_t>(S->nxm) * S->nym * S->nzm;
+  const size_t bytes = S->n * sizeof(double);
+  for (DevBuf *b : {&S->ux, &S->uy, &S->uz, &S->px, &S->py, &S->pz, &S->pp3}) { b->reserve(bytes); X3D_CUDA(cudaMemsetAsync(b->p, 0, bytes, ctx.stream)); }
+  for (int q = 0; q < S->ntime; ++q)
+    for (DevBuf *b : {&S->dux[q], &S->duy[q], &S->duz[q]}) { b->reserve(bytes); X3D_CUDA(cudaMemsetAsync(b->p, 0, bytes, ctx.stream)); }
+  for (auto &b : S->w) b.reserve(bytes);
+  S->red_partial.reserve(sizeof(double) * 8 * 4096);
+  S->red_out.reserve(sizeof(double) * 16);
+  X3D_CUDA(cudaMallocHost(&S->h_red, sizeof(double) * 16));
+  // operators
+  const int dv[3] = {p.nx, p.ny, p.nz};
+  for (int a = 0; a < 3; ++a) {
+    prep(ctx, S->d1[a][0], D1, a, S->A[a], 0, S->A[a].d1, dv);
+    prep(ctx, S->d1[a][1], D1, a, S->A[a], 1, S->A[a].d1p, dv);
+    prep(ctx, S->d2[a][0], D2, a, S->A[a], 0, S->A[a].d2, dv);
+    prep(ctx, S->d2[a][1], D2, a, S->A[a], 1, S->A[a].d2p, dv);
+  }
+  // divergence chain (navier.f90:297-336): x on (nx,ny,nz), y on (nxm,ny,nz), z on (nxm,nym,nz)
+  const int dy[3] = {S->nxm, p.ny, p.nz}, dz[3] = {S->nxm, S->nym, p.nz};
+  const int *dsv[3] = {dv, dy, dz};
+  for (int a = 0; a < 3; ++a) {
+    prep(ctx, S->dvp[a], DVP, a, S->A[a], 0, S->A[a].vp, dsv[a]);
+    prep(ctx, S->ivp[a], IVP, a, S->A[a], 1, S->A[a].ivpp, dsv[a]);
+  }
+  // gradp chain (navier.f90:404-431): z on (nxm,nym,nzm), y on (nxm,nym,nz), x on (nxm,ny,nz)
+  const int gz[3] = {S->nxm, S->nym, S->nzm}, gy[3] = {S->nxm, S->nym, p.nz}, gx[3] = {S->nxm, p.ny, p.nz};
+  const int *gsv[3] = {gx, gy, gz};
+  for (int a = 0; a < 3; ++a) {
+    const AxisCoeffs &A = S->A[a];
+    prep(ctx, S->dpv[a], DPV, a, A, 1, A.periodic ? A.vp : A.pvp, gsv[a]);
+    prep(ctx, S->ipv[a], IPV, a, A, 1, A.periodic ? A.ivp : A.ipvp, gsv[a]);
+  }
+  x3d_poisson_params pp{};
+  pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
+  pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
+  pp.xlx = p.xlx; pp.yly = p.yly; pp.zlz = p.zlz; pp.istret = 0;
+  poisson_init(ctx, pp);
+  ctx.solver = std::move(S);
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+static SolverImpl &SOL(Ctx &ctx) {
+  auto *S = dynamic_cast<SolverImpl *>(ctx.solver.get());
+  if (!S) throw Error("solver: x3d_solver_init has not been called");
+  return *S;
+}
+
+// Case-TGV.f90:90-95
+void solver_init_tgv(Ctx &ctx) {
+  SolverImpl &S = SOL(ctx);
+  const int nx = S.p.nx, ny = S.p.ny;
+  const double dx = S.A[0].d, dy = S.A[1].d, dz = S.A[2].d;
+  double *ux = B(S.ux), *uy = B(S.uy), *uz = B(S.uz);
+  map(ctx, S.n, [=] __device__(long long q) {
+    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny));
+    const double x = static_cast<double>(i) * dx, y = static_cast<double>(j) * dy, z = static_cast<double>(k) * dz;
+    ux[q] = sin(x) * cos(y) * cos(z);
+    uy[q] = -cos(x) * sin(y) * cos(z);
+    uz[q] = 0.0;
+  });
+  for (int q = 0; q < S.ntime; ++q)
+    for (DevBuf *b : {&S.dux[q], &S.duy[q], &S.duz[q]}) X3D_CUDA(cudaMemsetAsync(b->p, 0, S.n * sizeof(double), ctx.stream));
+  for (DevBuf *b : {&S.px, &S.py, &S.pz, &S.pp3}) X3D_CUDA(cudaMemsetAsync(b->p, 0, S.n * sizeof(double), ctx.stream));
+  S.itime = 0;
+}
+
+// transeq.f90:73-591 (incompressible, explicit diffusion, uniform mesh)
+static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, double *duz1) {
+  const long long n = static_cast<long long>(S.n);
+  const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  double *ta = B(S.w[0]), *tb = B(S.w[1]), *tc = B(S.w[2]), *td = B(S.w[3]), *te = B(S.w[4]), *tf = B(S.w[5]);
+  double *tg1 = B(S.w[6]), *th1 = B(S.w[7]), *ti1 = B(S.w[8]), *tg2 = B(S.w[9]), *th2 = B(S.w[10]), *ti2 = B(S.w[11]);
+  double *tg3 = B(S.w[12]), *th3 = B(S.w[13]), *ti3 = B(S.w[14]);
+  const double xnu = S.xnu, half = 0.5;
+  // x, :114-146
+  map(ctx, n, [=] __device__(long long q) { const double a = u[q]; ta[q] = a * a; tb[q] = a * v[q]; tc[q] = a * w[q]; });
+  run(ctx, S.d1[0][1], ta, td); run(ctx, S.d1[0][0], tb, te); run(ctx, S.d1[0][0], tc, tf);
+  run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);
+  map(ctx, n, [=] __device__(long long q) { const double a = u[q]; tg1[q] = td[q] + a * ta[q]; th1[q] = te[q] + a * tb[q]; ti1[q] = tf[q] + a * tc[q]; });
+  // y, :188-219
+  map(ctx, n, [=] __device__(long long q) { const double a = v[q]; td[q] = u[q] * a; te[q] = a * a; tf[q] = w[q] * a; });
+  run(ctx, S.d1[1][0], td, tg2); run(ctx, S.d1[1][1], te, th2); run(ctx, S.d1[1][0], tf, ti2);
+  run(ctx, S.d1[1][1], u, td); run(ctx, S.d1[1][0], v, te); run(ctx, S.d1[1][1], w, tf);
+  map(ctx, n, [=] __device__(long long q) { const double a = v[q]; tg2[q] = tg2[q] + a * td[q]; th2[q] = th2[q] + a * te[q]; ti2[q] = ti2[q] + a * tf[q]; });
+  // z, :249-314
+  map(ctx, n, [=] __device__(long long q) { const double a = w[q]; td[q] = u[q] * a; te[q] = v[q] * a; tf[q] = a * a; });
+  run(ctx, S.d1[2][0], td, tg3); run(ctx, S.d1[2][0], te, th3); run(ctx, S.d1[2][1], tf, ti3);
+  run(ctx, S.d1[2][1], u, td); run(ctx, S.d1[2][1], v, te); run(ctx, S.d1[2][0], w, tf);
+  run(ctx, S.d2[2][1], u, ta); run(ctx, S.d2[2][1], v, tb); run(ctx, S.d2[2][0], w, tc);
+  map(ctx, n, [=] __device__(long long q) {
+    const double a = w[q];
+    const double cx = tg3[q] + a * td[q], cy = th3[q] + a * te[q], cz = ti3[q] + a * tf[q];
+    const double zx = xnu * ta[q] - half * cx, zy = xnu * tb[q] - half * cy, zz = xnu * tc[q] - half * cz;
+    tg2[q] = zx - half * tg2[q]; th2[q] = zy - half * th2[q]; ti2[q] = zz - half * ti2[q];  // :323-325
+  });
+  // y diffusion, :336-433
+  run(ctx, S.d2[1][1], u, td); run(ctx, S.d2[1][0], v, te); run(ctx, S.d2[1][1], w, tf);
+  // x diffusion and final sum, :442-470
+  run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);
+  map(ctx, n, [=] __device__(long long q) {
+    const double ax = xnu * td[q] + tg2[q], ay = xnu * te[q] + th2[q], az = xnu * tf[q] + ti2[q];
+    dux1[q] = ax - half * tg1[q] + xnu * ta[q];
+    duy1[q] = ay - half * th1[q] + xnu * tb[q];
+    duz1[q] = az - half * ti1[q] + xnu * tc[q];
+  });
+}
+
+// time_integrators.f90:71-74,151-157 for the three components at once
+static void intt3(Ctx &ctx, SolverImpl &S, int itr) {
+  const long long n = static_cast<long long>(S.n);
+  double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  const double *a1 = B(S.dux[0]), *b1 = B(S.duy[0]), *c1 = B(S.duz[0]);
+  if (S.p.itimescheme == 1) {
+    const double g = S.gdt[0];
+    map(ctx, n, [=] __device__(long long q) { u[q] = g * a1[q] + u[q]; v[q] = g * b1[q] + v[q]; w[q] = g * c1[q] + w[q]; });
+    return;
+  }
+  double *a2 = B(S.dux[1]), *b2 = B(S.duy[1]), *c2 = B(S.duz[1]);
+  if (itr == 1) {
+    const double g = S.gdt[0];
+    map(ctx, n, [=] __device__(long long q) {
+      const double x = a1[q], y = b1[q], z = c1[q];
+      u[q] = g * x + u[q]; v[q] = g * y + v[q]; w[q] = g * z + w[q];
+      a2[q] = x; b2[q] = y; c2[q] = z;
+    });
+  } else {
+    const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
+    map(ctx, n, [=] __device__(long long q) {
+      const double x = a1[q], y = b1[q], z = c1[q];
+      u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
+      a2[q] = x; b2[q] = y; c2[q] = z;
+    });
+  }
+}
+
+// navier.f90:599-613,693-711,751-769 (free-slip faces)
+static void pre_correc(Ctx &ctx, SolverImpl &S) {
+  const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
+  double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  const bool x1 = S.p.nclx1 == 1, xn = S.p.nclxn == 1, y1 = S.p.ncly1 == 1, yn = S.p.nclyn == 1, z1 = S.p.nclz1 == 1, zn = S.p.nclzn == 1;
+  if (x1 || xn)
+    map(ctx, static_cast<long long>(ny) * nz, [=] __device__(long long q) {
+      if (x1) u[q * nx] = 0.0;
+      if (xn) u[q * nx + nx - 1] = 0.0;
+    });
+  if (y1 || yn)
+    map(ctx, static_cast<long long>(nx) * nz, [=] __device__(long long q) {
+      const long long i = q % nx, k = q / nx;
+      if (y1) v[i + static_cast<long long>(nx) * ny * k] = 0.0;
+      if (yn) v[i + static_cast<long long>(nx) * (ny - 1 + static_cast<long long>(ny) * k)] = 0.0;
+    });
+  if (z1 || zn)
+    map(ctx, static_cast<long long>(nx) * ny, [=] __device__(long long q) {
+      if (z1) w[q] = 0.0;
+      if (zn) w[q + static_cast<long long>(nx) * ny * (nz - 1)] = 0.0;
+    });
+}
+
+// navier.f90:257-347 ; result in out (nxm,nym,nzm)
+static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
+  double *pp1 = B(S.w[0]), *pgy1 = B(S.w[1]), *pgz1 = B(S.w[2]), *upi2 = B(S.w[3]), *duy = B(S.w[4]), *po3 = B(S.w[5]);
+  run(ctx, S.dvp[0], B(S.ux), pp1);    // :297
+  run(ctx, S.ivp[0], B(S.uy), pgy1);   // :313
+  run(ctx, S.ivp[0], B(S.uz), pgz1);   // :314
+  run(ctx, S.ivp[1], pp1, upi2);       // :321
+  run(ctx, S.dvp[1], pgy1, duy);       // :322
+  const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.p.nz;
+  map(ctx, n2, [=] __device__(long long q) { duy[q] = duy[q] + upi2[q]; });  // :325
+  run(ctx, S.ivp[1], pgz1, upi2);      // :327
+  run(ctx, S.ivp[2], duy, out);        // :333
+  run(ctx, S.dvp[2], upi2, po3);       // :335
+  const long long n3 = static_cast<long long>(S.n3);
+  if (nlock == 2) {                    // :339-347
+    const long long ref = static_cast<long long>(S.nxm) * S.nym * (S.nzm - 1);
+    double *tmp = B(S.red_out) + 8;
+    map(ctx, 1, [=] __device__(long long) { tmp[0] = out[ref] + po3[ref]; });
+    map(ctx, n3, [=] __device__(long long q) { out[q] = (out[q] + po3[q]) - tmp[0]; });
+  } else {
+    map(ctx, n3, [=] __device__(long long q) { out[q] = out[q] + po3[q]; });
+  }
+}
+
+// navier.f90:386-431
+static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3) {
+  double *ppi3 = B(S.w[0]), *pgz3 = B(S.w[1]), *ppi2 = B(S.w[2]), *pgy2 = B(S.w[3]), *pgzi2 = B(S.w[4]);
+  run(ctx, S.ipv[2], pp3, ppi3);   // :404
+  run(ctx, S.dpv[2], pp3, pgz3);   // :406
+  run(ctx, S.ipv[1], ppi3, ppi2);  // :413
+  run(ctx, S.dpv[1], ppi3, pgy2);  // :415
+  run(ctx, S.ipv[1], pgz3, pgzi2); // :417
+  run(ctx, S.dpv[0], ppi2, B(S.px));   // :426
+  run(ctx, S.ipv[0], pgy2, B(S.py));   // :428
+  run(ctx, S.ipv[0], pgzi2, B(S.pz));  // :430
+}
+
+void solver_step(Ctx &ctx, int nsteps) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const long long n = static_cast<long long>(S.n);
+  for (int st = 0; st < nsteps; ++st) {
+    S.itime += 1;
+    for (int itr = 1; itr <= S.iadvance; ++itr) {  // xcompact3d.f90:46-88
+      momentum_rhs(ctx, S, B(S.dux[0]), B(S.duy[0]), B(S.duz[0]));
+      intt3(ctx, S, itr);
+      pre_correc(ctx, S);
+      divergence(ctx, S, B(S.pp3), 1);
+      poisson_solve_device(ctx, B(S.pp3));
+      gradp(ctx, S, B(S.pp3));
+      double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+      const double *px = B(S.px), *py = B(S.py), *pz = B(S.pz);
+      map(ctx, n, [=] __device__(long long q) { u[q] = u[q] - px[q]; v[q] = v[q] - py[q]; w[q] = w[q] - pz[q]; });  // cor_vel
+    }
+  }
+}
+
+// Case-TGV.f90:246-380 ; out5 = eek, eps, eps2, enst, DIV U max
+void solver_diagnostics_tgv(Ctx &ctx, double *out5) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
+  const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  double *ta = B(S.w[0]), *tb = B(S.w[1]), *tc = B(S.w[2]), *td = B(S.w[3]), *te = B(S.w[4]), *tf = B(S.w[5]);
+  double *tg = B(S.w[6]), *th = B(S.w[7]), *ti = B(S.w[8]);
+  const int xs1 = S.p.nclx1 == 1 ? nx - 1 : nx, xs2 = S.p.ncly1 == 1 ? ny - 1 : ny, xs3 = S.p.nclz1 == 1 ? nz - 1 : nz;
+  const double ncell = static_cast<double>(S.p.nclx1 == 1 ? S.nxm : nx) * (S.p.ncly1 == 1 ? S.nym : ny) * (S.p.nclz1 == 1 ? S.nzm : nz);
+  run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);  // :261-263
+  run(ctx, S.d1[1][1], u, td); run(ctx, S.d1[1][0], v, te); run(ctx, S.d1[1][1], w, tf);  // :265-267
+  run(ctx, S.d1[2][1], u, tg); run(ctx, S.d1[2][1], v, th); run(ctx, S.d1[2][0], w, ti);  // :269-271
+  const double xnu = S.xnu;
+  const long long n = static_cast<long long>(S.n);
+  const int nb = gridn(ctx, n) > 4096 ? 4096 : gridn(ctx, n);
+  double *partial = B(S.red_partial), *dout = B(S.red_out);
+  auto inside = [=] __device__(long long q) {
+    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny));
+    return i < xs1 && j < xs2 && k < xs3;
+  };
+  k_reduce_partial<3><<<nb, 256, 0, ctx.stream>>>(n, [=] __device__(long long q, double *acc) {
+    if (!inside(q)) return;
+    const double a = tf[q] - th[q], b = tg[q] - tc[q], c = tb[q] - td[q];
+    acc[0] += 0.5 * (a * a + b * b + c * c);                                                      // enstrophy :291-293
+    const double s1 = 2.0 * ta[q], s2 = 2.0 * te[q], s3 = 2.0 * ti[q], s4 = td[q] + tb[q], s5 = tg[q] + tc[q], s6 = th[q] + tf[q];
+    acc[1] += 0.5 * xnu * (s1 * s1 + s2 * s2 + s3 * s3 + 2.0 * s4 * s4 + 2.0 * s5 * s5 + 2.0 * s6 * s6);  // eps :305-308
+    acc[2] += 0.5 * (u[q] * u[q] + v[q] * v[q] + w[q] * w[q]);                                   // eek :323
+  }, partial);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  k_reduce_final<3><<<1, 256, 0, ctx.stream>>>(nb, partial, dout);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);  // :332-334
+  run(ctx, S.d2[1][1], u, td); run(ctx, S.d2[1][0], v, te); run(ctx, S.d2[1][1], w, tf);  // :336-338
+  run(ctx, S.d2[2][1], u, tg); run(ctx, S.d2[2][1], v, th); run(ctx, S.d2[2][0], w, ti);  // :340-342
+  k_reduce_partial<1><<<nb, 256, 0, ctx.stream>>>(n, [=] __device__(long long q, double *acc) {
+    if (!inside(q)) return;
+    acc[0] += (-xnu) * (u[q] * (ta[q] + td[q] + tg[q]) + v[q] * (tb[q] + te[q] + th[q]) + w[q] * (tc[q] + tf[q] + ti[q]));  // :362-365
+  }, partial);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  k_reduce_final<1><<<1, 256, 0, ctx.stream>>>(nb, partial, dout + 3);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  // DIV U max of the current field (divergence nlock=2, navier.f90:341-361)
+  double *dv = B(S.w[9]);
+  divergence(ctx, S, dv, 2);
+  const long long n3 = static_cast<long long>(S.n3);
+  const int nb3 = gridn(ctx, n3) > 4096 ? 4096 : gridn(ctx, n3);
+  k_max_partial<<<nb3, 256, 0, ctx.stream>>>(n3, dv, partial);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  k_max_final<<<1, 256, 0, ctx.stream>>>(nb3, partial, dout + 4);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  X3D_CUDA(cudaMemcpyAsync(S.h_red, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  out5[0] = S.h_red[2] / ncell;  // eek
+  out5[1] = S.h_red[1] / ncell;  // eps
+  out5[2] = S.h_red[3] / ncell;  // eps2
+  out5[3] = S.h_red[0] / ncell;  // enstrophy
+  out5[4] = S.h_red[4];
+}
+
+void solver_divergence(Ctx &ctx, double *divmax, double *divmean) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  double *dv = B(S.w[9]);
+  divergence(ctx, S, dv, 2);
+  const long long n3 = static_cast<long long>(S.n3);
+  const int nb3 = gridn(ctx, n3) > 4096 ? 4096 : gridn(ctx, n3);
+  double *partial = B(S.red_partial), *dout = B(S.red_out);
+  k_max_partial<<<nb3, 256, 0, ctx.stream>>>(n3, dv, partial);
+  k_max_final<<<1, 256, 0, ctx.stream>>>(nb3, partial, dout);
+  k_reduce_partial<1><<<nb3, 256, 0, ctx.stream>>>(n3, [=] __device__(long long q, double *acc) { acc[0] += fabs(dv[q]); }, partial);
+  k_reduce_final<1><<<1, 256, 0, ctx.stream>>>(nb3, partial, dout + 1);
+  X3D_CUDA(cudaGetLastError()); ctx.launches += 4;
+  X3D_CUDA(cudaMemcpyAsync(S.h_red, dout, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  if (divmax) *divmax = S.h_red[0];
+  if (divmean) *divmean = S.h_red[1] / static_cast<double>(n3);
+}
+
+void solver_set_velocity(Ctx &ctx, const double *ux, const double *uy, const double *uz) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const size_t bytes = S.n * sizeof(double);
+  X3D_CUDA(cudaMemcpyAsync(S.ux.p, ux, bytes, cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(S.uy.p, uy, bytes, cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(S.uz.p, uz, bytes, cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const size_t bytes = S.n * sizeof(double);
+  X3D_CUDA(cudaMemcpyAsync(ux, S.ux.p, bytes, cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(uy, S.uy.p, bytes, cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(uz, S.uz.p, bytes, cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+}  // namespace x3d

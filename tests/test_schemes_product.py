@@ -1,0 +1,50 @@
+"""The product's own schemes() (x3d_schemes_axis, CPU code inside libx3d_b200.so) against the
+golden vectors from the reference source and against the oracle.  CPU only."""
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from incompact3d_b200 import AxisSchemes
+from refnames import canon_scalar
+
+PAIRS = {"d1": ("ff", "fs", "fw"), "d1p": ("ffp", "fsp", "fwp"), "d2": ("sf", "ss", "sw"), "d2p": ("sfp", "ssp", "swp"),
+         "vp": ("cfx6", "csx6", "cwx6"), "vpp": ("cfxp6", "csxp6", "cwxp6"), "ivp": ("cifx6", "cisx6", "ciwx6"),
+         "ivpp": ("cifxp6", "cisxp6", "ciwxp6"), "pv": ("cfi6", "csi6", "cwi6"), "pvp": ("cfip6", "csip6", "cwip6"),
+         "ipv": ("cifi6", "cisi6", "ciwi6"), "ipvp": ("cifip6", "cisip6", "ciwip6")}
+
+
+@pytest.mark.parametrize("bc", ["00", "11", "12", "21", "22"])
+@pytest.mark.parametrize("opts", [(4, 4, 3), (4, 5, 3), (1, 1, 1), (4, 4, 2), (4, 4, 1)])
+@pytest.mark.parametrize("n", [12, 65, 128])
+def test_product_schemes_match_oracle(bc, opts, n):
+    fd, sd, ip = opts
+    length = 3.7
+    P = AxisSchemes(n, int(bc[0]), int(bc[1]), length, ifirstder=fd, isecondder=sd, ipinter=ip)
+    O = ol.Axis(n, int(bc[0]), int(bc[1]), length, ifirstder=fd, isecondder=sd, ipinter=ip)
+    for name, _ in ol.DerivCoeffs._fields_:
+        assert getattr(P.c, name) == pytest.approx(getattr(O.c, name), rel=1e-15, abs=1e-300), name
+    for key, names in PAIRS.items():
+        got = P.lu(key)
+        for g, nm in zip(got, names):
+            np.testing.assert_allclose(g, O.arr(nm), rtol=4e-15, atol=1e-300, err_msg=f"{key}/{nm}")
+
+
+def test_product_schemes_match_reference_golden(golden_dir):
+    sch = np.load(f"{golden_dir}/schemes.npz")
+    ops = np.load(f"{golden_dir}/operators.npz")
+    n_checked = 0
+    for tag in sorted({k.split("/")[0] for k in sch.files}):
+        m = re.match(r"^([xyz])(\d\d)_s(\d)$", tag)
+        if not m:
+            continue
+        ax, bc, second = m.group(1), m.group(2), int(m.group(3))
+        n = int(ops["meta/n" + ax])
+        P = AxisSchemes(n, int(bc[0]), int(bc[1]), float(ops["meta/lengths"]["xyz".index(ax)]), isecondder=second)
+        for nm, v in zip(sch[tag + "/scalar_names"], sch[tag + "/scalar_values"]):
+            cn = canon_scalar(str(nm), ax)
+            if hasattr(P.c, cn):
+                assert getattr(P.c, cn) == pytest.approx(v, rel=2e-15, abs=1e-300), (tag, nm)
+                n_checked += 1
+    assert n_checked > 1000

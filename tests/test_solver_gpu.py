@@ -1,0 +1,77 @@
+"""GPU parity of the device-resident time step (x3d_solver_*, C ABI).
+
+ * BASELINE config #1: TGV 65^3 free-slip, Re=1600, dt=0.005, RK3, 100 steps: E_k / eps / eps2 /
+   enstrophy histories against the reference's golden file (real Fortran output) within 1e-9
+   relative, post-projection DIV U max at machine level;
+ * periodic TGV (the 512^3 benchmark configuration at 64^3 / 48x40x56): velocity fields and
+   diagnostics against the oracle after a few steps."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle_lib as ol
+from test_oracle_tgv import PI_IN, make_solver
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tgv_65_free_slip_matches_reference_golden(golden_dir):
+    from incompact3d_b200 import X3D
+    ref = np.loadtxt(os.path.join(golden_dir, "tgv_reference_time_evol.dat"))
+    x = X3D(0)
+    x.solver_init(65, 65, 65, ncl=(1, 1, 1, 1, 1, 1), xlx=PI_IN, yly=PI_IN, zlz=PI_IN, re=1600.0, dt=0.005)
+    x.solver_init_tgv()
+    worst = 0.0
+    for row in range(10):
+        x.solver_step(10)
+        d = x.solver_diagnostics_tgv()
+        got = np.array([d["eek"], d["eps"], d["eps2"], d["enst"]])
+        err = np.abs(got / ref[row, 1:] - 1.0)
+        worst = max(worst, err.max())
+        assert err.max() < 1e-9, (row, err)
+        assert abs(d["divmax"]) < 1e-11, d
+    print("worst relative deviation from the reference golden file:", worst)
+    x.close()
+
+
+@pytest.mark.parametrize("nn,ncl", [((64, 64, 64), (0,) * 6), ((48, 40, 56), (0,) * 6), ((33, 33, 40), (1, 1, 1, 1, 0, 0))])
+def test_solver_matches_oracle(nn, ncl):
+    from incompact3d_b200 import X3D
+    length = 2 * np.pi
+    L = ol.lib()
+    Ls, s = make_solver(n=nn, ncl=ncl, length=length, re=1600.0, dt=0.002)
+    Ls.x3do_solver_init_tgv(s)
+    x = X3D(0)
+    x.solver_init(*nn, ncl=ncl, xlx=length, yly=length, zlz=length, re=1600.0, dt=0.002)
+    x.solver_init_tgv()
+    n = nn[0] * nn[1] * nn[2]
+    # perturb the TGV field so that all velocity components and all operators are exercised
+    rng = np.random.default_rng(3)
+    ux, uy, uz = x.solver_get_velocity()
+    k = 2 * np.pi / length
+    xs, ys, zs = (np.arange(m) * (length / (m if c == 0 else m - 1)) for m, c in zip(nn, ncl[::2]))
+    uz += 0.3 * np.asfortranarray(np.cos(k * xs)[:, None, None] * np.cos(k * ys)[None, :, None] * np.sin(k * zs)[None, None, :])
+    x.solver_set_velocity(ux, uy, uz)
+    dp = C.POINTER(C.c_double)
+    Ls.x3do_solver_set_velocity(s, ux.ctypes.data_as(dp), uy.ctypes.data_as(dp), uz.ctypes.data_as(dp))
+    for it in range(3):
+        x.solver_step(1)
+        assert Ls.x3do_solver_step(s, 1) == 0
+        gu, gv, gw = x.solver_get_velocity()
+        ru, rv, rw = (np.zeros(nn, order="F") for _ in range(3))
+        Ls.x3do_solver_get_velocity(s, ru.ctypes.data_as(dp), rv.ctypes.data_as(dp), rw.ctypes.data_as(dp))
+        scale = max(np.abs(ru).max(), np.abs(rv).max(), np.abs(rw).max())
+        for a, b in ((gu, ru), (gv, rv), (gw, rw)):
+            assert np.abs(a - b).max() / scale < 1e-11, (it, np.abs(a - b).max() / scale)
+    out = (C.c_double * 4)()
+    Ls.x3do_solver_postprocess_tgv(s, out)
+    d = x.solver_diagnostics_tgv()
+    got = np.array([d["eek"], d["eps"], d["eps2"], d["enst"]])
+    assert np.abs(got / np.array(out[:]) - 1).max() < 1e-10
+    dmax, dmean = x.solver_divergence()
+    assert abs(dmax) < 1e-11 and dmean < 1e-12
+    Ls.x3do_solver_destroy(s)
+    x.close()
