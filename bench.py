@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=512, help="nodes per direction (periodic TGV)")
-    ap.add_argument("--cpu-n", type=int, default=128, help="box size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=256, help="box size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -229,7 +229,7 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu_baseline and rank == 0:
         try:
-            steps_cpu = 3
+            steps_cpu = 4
             r = cpu_reference_run(args.cpu_n, steps_cpu, 1)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                    "sample": f"periodic TGV {args.cpu_n}^3, {steps_cpu} RK3 steps after 1 warm-up ({r['seconds']:.1f} s), oracle "

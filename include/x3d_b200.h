@@ -42,6 +42,11 @@ int x3d_sync(x3d_ctx *ctx);
 /* the cudaStream_t the context launches on (as an integer handle) */
 unsigned long long x3d_stream(x3d_ctx *ctx);
 
+/* optional per-launch timing with CUDA events on the context stream, grouped by kernel class;
+ * x3d_profile_end writes a JSON array of {name,count,total_ms,avg_ms} into buf                 */
+int x3d_profile_begin(x3d_ctx *ctx);
+int x3d_profile_end(x3d_ctx *ctx, char *buf, int cap);
+
 /* ---- hidden module state made explicit -------------------------------
  * The reference operators read stencil scalars from modules derivX/Y/Z
  * (src/module_param.f90:559-617), filter scalars from parfiX/Y/Z

@@ -310,6 +310,23 @@ def _solver_get_velocity(self, ux=None, uy=None, uz=None):
     return ux, uy, uz
 
 
+def _profile_step(self, nsteps=1):
+    """run `nsteps` solver steps with per-launch CUDA-event timing; -> list of kernel classes"""
+    import json
+    self._L.x3d_profile_begin.argtypes = [C.c_void_p]
+    self._L.x3d_profile_end.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    self._check(self._L.x3d_profile_begin(self._h))
+    self.solver_step(nsteps)
+    buf = C.create_string_buffer(1 << 16)
+    self._check(self._L.x3d_profile_end(self._h, buf, len(buf)))
+    out = json.loads(buf.value.decode())
+    for r in out:
+        r["count"] //= nsteps
+        r["total_ms"] /= nsteps
+    return out
+
+
+X3D.profile_step = _profile_step
 X3D.poisson_init = _poisson_init
 X3D.poisson = _poisson
 X3D.decomp_init = _decomp_init

@@ -248,6 +248,45 @@ int x3d_interzpv(x3d_ctx *ctx, double *tz, const double *uz, double *, double *,
 }
 
 
+// ---- per-launch timing ------------------------------------------------------------------------
+int x3d_profile_begin(x3d_ctx *ctx) {
+  return guard([&] {
+    X3D_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    for (auto &r : ctx->c.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->c.prof.clear();
+    ctx->c.profiling = true;
+  });
+}
+// writes a JSON array [{"name":..,"count":..,"total_ms":..,"avg_ms":..},..] into buf
+int x3d_profile_end(x3d_ctx *ctx, char *buf, int cap) {
+  return guard([&] {
+    Ctx &c = ctx->c;
+    c.profiling = false;
+    X3D_CUDA(cudaStreamSynchronize(c.stream));
+    std::map<std::string, std::pair<int, double>> acc;
+    for (auto &r : c.prof) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      auto &e = acc[r.name];
+      e.first += 1; e.second += ms;
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    c.prof.clear();
+    std::string out = "[";
+    bool first = true;
+    for (auto &kv : acc) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s{\"name\":\"%s\",\"count\":%d,\"total_ms\":%.6f,\"avg_ms\":%.6f}", first ? "" : ",",
+               kv.first.c_str(), kv.second.first, kv.second.second, kv.second.second / kv.second.first);
+      out += line;
+      first = false;
+    }
+    out += "]";
+    if (static_cast<int>(out.size()) + 1 > cap) throw Error("x3d_profile_end: buffer too small");
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+  });
+}
+
 // ---- decomposition / transposes ----------------------------------------------------------
 int x3d_decomp_init(x3d_ctx *ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *id) {
   return guard([&] { decomp_init(ctx->c, nx, ny, nz, p_row, p_col, rank, nranks, id); });

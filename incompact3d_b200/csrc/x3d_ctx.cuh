@@ -18,6 +18,11 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
 };
 
+struct ProfRec {
+  const char *name;
+  cudaEvent_t a, b;
+};
+
 struct PoissonState;
 struct DecompState;
 struct SolverState;
@@ -35,6 +40,9 @@ struct Ctx {
   bool have_dc[3] = {false, false, false}, have_fc[3] = {false, false, false};
   int iibm = 0, istret = 0, iimplicit = 0;
   bool ncl[3] = {true, true, true};
+  // optional per-launch CUDA-event timing (x3d_profile_begin / x3d_profile_end)
+  bool profiling = false;
+  std::vector<ProfRec> prof;
   // caches
   std::map<uint64_t, std::unique_ptr<TriTable>> tri_cache;
   // staging for host-pointer (drop-in) calls
@@ -45,6 +53,25 @@ struct Ctx {
   std::unique_ptr<SolverState> solver;
   Ctx();
   ~Ctx();
+};
+
+// RAII scope that brackets the launches of one kernel class with CUDA events when profiling is on
+struct ProfScope {
+  Ctx &ctx;
+  bool on;
+  ProfRec r{};
+  ProfScope(Ctx &c, const char *name) : ctx(c), on(c.profiling) {
+    if (!on) return;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, ctx.stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, ctx.stream);
+    ctx.prof.push_back(r);
+  }
 };
 
 // device pointer classification: true if p is device (or managed) memory

@@ -79,6 +79,7 @@ void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double 
   const int L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out, ctx.strided_variant);
   if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 1056)");
   const TriTable &T = get_tri(ctx, call.f, call.s, call.w, n_out, L, op.periodic != 0, op.alpha, call.post);
+  ProfScope ps(ctx, call.axis == 0 ? "compact_x(k_contig)" : (call.axis == 1 ? "compact_y(k_strided)" : "compact_z(k_strided)"));
   switch (op.kind) {
     case D1: launch_kind_D1(ctx, op, g, T, d_u, d_t); break;
     case D2: launch_kind_D2(ctx, op, g, T, d_u, d_t); break;

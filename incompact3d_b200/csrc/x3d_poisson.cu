@@ -345,13 +345,21 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     X3D_CUDA(cudaGetLastError()); ctx.launches++;
     fft_in = rw;
   }
-  X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cw)));
-  X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_FORWARD));
+  {
+    ProfScope ps(ctx, "fft_z_r2c(cuFFT)");
+    X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cw)));
+  }
+  {
+    ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
+    X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_FORWARD));
+  }
   auto stage = [&](unsigned mode, const double2 *in, double2 *out) {
+    ProfScope ps(ctx, "poisson_spectral(k_spec)");
     k_spec_stage<<<gs, 256, 0, ctx.stream>>>(a, mode, in, out);
     X3D_CUDA(cudaGetLastError()); ctx.launches++;
   };
   if (!any) {
+    ProfScope ps(ctx, "poisson_spectral(k_spec)");
     k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
     X3D_CUDA(cudaGetLastError()); ctx.launches++;
   } else if (P->bcx == 1 && P->bcy == 0) {  // poisson_100, :472-635
@@ -366,8 +374,14 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     stage(S_PREX, cw, cwb);
     stage(S_PREY | S_ROTZ_B, cwb, cw);
   }
-  X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_INVERSE));
-  X3D_CUFFT(cufftExecZ2D(P->plan_c2r, reinterpret_cast<cufftDoubleComplex *>(cw), any ? rw : d_rhs));
+  {
+    ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
+    X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_INVERSE));
+  }
+  {
+    ProfScope ps(ctx, "fft_z_c2r(cuFFT)");
+    X3D_CUFFT(cufftExecZ2D(P->plan_c2r, reinterpret_cast<cufftDoubleComplex *>(cw), any ? rw : d_rhs));
+  }
   if (any) {
     k_reorder<<<gr, 256, 0, ctx.stream>>>(rw, d_rhs, nx, ny, nz, P->d_map[1][0], P->d_map[1][1], P->d_map[1][2]);
     X3D_CUDA(cudaGetLastError()); ctx.launches++;

@@ -146,6 +146,7 @@ int gridn(const Ctx &ctx, long long n) {
 }
 template <class F>
 void map(Ctx &ctx, long long n, F f) {
+  ProfScope ps(ctx, "elementwise(k_map)");
   k_map<<<gridn(ctx, n), 256, 0, ctx.stream>>>(n, f);
   X3D_CUDA(cudaGetLastError());
   ctx.launches++;
