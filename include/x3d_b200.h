@@ -210,6 +210,17 @@ int x3d_decomp_info_get(x3d_ctx *ctx, int decomp_id, x3d_decomp_info *out);
 /* transpose_x_to_y etc. (call sites src/transeq.f90:163,236,318,437); the
  * complex variants are used on the spectral decomposition sp
  * (src/poisson.f90:759).  Bit-exact data movement.                           */
+/* CPU-only helpers (no context, no GPU): the pencil extents of any rank, and the all-to-all(v)
+ * plan of one transpose (which: 0 x->y, 1 y->z, 2 z->y, 3 y->x): peers (global ranks), element counts
+ * and displacements in the packed buffers, and the local send / receive pencil shapes.              */
+int x3d_decomp_compute(int nx, int ny, int nz, int p_row, int p_col, int rank, x3d_decomp_info *out);
+int x3d_transpose_plan(int nx, int ny, int nz, int p_row, int p_col, int rank, int which, int *npeers,
+                       int *peer_ranks, long long *scount, long long *sdispl, long long *rcount,
+                       long long *rdispl, int *send_dims, int *recv_dims);
+/* the two halves of a transpose, device pointers: pencil -> packed send buffer, packed receive buffer ->
+ * pencil (what x3d_transpose_* runs around the NCCL exchange)                                       */
+int x3d_transpose_pack(x3d_ctx *ctx, int which, const double *src, double *packed, int decomp_id, int complex_);
+int x3d_transpose_unpack(x3d_ctx *ctx, int which, const double *packed, double *dst, int decomp_id, int complex_);
 int x3d_transpose_x_to_y(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
 int x3d_transpose_y_to_z(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
 int x3d_transpose_z_to_y(x3d_ctx *ctx, const double *src, double *dst, int decomp_id);
@@ -252,6 +263,8 @@ int x3d_solver_init_tgv(x3d_ctx *ctx);
 /* set / get the x-pencil velocity fields (host or device pointers) */
 int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, const double *uz);
 int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz);
+/* local x-pencil extents (nx, ny, nz_local) of this rank and its 0-based z offset */
+int x3d_solver_local_shape(x3d_ctx *ctx, int *dims3, int *zstart0);
 /* advance nsteps full time steps (iadvance_time sub-steps each) */
 int x3d_solver_step(x3d_ctx *ctx, int nsteps);
 /* out5 = (eek, eps, eps2, enst, divmax) as postprocess_tgv writes them      */

@@ -261,7 +261,12 @@ def _solver_init(self, nx, ny, nz, ncl=(0, 0, 0, 0, 0, 0), xlx=2 * np.pi, yly=2 
     fn = self._L.x3d_solver_init
     fn.argtypes = [C.c_void_p, C.POINTER(_lib.SolverParams)]
     self._check(fn(self._h, C.byref(p)))
-    self._solver_shape = (int(nx), int(ny), int(nz))
+    d3, z0 = (C.c_int * 3)(), C.c_int()
+    f2 = self._L.x3d_solver_local_shape
+    f2.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    self._check(f2(self._h, d3, C.byref(z0)))
+    self._solver_shape = tuple(d3)
+    self.solver_zstart = z0.value
 
 
 def _solver_init_tgv(self):
@@ -341,3 +346,63 @@ X3D.solver_diagnostics_tgv = _solver_diag
 X3D.solver_divergence = _solver_divergence
 X3D.solver_set_velocity = _solver_set_velocity
 X3D.solver_get_velocity = _solver_get_velocity
+
+
+# ---------------------------------------------------------------------------------------
+# decomposition helpers (CPU only) and the two halves of a transpose
+# ---------------------------------------------------------------------------------------
+TRANSPOSES = {"x_to_y": 0, "y_to_z": 1, "z_to_y": 2, "y_to_x": 3}
+
+
+def decomp_compute(nx, ny, nz, p_row, p_col, rank):
+    """pencil extents of `rank` (1-based inclusive starts/ends like TYPE(DECOMP_INFO)); no GPU needed"""
+    L = _lib.load()
+    info = _lib.DecompInfo()
+    L.x3d_decomp_compute.argtypes = [C.c_int] * 6 + [C.POINTER(_lib.DecompInfo)]
+    if L.x3d_decomp_compute(nx, ny, nz, p_row, p_col, rank, C.byref(info)):
+        raise X3DError(L.x3d_last_error().decode())
+    return {k: list(getattr(info, k)) for k, _ in _lib.DecompInfo._fields_}
+
+
+def transpose_plan(nx, ny, nz, p_row, p_col, rank, which):
+    """all-to-all(v) plan of one transpose for one rank; no GPU needed"""
+    L = _lib.load()
+    w = TRANSPOSES[which] if isinstance(which, str) else int(which)
+    cap = max(p_row, p_col)
+    npeers = C.c_int()
+    peers = (C.c_int * cap)()
+    arrs = [(C.c_longlong * cap)() for _ in range(4)]
+    sd, rd = (C.c_int * 3)(), (C.c_int * 3)()
+    L.x3d_transpose_plan.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.POINTER(C.c_longlong)] * 4 + [C.POINTER(C.c_int)] * 2
+    if L.x3d_transpose_plan(nx, ny, nz, p_row, p_col, rank, w, C.byref(npeers), peers, *arrs, sd, rd):
+        raise X3DError(L.x3d_last_error().decode())
+    n = npeers.value
+    return dict(peers=list(peers[:n]), scount=list(arrs[0][:n]), sdispl=list(arrs[1][:n]), rcount=list(arrs[2][:n]),
+                rdispl=list(arrs[3][:n]), send_dims=list(sd), recv_dims=list(rd))
+
+
+def nccl_unique_id() -> bytes:
+    L = _lib.load()
+    buf = C.create_string_buffer(128)
+    L.x3d_nccl_unique_id.argtypes = [C.c_char_p]
+    if L.x3d_nccl_unique_id(buf):
+        raise X3DError(L.x3d_last_error().decode())
+    return buf.raw
+
+
+def _transpose_pack(self, which, src, packed, decomp_id=0, is_complex=False):
+    keep = []
+    fn = self._L.x3d_transpose_pack
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    self._check(fn(self._h, TRANSPOSES[which], _addr(src, keep), _addr(packed, keep), decomp_id, int(is_complex)))
+
+
+def _transpose_unpack(self, which, packed, dst, decomp_id=0, is_complex=False):
+    keep = []
+    fn = self._L.x3d_transpose_unpack
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    self._check(fn(self._h, TRANSPOSES[which], _addr(packed, keep), _addr(dst, keep), decomp_id, int(is_complex)))
+
+
+X3D.transpose_pack = _transpose_pack
+X3D.transpose_unpack = _transpose_unpack

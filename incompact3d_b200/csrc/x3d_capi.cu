@@ -18,10 +18,18 @@ void solver_diagnostics_tgv(Ctx &ctx, double *out5);
 void solver_divergence(Ctx &ctx, double *divmax, double *divmean);
 void solver_set_velocity(Ctx &ctx, const double *ux, const double *uy, const double *uz);
 void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz);
+void solver_local_shape(Ctx &ctx, int *d3, int *z0);
 void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id);
 int decomp_info_init(Ctx &ctx, int nx, int ny, int nz);
 void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out);
 void transpose(Ctx &ctx, int which, const double *src, double *dst, int id, int elem);
+void transpose_pack(Ctx &ctx, int which, const double *d_src, double *d_packed, int id, int elem);
+void transpose_unpack(Ctx &ctx, int which, const double *d_packed, double *d_dst, int id, int elem);
+void nccl_unique_id(void *out128);
+void decomp_compute(int nx, int ny, int nz, int p_row, int p_col, int rank, x3d_decomp_info *out);
+void transpose_plan_host(int nx, int ny, int nz, int p_row, int p_col, int rank, int which, int *npeers, int *peer_ranks,
+                         long long *scount, long long *sdispl, long long *rcount, long long *rdispl, int *send_dims,
+                         int *recv_dims);
 }
 
 struct x3d_ctx {
@@ -292,13 +300,29 @@ int x3d_decomp_init(x3d_ctx *ctx, int nx, int ny, int nz, int p_row, int p_col, 
   return guard([&] { decomp_init(ctx->c, nx, ny, nz, p_row, p_col, rank, nranks, id); });
 }
 int x3d_nccl_unique_id(void *out128) {
-  return guard([&] { (void)out128; throw Error("x3d_nccl_unique_id: NCCL path not wired yet"); });
+  return guard([&] { nccl_unique_id(out128); });
 }
 int x3d_decomp_info_init(x3d_ctx *ctx, int nx, int ny, int nz, int *decomp_id) {
   return guard([&] { *decomp_id = decomp_info_init(ctx->c, nx, ny, nz); });
 }
 int x3d_decomp_info_get(x3d_ctx *ctx, int decomp_id, x3d_decomp_info *out) {
   return guard([&] { decomp_info_get(ctx->c, decomp_id, out); });
+}
+int x3d_decomp_compute(int nx, int ny, int nz, int p_row, int p_col, int rank, x3d_decomp_info *out) {
+  return guard([&] { decomp_compute(nx, ny, nz, p_row, p_col, rank, out); });
+}
+int x3d_transpose_plan(int nx, int ny, int nz, int p_row, int p_col, int rank, int which, int *npeers, int *peer_ranks,
+                       long long *scount, long long *sdispl, long long *rcount, long long *rdispl, int *send_dims,
+                       int *recv_dims) {
+  return guard([&] {
+    transpose_plan_host(nx, ny, nz, p_row, p_col, rank, which, npeers, peer_ranks, scount, sdispl, rcount, rdispl, send_dims, recv_dims);
+  });
+}
+int x3d_transpose_pack(x3d_ctx *ctx, int which, const double *src, double *packed, int decomp_id, int complex_) {
+  return guard([&] { transpose_pack(ctx->c, which, src, packed, decomp_id, complex_ ? 2 : 1); });
+}
+int x3d_transpose_unpack(x3d_ctx *ctx, int which, const double *packed, double *dst, int decomp_id, int complex_) {
+  return guard([&] { transpose_unpack(ctx->c, which, packed, dst, decomp_id, complex_ ? 2 : 1); });
 }
 #define X3D_DEF_TR(name, which)                                                                            \
   int x3d_transpose_##name(x3d_ctx *ctx, const double *src, double *dst, int id) {                         \
@@ -342,6 +366,9 @@ int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, co
 }
 int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz) {
   return guard([&] { solver_get_velocity(ctx->c, ux, uy, uz); });
+}
+int x3d_solver_local_shape(x3d_ctx *ctx, int *dims3, int *zstart0) {
+  return guard([&] { solver_local_shape(ctx->c, dims3, zstart0); });
 }
 int x3d_solver_step(x3d_ctx *ctx, int nsteps) { return guard([&] { solver_step(ctx->c, nsteps); }); }
 int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5) { return guard([&] { solver_diagnostics_tgv(ctx->c, out5); }); }

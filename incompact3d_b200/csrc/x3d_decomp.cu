@@ -5,8 +5,16 @@
 // Distribution rule of 2DECOMP&FFT: an extent n over p ranks gives n/p points each, the LAST
 // mod(n,p) ranks get one more.  The process grid is p_row x p_col; rank = row*p_col + col
 // (MPI_CART row-major).  x-pencil (nx, ny/p_row, nz/p_col), y-pencil (nx/p_row, ny, nz/p_col),
-// z-pencil (nx/p_row, ny/p_col, nz).  x<->y exchanges inside a column group of p_row ranks,
-// y<->z inside a row group of p_col ranks.
+// z-pencil (nx/p_row, ny/p_col, nz).  x<->y exchanges inside the p_row ranks that share a
+// column index, y<->z inside the p_col ranks that share a row index.
+//
+// A transpose is  pack kernel -> all-to-all(v) -> unpack kernel.  The exchange is a grouped
+// ncclSend/ncclRecv over NVLink/NVSwitch (NCCL resolved at run time from the libnccl already
+// loaded in the process, so that the library has no link-time NCCL dependency).  One rank (or
+// one rank per group) degenerates to a bit-exact device copy.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstring>
 #include "x3d_state.cuh"
 
 namespace x3d {
@@ -14,38 +22,181 @@ namespace x3d {
 void distribute(int n, int p, std::vector<int> &st, std::vector<int> &sz) {
   st.assign(p, 0); sz.assign(p, 0);
   const int base = n / p, rem = n % p;
-  int s = 1;
+  int s = 0;
   for (int r = 0; r < p; ++r) {
     sz[r] = base + (r >= p - rem ? 1 : 0);
-    st[r] = s;
+    st[r] = s;  // 0-based
     s += sz[r];
   }
 }
 
+// ---- NCCL, resolved lazily --------------------------------------------------------------------
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi &nccl() {
+  static NcclApi api;
+  if (api.h) return api;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) { api.h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (api.h) break; }  // already in the process (torch)
+  if (!api.h)
+    for (const char *nm : names) { api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+  if (!api.h) throw Error(std::string("cannot load libnccl: ") + dlerror());
+#define X3D_SYM(field, name)                                                          \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.h, name));               \
+  if (!api.field) throw Error(std::string("libnccl lacks ") + name)
+  X3D_SYM(GetUniqueId, "ncclGetUniqueId"); X3D_SYM(CommInitRank, "ncclCommInitRank"); X3D_SYM(CommSplit, "ncclCommSplit");
+  X3D_SYM(CommDestroy, "ncclCommDestroy"); X3D_SYM(Send, "ncclSend"); X3D_SYM(Recv, "ncclRecv");
+  X3D_SYM(AllReduce, "ncclAllReduce"); X3D_SYM(GroupStart, "ncclGroupStart"); X3D_SYM(GroupEnd, "ncclGroupEnd");
+  X3D_SYM(GetErrorString, "ncclGetErrorString");
+#undef X3D_SYM
+  return api;
+}
+#define X3D_NCCL(call)                                                                                 \
+  do {                                                                                                 \
+    ncclResult_t r_ = (call);                                                                          \
+    if (r_ != ncclSuccess) throw ::x3d::Error(std::string(#call) + ": " + nccl().GetErrorString(r_));  \
+  } while (0)
+
+// ---- plans ------------------------------------------------------------------------------------------
+struct SidePlan {       // how one pencil array maps onto the packed exchange buffer
+  int dims[3];          // local pencil extents
+  int axis;             // direction that is cut into per-peer blocks
+  std::vector<int> blk_start, blk_size;     // per peer, along `axis` (local 0-based coordinates)
+  std::vector<long long> disp, count;       // per peer, in elements
+  int *d_meta = nullptr;                    // device: blk_of[dims[axis]] | blk_start[np] | blk_size[np]
+  long long *d_disp = nullptr;
+};
+struct TransposePlan {
+  int npeers = 1;
+  SidePlan send, recv;
+  bool built = false;
+};
+
 struct DecompImpl : DecompState {
   int nx = 0, ny = 0, nz = 0, p_row = 1, p_col = 1, rank = 0, nranks = 1;
   int row = 0, col = 0;
+  bool have_nccl = false;
+  ncclComm_t world = nullptr, comm_row = nullptr, comm_col = nullptr;  // comm_row: the p_row ranks of my column (x<->y)
   std::vector<x3d_decomp_info> infos;
-  std::vector<int> dims;  // 3 per info
+  std::vector<std::array<int, 3>> gdims;
+  std::vector<std::array<TransposePlan, 4>> plans;
+  DevBuf sendbuf, recvbuf, meta;
+  std::vector<void *> dev_allocs;
+  ~DecompImpl() override {
+    for (void *p : dev_allocs) cudaFree(p);
+    if (have_nccl) {
+      if (comm_row) nccl().CommDestroy(comm_row);
+      if (comm_col) nccl().CommDestroy(comm_col);
+      if (world) nccl().CommDestroy(world);
+    }
+  }
 };
 
-static x3d_decomp_info make_info(const DecompImpl &D, int nx, int ny, int nz) {
+static x3d_decomp_info make_info(int p_row, int p_col, int row, int col, int nx, int ny, int nz) {
   x3d_decomp_info I{};
   std::vector<int> st, sz;
-  auto setp = [&](int *s, int *e, int *z, int d, int lo, int n) { s[d] = lo; z[d] = n; e[d] = lo + n - 1; };
-  // x-pencil: x complete, y split by p_row (row index), z split by p_col (col index)
-  setp(I.xst, I.xen, I.xsz, 0, 1, nx);
-  distribute(ny, D.p_row, st, sz); setp(I.xst, I.xen, I.xsz, 1, st[D.row], sz[D.row]);
-  distribute(nz, D.p_col, st, sz); setp(I.xst, I.xen, I.xsz, 2, st[D.col], sz[D.col]);
-  // y-pencil: x split by p_row, y complete, z split by p_col
-  distribute(nx, D.p_row, st, sz); setp(I.yst, I.yen, I.ysz, 0, st[D.row], sz[D.row]);
-  setp(I.yst, I.yen, I.ysz, 1, 1, ny);
-  distribute(nz, D.p_col, st, sz); setp(I.yst, I.yen, I.ysz, 2, st[D.col], sz[D.col]);
-  // z-pencil: x split by p_row, y split by p_col, z complete
-  distribute(nx, D.p_row, st, sz); setp(I.zst, I.zen, I.zsz, 0, st[D.row], sz[D.row]);
-  distribute(ny, D.p_col, st, sz); setp(I.zst, I.zen, I.zsz, 1, st[D.col], sz[D.col]);
-  setp(I.zst, I.zen, I.zsz, 2, 1, nz);
+  auto setp = [&](int *s, int *e, int *z, int d, int lo0, int n) { s[d] = lo0 + 1; z[d] = n; e[d] = lo0 + n; };
+  setp(I.xst, I.xen, I.xsz, 0, 0, nx);
+  distribute(ny, p_row, st, sz); setp(I.xst, I.xen, I.xsz, 1, st[row], sz[row]);
+  distribute(nz, p_col, st, sz); setp(I.xst, I.xen, I.xsz, 2, st[col], sz[col]);
+  distribute(nx, p_row, st, sz); setp(I.yst, I.yen, I.ysz, 0, st[row], sz[row]);
+  setp(I.yst, I.yen, I.ysz, 1, 0, ny);
+  distribute(nz, p_col, st, sz); setp(I.yst, I.yen, I.ysz, 2, st[col], sz[col]);
+  distribute(nx, p_row, st, sz); setp(I.zst, I.zen, I.zsz, 0, st[row], sz[row]);
+  distribute(ny, p_col, st, sz); setp(I.zst, I.zen, I.zsz, 1, st[col], sz[col]);
+  setp(I.zst, I.zen, I.zsz, 2, 0, nz);
   return I;
+}
+
+void decomp_compute(int nx, int ny, int nz, int p_row, int p_col, int rank, x3d_decomp_info *out) {
+  if (p_row < 1 || p_col < 1 || rank < 0 || rank >= p_row * p_col) throw Error("x3d_decomp_compute: bad process grid");
+  *out = make_info(p_row, p_col, rank / p_col, rank % p_col, nx, ny, nz);
+}
+
+// which: 0 x->y, 1 y->z, 2 z->y, 3 y->x.  Host-only description of the exchange of rank (row,col).
+static void build_plan_host(int p_row, int p_col, int row, int col, int nx, int ny, int nz, int which, TransposePlan &T) {
+  std::vector<int> xs, xz, yxs, yxz, ycs, ycz, zs, zz;
+  distribute(nx, p_row, xs, xz);     // x split (y- and z-pencils)
+  distribute(ny, p_row, yxs, yxz);   // y split in x-pencils
+  distribute(ny, p_col, ycs, ycz);   // y split in z-pencils
+  distribute(nz, p_col, zs, zz);     // z split (x- and y-pencils)
+  const bool xy = (which == 0 || which == 3);
+  const int np = xy ? p_row : p_col;
+  const int me = xy ? row : col;
+  T.npeers = np;
+  auto side = [&](SidePlan &S, int d0, int d1, int d2, int axis, const std::vector<int> &bs, const std::vector<int> &bz) {
+    S.dims[0] = d0; S.dims[1] = d1; S.dims[2] = d2; S.axis = axis;
+    S.blk_start = bs; S.blk_size = bz;
+    S.disp.assign(np, 0); S.count.assign(np, 0);
+    long long off = 0;
+    for (int m = 0; m < np; ++m) {
+      long long c = 1;
+      for (int d = 0; d < 3; ++d) c *= (d == axis ? bz[m] : S.dims[d]);
+      S.count[m] = c; S.disp[m] = off; off += c;
+    }
+  };
+  const int X[3] = {nx, yxz[row], zz[col]}, Y[3] = {xz[row], ny, zz[col]}, Z[3] = {xz[row], ycz[col], nz};
+  (void)me;
+  switch (which) {
+    case 0: side(T.send, X[0], X[1], X[2], 0, xs, xz); side(T.recv, Y[0], Y[1], Y[2], 1, yxs, yxz); break;   // x->y
+    case 3: side(T.send, Y[0], Y[1], Y[2], 1, yxs, yxz); side(T.recv, X[0], X[1], X[2], 0, xs, xz); break;   // y->x
+    case 1: side(T.send, Y[0], Y[1], Y[2], 1, ycs, ycz); side(T.recv, Z[0], Z[1], Z[2], 2, zs, zz); break;   // y->z
+    case 2: side(T.send, Z[0], Z[1], Z[2], 2, zs, zz); side(T.recv, Y[0], Y[1], Y[2], 1, ycs, ycz); break;   // z->y
+    default: throw Error("bad transpose selector");
+  }
+}
+
+// CPU-only: the exchange plan of one rank (tests drive a gloo all-to-all with it)
+void transpose_plan_host(int nx, int ny, int nz, int p_row, int p_col, int rank, int which, int *npeers, int *peer_ranks,
+                         long long *scount, long long *sdispl, long long *rcount, long long *rdispl, int *send_dims,
+                         int *recv_dims) {
+  TransposePlan T;
+  const int row = rank / p_col, col = rank % p_col;
+  build_plan_host(p_row, p_col, row, col, nx, ny, nz, which, T);
+  *npeers = T.npeers;
+  const bool xy = (which == 0 || which == 3);
+  for (int m = 0; m < T.npeers; ++m) {
+    peer_ranks[m] = xy ? m * p_col + col : row * p_col + m;
+    scount[m] = T.send.count[m]; sdispl[m] = T.send.disp[m];
+    rcount[m] = T.recv.count[m]; rdispl[m] = T.recv.disp[m];
+  }
+  for (int d = 0; d < 3; ++d) { send_dims[d] = T.send.dims[d]; recv_dims[d] = T.recv.dims[d]; }
+}
+
+// ---- pack / unpack kernels ------------------------------------------------------------------------
+// arr: local pencil (d0,d1,d2); the extent along `axis` is cut into blocks, block m goes to / comes from
+// peer m and is stored contiguously (natural order of the sub-box) at packed + disp[m].
+template <typename T, bool PACK>
+__global__ void k_boxcopy(T *__restrict__ packed, T *__restrict__ arr, int d0, int d1, int d2, int axis,
+                          const int *__restrict__ blk_of, const int *__restrict__ blk_start, const int *__restrict__ blk_size,
+                          const long long *__restrict__ disp) {
+  const long long tot = static_cast<long long>(d0) * d1 * d2;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < tot;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % d0);
+    const int j = static_cast<int>((idx / d0) % d1);
+    const int k = static_cast<int>(idx / (static_cast<long long>(d0) * d1));
+    const int c = axis == 0 ? i : (axis == 1 ? j : k);
+    const int m = blk_of[c];
+    const int cl = c - blk_start[m], bs = blk_size[m];
+    long long off;
+    if (axis == 0) off = cl + static_cast<long long>(bs) * (j + static_cast<long long>(d1) * k);
+    else if (axis == 1) off = i + static_cast<long long>(d0) * (cl + static_cast<long long>(bs) * k);
+    else off = i + static_cast<long long>(d0) * (j + static_cast<long long>(d1) * cl);
+    if (PACK) packed[disp[m] + off] = arr[idx];
+    else arr[idx] = packed[disp[m] + off];
+  }
 }
 
 static DecompImpl &DEC(Ctx &ctx) {
@@ -54,23 +205,68 @@ static DecompImpl &DEC(Ctx &ctx) {
   return *D;
 }
 
+static void upload_side(Ctx &ctx, DecompImpl &D, SidePlan &S) {
+  const int np = static_cast<int>(S.blk_start.size());
+  const int ext = S.dims[S.axis];
+  std::vector<int> meta(ext + 2 * np);
+  for (int m = 0; m < np; ++m)
+    for (int q = 0; q < S.blk_size[m]; ++q) meta[S.blk_start[m] + q] = m;
+  for (int m = 0; m < np; ++m) { meta[ext + m] = S.blk_start[m]; meta[ext + np + m] = S.blk_size[m]; }
+  X3D_CUDA(cudaMalloc(&S.d_meta, meta.size() * sizeof(int)));
+  X3D_CUDA(cudaMalloc(&S.d_disp, np * sizeof(long long)));
+  D.dev_allocs.push_back(S.d_meta); D.dev_allocs.push_back(S.d_disp);
+  X3D_CUDA(cudaMemcpyAsync(S.d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(S.d_disp, S.disp.data(), np * sizeof(long long), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+static TransposePlan &get_plan(Ctx &ctx, DecompImpl &D, int id, int which) {
+  if (id < 0 || id >= static_cast<int>(D.infos.size())) throw Error("bad decomposition id");
+  TransposePlan &T = D.plans[id][which];
+  if (!T.built) {
+    build_plan_host(D.p_row, D.p_col, D.row, D.col, D.gdims[id][0], D.gdims[id][1], D.gdims[id][2], which, T);
+    upload_side(ctx, D, T.send);
+    upload_side(ctx, D, T.recv);
+    T.built = true;
+  }
+  return T;
+}
+
 void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id) {
+  X3D_CUDA(cudaSetDevice(ctx.device));
   if (p_row < 1 || p_col < 1 || p_row * p_col != nranks) throw Error("x3d_decomp_init: p_row*p_col must equal nranks");
   if (rank < 0 || rank >= nranks) throw Error("x3d_decomp_init: bad rank");
-  if (nranks > 1) throw Error("x3d_decomp_init: multi-rank transposes (NCCL) not wired yet");
-  (void)nccl_id;
   auto D = std::make_unique<DecompImpl>();
   D->nx = nx; D->ny = ny; D->nz = nz; D->p_row = p_row; D->p_col = p_col; D->rank = rank; D->nranks = nranks;
   D->row = rank / p_col; D->col = rank % p_col;
-  D->infos.push_back(make_info(*D, nx, ny, nz));
-  D->dims = {nx, ny, nz};
+  D->infos.push_back(make_info(p_row, p_col, D->row, D->col, nx, ny, nz));
+  D->gdims.push_back({nx, ny, nz});
+  D->plans.emplace_back();
+  if (nranks > 1 && nccl_id) {
+    NcclApi &N = nccl();
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    std::memcpy(&id, nccl_id, sizeof(id));
+    X3D_NCCL(N.CommInitRank(&D->world, nranks, id, rank));
+    // x<->y: ranks sharing my column index; y<->z: ranks sharing my row index
+    X3D_NCCL(N.CommSplit(D->world, D->col, D->row, &D->comm_row, nullptr));
+    X3D_NCCL(N.CommSplit(D->world, D->row, D->col, &D->comm_col, nullptr));
+    D->have_nccl = true;
+  }
   ctx.decomp = std::move(D);
+}
+
+void nccl_unique_id(void *out128) {
+  ncclUniqueId id;
+  X3D_NCCL(nccl().GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
 }
 
 int decomp_info_init(Ctx &ctx, int nx, int ny, int nz) {
   DecompImpl &D = DEC(ctx);
-  D.infos.push_back(make_info(D, nx, ny, nz));
-  D.dims.insert(D.dims.end(), {nx, ny, nz});
+  D.infos.push_back(make_info(D.p_row, D.p_col, D.row, D.col, nx, ny, nz));
+  D.gdims.push_back({nx, ny, nz});
+  D.plans.emplace_back();
   return static_cast<int>(D.infos.size()) - 1;
 }
 
@@ -80,21 +276,96 @@ void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out) {
   *out = D.infos[id];
 }
 
-// which: 0 x->y, 1 y->z, 2 z->y, 3 y->x ; elem = doubles per element (1 real, 2 complex)
+static int grid_for(const Ctx &ctx, long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = static_cast<long long>(ctx.sm_count) * 16;
+  return static_cast<int>(b < cap ? b : cap);
+}
+
+template <bool PACK>
+static void boxcopy(Ctx &ctx, const SidePlan &S, double *packed, double *arr, int elem) {
+  const long long tot = static_cast<long long>(S.dims[0]) * S.dims[1] * S.dims[2];
+  if (tot == 0) return;
+  const int ext = S.dims[S.axis], np = static_cast<int>(S.blk_start.size());
+  const int *blk_of = S.d_meta, *bst = S.d_meta + ext, *bsz = S.d_meta + ext + np;
+  ProfScope ps(ctx, PACK ? "transpose_pack(k_boxcopy)" : "transpose_unpack(k_boxcopy)");
+  if (elem == 1)
+    k_boxcopy<double, PACK><<<grid_for(ctx, tot), 256, 0, ctx.stream>>>(packed, arr, S.dims[0], S.dims[1], S.dims[2], S.axis, blk_of, bst, bsz, S.d_disp);
+  else
+    k_boxcopy<double2, PACK><<<grid_for(ctx, tot), 256, 0, ctx.stream>>>(reinterpret_cast<double2 *>(packed), reinterpret_cast<double2 *>(arr),
+                                                                     S.dims[0], S.dims[1], S.dims[2], S.axis, blk_of, bst, bsz, S.d_disp);
+  X3D_CUDA(cudaGetLastError());
+  ctx.launches++;
+}
+
+void transpose_pack(Ctx &ctx, int which, const double *d_src, double *d_packed, int id, int elem) {
+  DecompImpl &D = DEC(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  boxcopy<true>(ctx, get_plan(ctx, D, id, which).send, d_packed, const_cast<double *>(d_src), elem);
+}
+void transpose_unpack(Ctx &ctx, int which, const double *d_packed, double *d_dst, int id, int elem) {
+  DecompImpl &D = DEC(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  boxcopy<false>(ctx, get_plan(ctx, D, id, which).recv, const_cast<double *>(d_packed), d_dst, elem);
+}
+
+// device pointers; src and dst pencils of decomposition `id`
+void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem) {
+  DecompImpl &D = DEC(ctx);
+  TransposePlan &T = get_plan(ctx, D, id, which);
+  const long long ns = static_cast<long long>(T.send.dims[0]) * T.send.dims[1] * T.send.dims[2];
+  const long long nr = static_cast<long long>(T.recv.dims[0]) * T.recv.dims[1] * T.recv.dims[2];
+  if (T.npeers == 1) {  // the group has one rank: pencils coincide, bit-exact copy
+    if (d_src != d_dst) X3D_CUDA(cudaMemcpyAsync(d_dst, d_src, ns * elem * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    return;
+  }
+  if (!D.have_nccl) throw Error("transpose: this context was initialised without a NCCL id (pack/unpack only)");
+  D.sendbuf.reserve(ns * elem * sizeof(double));
+  D.recvbuf.reserve(nr * elem * sizeof(double));
+  double *sb = static_cast<double *>(D.sendbuf.p), *rb = static_cast<double *>(D.recvbuf.p);
+  boxcopy<true>(ctx, T.send, sb, const_cast<double *>(d_src), elem);
+  {
+    ProfScope ps(ctx, "transpose_alltoall(NCCL)");
+    NcclApi &N = nccl();
+    ncclComm_t comm = (which == 0 || which == 3) ? D.comm_row : D.comm_col;
+    X3D_NCCL(N.GroupStart());
+    for (int m = 0; m < T.npeers; ++m) {
+      if (T.send.count[m]) X3D_NCCL(N.Send(sb + T.send.disp[m] * elem, T.send.count[m] * elem, ncclDouble, m, comm, ctx.stream));
+      if (T.recv.count[m]) X3D_NCCL(N.Recv(rb + T.recv.disp[m] * elem, T.recv.count[m] * elem, ncclDouble, m, comm, ctx.stream));
+    }
+    X3D_NCCL(N.GroupEnd());
+  }
+  boxcopy<false>(ctx, T.recv, rb, d_dst, elem);
+}
+
+// host-or-device entry of the C ABI
 void transpose(Ctx &ctx, int which, const double *src, double *dst, int id, int elem) {
   DecompImpl &D = DEC(ctx);
   X3D_CUDA(cudaSetDevice(ctx.device));
-  if (id < 0 || id >= static_cast<int>(D.infos.size())) throw Error("bad decomposition id");
-  const x3d_decomp_info &I = D.infos[id];
-  const int *ssz = (which == 0) ? I.xsz : (which == 1 || which == 3) ? I.ysz : I.zsz;
-  const size_t bytes = static_cast<size_t>(ssz[0]) * ssz[1] * ssz[2] * elem * sizeof(double);
-  if (D.nranks == 1) {
-    // one rank: all pencils coincide; the transpose is a plain (bit-exact) copy
-    if (src != dst) X3D_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx.stream));
-    if (!is_device_ptr(dst) || !is_device_ptr(src)) X3D_CUDA(cudaStreamSynchronize(ctx.stream));
-    return;
-  }
-  throw Error("multi-rank transpose not wired yet");
+  TransposePlan &T = get_plan(ctx, D, id, which);
+  const size_t bs = static_cast<size_t>(T.send.dims[0]) * T.send.dims[1] * T.send.dims[2] * elem * sizeof(double);
+  const size_t br = static_cast<size_t>(T.recv.dims[0]) * T.recv.dims[1] * T.recv.dims[2] * elem * sizeof(double);
+  const bool sdev = is_device_ptr(src), ddev = is_device_ptr(dst);
+  const double *ds = src;
+  double *dd = dst;
+  if (!sdev) { ctx.stage_in.reserve(bs); X3D_CUDA(cudaMemcpyAsync(ctx.stage_in.p, src, bs, cudaMemcpyHostToDevice, ctx.stream)); ds = static_cast<double *>(ctx.stage_in.p); }
+  if (!ddev) { ctx.stage_out.reserve(br); dd = static_cast<double *>(ctx.stage_out.p); }
+  transpose_device(ctx, which, ds, dd, id, elem);
+  if (!ddev) X3D_CUDA(cudaMemcpyAsync(dst, dd, br, cudaMemcpyDeviceToHost, ctx.stream));
+  if (!sdev || !ddev) X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+// sum / max all-reduce of a few doubles on the device (diagnostics; navier.f90:360-361)
+void allreduce(Ctx &ctx, double *d_buf, int n, bool is_max) {
+  auto *D = dynamic_cast<DecompImpl *>(ctx.decomp.get());
+  if (!D || D->nranks == 1) return;
+  if (!D->have_nccl) throw Error("allreduce: no NCCL communicator");
+  X3D_NCCL(nccl().AllReduce(d_buf, d_buf, n, ncclDouble, is_max ? ncclMax : ncclSum, D->world, ctx.stream));
+}
+
+void decomp_shape(Ctx &ctx, int *p_row, int *p_col, int *rank, int *nranks) {
+  DecompImpl &D = DEC(ctx);
+  *p_row = D.p_row; *p_col = D.p_col; *rank = D.rank; *nranks = D.nranks;
 }
 
 }  // namespace x3d

@@ -15,6 +15,11 @@
 
 namespace x3d {
 
+int decomp_info_init(Ctx &ctx, int nx, int ny, int nz);
+void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out);
+void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem);
+void decomp_shape(Ctx &ctx, int *p_row, int *p_col, int *rank, int *nranks);
+
 #define X3D_CUFFT(call)                                                                         \
   do {                                                                                          \
     cufftResult r_ = (call);                                                                    \
@@ -24,12 +29,17 @@ namespace x3d {
 
 struct PoissonImpl : PoissonState {
   x3d_poisson_params p{};
-  int nx = 0, ny = 0, nz = 0, nzh = 0;  // pressure mesh
+  int nx = 0, ny = 0, nz = 0, nzh = 0;  // pressure mesh (global)
   int bcx = 0, bcy = 0, bcz = 0;
+  // slab decomposition (p_row = 1): physical z-pencil (nx, nyl, nz), spectral y-pencil (nx, ny, nzhl)
+  int nranks = 1, id_ph = -1, id_sp = -1;
+  int nyl = 0, nzl = 0, nzhl = 0, k0 = 0;
+  DevBuf cwz, rwork2;
   cufftHandle plan_r2c = 0, plan_c2r = 0, plan_xy = 0;
   bool plans = false;
   DevBuf cw, cwb, rwork, tables, fftwork, maps;
   int *d_map[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [backward][axis]
+  int *d_idx = nullptr;  // identity map (for axes that are split across ranks)
   // device table layout (doubles): ax,bx[nx] ay,by[ny] az,bz[nzh] | xk2[nx] yk2[ny] zk2[nzh][2] | tx[nx] ty[ny] tz[nzh][2]
   double *d_ax = nullptr, *d_bx = nullptr, *d_ay = nullptr, *d_by = nullptr, *d_az = nullptr, *d_bz = nullptr;
   double *d_xk2 = nullptr, *d_yk2 = nullptr, *d_zk2 = nullptr, *d_tx = nullptr, *d_ty = nullptr, *d_tz = nullptr;
@@ -43,7 +53,8 @@ namespace {
 constexpr double EPS = 1.e-16;  // src/poisson.f90:25
 
 struct SpecArgs {
-  int nx, ny, nzh, nz;
+  int nx, ny, nzh, nz;  // nzh = LOCAL number of spectral z planes; global plane = k + k0
+  int k0;
   int bcx, bcy, bcz;
   double norm_x, norm_y, norm_z;
   const double *ax, *bx, *ay, *by, *az, *bz;
@@ -51,7 +62,8 @@ struct SpecArgs {
 };
 
 // modified wavenumber of mode (i,j,k): (re,im) pair, src/poisson.f90:1733-1738 / :1787-1800
-__device__ __forceinline__ double2 kxyz_of(const SpecArgs &a, int i, int j, int k) {
+__device__ __forceinline__ double2 kxyz_of(const SpecArgs &a, int i, int j, int kl) {
+  const int k = kl + a.k0;
   const double fx = a.tx[i], fy = a.ty[j];
   const double fzr = a.tz[2 * k], fzi = a.tz[2 * k + 1];
   const double xk = a.xk2[i], yk = a.yk2[j];
@@ -84,7 +96,8 @@ __global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(idx % a.nx);
     const int j = static_cast<int>((idx / a.nx) % a.ny);
-    const int k = static_cast<int>(idx / (static_cast<long long>(a.nx) * a.ny));
+    const int kl = static_cast<int>(idx / (static_cast<long long>(a.nx) * a.ny));
+    const int k = kl + a.k0;
     double2 c = cw[idx];
     c.x = c.x / a.norm_x / a.norm_y / a.norm_z;
     c.y = c.y / a.norm_x / a.norm_y / a.norm_z;
@@ -93,7 +106,7 @@ __global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
     if (j + 1 > a.ny / 2 + 1) c = neg(c);
     c = rot_fwd(c, a.ax[i], a.bx[i]);
     if (i + 1 > a.nx / 2 + 1) c = neg(c);
-    const double2 kk = kxyz_of(a, i, j, k);
+    const double2 kk = kxyz_of(a, i, j, kl);
     if (kk.x < EPS || kk.y < EPS) c = make_double2(0.0, 0.0);  // :366
     else c = make_double2(c.x / (-kk.x), c.y / (-kk.y));
     c = make_double2(c.x * a.bz[k] - c.y * a.az[k], -c.y * a.bz[k] - c.x * a.az[k]);  // :381-384
@@ -111,7 +124,8 @@ __global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
 enum : unsigned { S_NORM = 1, S_ROTZ_F = 2, S_ROTY_F = 4, S_ROTX_F = 8, S_POSTY = 16, S_POSTX = 32, S_DIVIDE = 64,
                   S_ZERO010 = 128, S_PREX = 256, S_PREY = 512, S_ROTX_B = 1024, S_ROTY_B = 2048, S_ROTZ_B = 4096 };
 
-__device__ __forceinline__ double2 pointwise_fwd(const SpecArgs &a, unsigned mode, double2 c, int i, int j, int k) {
+__device__ __forceinline__ double2 pointwise_fwd(const SpecArgs &a, unsigned mode, double2 c, int i, int j, int kl) {
+  const int k = kl + a.k0;
   if (mode & S_NORM) { c.x = c.x / a.norm_x / a.norm_y / a.norm_z; c.y = c.y / a.norm_x / a.norm_y / a.norm_z; }
   if (mode & S_ROTZ_F) c = rot_fwd(c, a.az[k], a.bz[k]);
   if (mode & S_ROTY_F) { c = rot_fwd(c, a.ay[j], a.by[j]); if (j + 1 > a.ny / 2 + 1) c = neg(c); }
@@ -144,7 +158,7 @@ __global__ void k_spec_stage(SpecArgs a, unsigned mode, const double2 *__restric
       }
     }
     if (mode & S_DIVIDE) c = divide4(c, kxyz_of(a, i, j, k));
-    if (mode & S_ZERO010) { if (i + 1 == a.nx / 2 + 1 && k + 1 == a.nz / 2 + 1) c = make_double2(0.0, 0.0); }  // :902-908
+    if (mode & S_ZERO010) { if (i + 1 == a.nx / 2 + 1 && k + a.k0 + 1 == a.nz / 2 + 1) c = make_double2(0.0, 0.0); }  // :902-908
     if (mode & S_PREX) {
       if (i > 0) c = dct_pre(c, in[(a.nx - i) + a.nx * static_cast<long long>(j) + sxy * k], a.ax[i], a.bx[i]);
     }
@@ -153,7 +167,7 @@ __global__ void k_spec_stage(SpecArgs a, unsigned mode, const double2 *__restric
     }
     if (mode & S_ROTX_B) { c = rot_bwd(c, a.ax[i], a.bx[i]); if (i + 1 > a.nx / 2 + 1) c = neg(c); }
     if (mode & S_ROTY_B) { c = rot_bwd(c, a.ay[j], a.by[j]); if (j + 1 > a.ny / 2 + 1) c = neg(c); }
-    if (mode & S_ROTZ_B) c = rot_bwd(c, a.az[k], a.bz[k]);
+    if (mode & S_ROTZ_B) c = rot_bwd(c, a.az[k + a.k0], a.bz[k + a.k0]);
     out[idx] = c;
   }
 }
@@ -300,68 +314,125 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
         off[bw][a] = hm.size();
         hm.insert(hm.end(), m.begin(), m.end());
       }
+    const size_t o_idx = hm.size();
+    for (int q = 0; q < std::max(nx, std::max(ny, nz)); ++q) hm.push_back(q);
     P->maps.reserve(hm.size() * sizeof(int));
     X3D_CUDA(cudaMemcpyAsync(P->maps.p, hm.data(), hm.size() * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
     X3D_CUDA(cudaStreamSynchronize(ctx.stream));
     for (int bw = 0; bw < 2; ++bw)
       for (int a = 0; a < 3; ++a) P->d_map[bw][a] = static_cast<int *>(P->maps.p) + off[bw][a];
+    P->d_idx = static_cast<int *>(P->maps.p) + o_idx;
   }
-  // FFT plans
+  // decomposition: one rank, or slabs (p_row = 1) when x3d_decomp_init was called with several ranks
+  P->nranks = 1;
+  P->nyl = ny; P->nzl = nz; P->nzhl = nzh; P->k0 = 0;
+  if (ctx.decomp) {
+    int pr, pc, rk, nr;
+    decomp_shape(ctx, &pr, &pc, &rk, &nr);
+    if (nr > 1) {
+      if (pr != 1) throw Error("x3d_poisson_init: the distributed solver uses slabs (p_row = 1)");
+      P->nranks = nr;
+      P->id_ph = decomp_info_init(ctx, nx, ny, nz);
+      P->id_sp = decomp_info_init(ctx, nx, ny, nzh);
+      x3d_decomp_info ph{}, sp{};
+      decomp_info_get(ctx, P->id_ph, &ph);
+      decomp_info_get(ctx, P->id_sp, &sp);
+      P->nyl = ph.zsz[1]; P->nzl = ph.ysz[2];
+      P->nzhl = sp.ysz[2]; P->k0 = sp.yst[2] - 1;
+    }
+  }
+  // FFT plans (local extents)
+  const int nyl = P->nyl, nzhl = P->nzhl;
   int nzv[1] = {nz};
   int inembed[1] = {nz}, onembed[1] = {nzh};
-  const int nxy = nx * ny;
+  const int nxyl = nx * nyl;
   size_t ws = 0, wmax = 0;
   X3D_CUFFT(cufftCreate(&P->plan_r2c)); X3D_CUFFT(cufftCreate(&P->plan_c2r)); X3D_CUFFT(cufftCreate(&P->plan_xy));
   P->plans = true;
   X3D_CUFFT(cufftSetAutoAllocation(P->plan_r2c, 0)); X3D_CUFFT(cufftSetAutoAllocation(P->plan_c2r, 0)); X3D_CUFFT(cufftSetAutoAllocation(P->plan_xy, 0));
-  X3D_CUFFT(cufftMakePlanMany(P->plan_r2c, 1, nzv, inembed, nxy, 1, onembed, nxy, 1, CUFFT_D2Z, nxy, &ws)); wmax = std::max(wmax, ws);
-  X3D_CUFFT(cufftMakePlanMany(P->plan_c2r, 1, nzv, onembed, nxy, 1, inembed, nxy, 1, CUFFT_Z2D, nxy, &ws)); wmax = std::max(wmax, ws);
+  if (nxyl > 0) {
+    X3D_CUFFT(cufftMakePlanMany(P->plan_r2c, 1, nzv, inembed, nxyl, 1, onembed, nxyl, 1, CUFFT_D2Z, nxyl, &ws)); wmax = std::max(wmax, ws);
+    X3D_CUFFT(cufftMakePlanMany(P->plan_c2r, 1, nzv, onembed, nxyl, 1, inembed, nxyl, 1, CUFFT_Z2D, nxyl, &ws)); wmax = std::max(wmax, ws);
+  }
   int nyx[2] = {ny, nx};
-  X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nxy, nullptr, 1, nxy, CUFFT_Z2Z, nzh, &ws)); wmax = std::max(wmax, ws);
+  if (nzhl > 0) { X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, nzhl, &ws)); wmax = std::max(wmax, ws); }
   P->fftwork.reserve(wmax ? wmax : 16);
   X3D_CUFFT(cufftSetWorkArea(P->plan_r2c, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_c2r, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_xy, P->fftwork.p));
   X3D_CUFFT(cufftSetStream(P->plan_r2c, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_c2r, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_xy, ctx.stream));
-  const size_t nsp = static_cast<size_t>(nx) * ny * nzh;
-  P->cw.reserve(nsp * 16);
-  if (p.bcx || p.bcy) P->cwb.reserve(nsp * 16);
-  if (p.bcx || p.bcy || p.bcz) P->rwork.reserve(static_cast<size_t>(nx) * ny * nz * 8);
+  const size_t nsp_y = static_cast<size_t>(nx) * ny * std::max(nzhl, 1);       // spectral y-pencil
+  const size_t nsp_z = static_cast<size_t>(nx) * std::max(nyl, 1) * nzh;       // spectral z-pencil
+  const size_t nr_z = static_cast<size_t>(nx) * std::max(nyl, 1) * nz;         // physical z-pencil
+  const size_t nr_y = static_cast<size_t>(nx) * ny * std::max(P->nzl, 1);      // physical y-pencil
+  P->cw.reserve(nsp_y * 16);
+  if (P->nranks > 1) P->cwz.reserve(nsp_z * 16);
+  if (p.bcx || p.bcy) P->cwb.reserve(nsp_y * 16);
+  if (p.bcx || p.bcy || p.bcz) P->rwork.reserve(std::max(nr_z, nr_y) * 8);
+  if (P->nranks > 1 && (p.bcx || p.bcy)) P->rwork2.reserve(std::max(nr_z, nr_y) * 8);
   ctx.poisson = std::move(P);
 }
 
+static void reorder_launch(Ctx &ctx, const double *in, double *out, int d0, int d1, int d2, const int *mx, const int *my, const int *mz) {
+  const long long n = static_cast<long long>(d0) * d1 * d2;
+  if (n == 0) return;
+  ProfScope ps(ctx, "poisson_reorder(k_reorder)");
+  k_reorder<<<grid_for(n, ctx.sm_count), 256, 0, ctx.stream>>>(in, out, d0, d1, d2, mx, my, mz);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+}
+
+// rhs: z-pencil of the pressure mesh (nx, nyl, nz), in place
 void poisson_solve_device(Ctx &ctx, double *d_rhs) {
   auto *P = dynamic_cast<PoissonImpl *>(ctx.poisson.get());
   if (!P) throw Error("x3d_poisson: x3d_poisson_init has not been called");
-  const int nx = P->nx, ny = P->ny, nz = P->nz, nzh = P->nzh;
-  const long long nr = static_cast<long long>(nx) * ny * nz, nsp = static_cast<long long>(nx) * ny * nzh;
-  SpecArgs a{nx, ny, nzh, nz, P->bcx, P->bcy, P->bcz, static_cast<double>(nx), static_cast<double>(ny), static_cast<double>(nz),
+  const int nx = P->nx, ny = P->ny, nz = P->nz, nzh = P->nzh, nyl = P->nyl, nzl = P->nzl, nzhl = P->nzhl;
+  const bool multi = P->nranks > 1;
+  const long long nsp = static_cast<long long>(nx) * ny * nzhl;
+  SpecArgs a{nx, ny, nzhl, nz, P->k0, P->bcx, P->bcy, P->bcz, static_cast<double>(nx), static_cast<double>(ny), static_cast<double>(nz),
              P->d_ax, P->d_bx, P->d_ay, P->d_by, P->d_az, P->d_bz, P->d_xk2, P->d_yk2, P->d_zk2, P->d_tx, P->d_ty, P->d_tz};
   double2 *cw = static_cast<double2 *>(P->cw.p), *cwb = static_cast<double2 *>(P->cwb.p);
-  double *rw = static_cast<double *>(P->rwork.p);
-  const int gr = grid_for(nr, ctx.sm_count), gs = grid_for(nsp, ctx.sm_count);
+  double2 *cwz = multi ? static_cast<double2 *>(P->cwz.p) : cw;   // spectral z-pencil (aliases the y-pencil on one rank)
+  double *rw = static_cast<double *>(P->rwork.p), *rw2 = static_cast<double *>(P->rwork2.p);
+  const int gs = grid_for(nsp, ctx.sm_count);
   const bool any = P->bcx || P->bcy || P->bcz;
+  // identity maps are the d_map entries of inactive axes; local extents along split axes use a prefix of them
+  const int *ident_y = P->d_map[0][1], *ident_z = P->d_map[0][2];
   double *fft_in = d_rhs;
-  if (any) {
-    k_reorder<<<gr, 256, 0, ctx.stream>>>(d_rhs, rw, nx, ny, nz, P->d_map[0][0], P->d_map[0][1], P->d_map[0][2]);
-    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  if (any && !multi) {
+    reorder_launch(ctx, d_rhs, rw, nx, ny, nz, P->d_map[0][0], P->d_map[0][1], P->d_map[0][2]);
     fft_in = rw;
+  } else if (any) {
+    // z is complete in the z-pencil; x and y are complete in the y-pencil (src/poisson.f90:1047-1101)
+    const double *cur = d_rhs;
+    if (P->bcz) { reorder_launch(ctx, cur, rw, nx, nyl, nz, P->d_idx, P->d_idx, P->d_map[0][2]); cur = rw; }
+    if (P->bcx || P->bcy) {
+      transpose_device(ctx, 2, cur, rw2, P->id_ph, 1);                                   // z -> y
+      reorder_launch(ctx, rw2, rw, nx, ny, nzl, P->d_map[0][0], P->d_map[0][1], P->d_idx);
+      transpose_device(ctx, 1, rw, rw2, P->id_ph, 1);                                    // y -> z
+      cur = rw2;
+    }
+    fft_in = const_cast<double *>(cur);
+    (void)ident_y; (void)ident_z;
   }
-  {
+  if (static_cast<long long>(nx) * nyl > 0) {
     ProfScope ps(ctx, "fft_z_r2c(cuFFT)");
-    X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cw)));
+    X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cwz)));
   }
-  {
+  if (multi) transpose_device(ctx, 2, reinterpret_cast<double *>(cwz), reinterpret_cast<double *>(cw), P->id_sp, 2);  // z -> y
+  if (nzhl > 0) {
     ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
     X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_FORWARD));
   }
   auto stage = [&](unsigned mode, const double2 *in, double2 *out) {
+    if (nsp == 0) return;
     ProfScope ps(ctx, "poisson_spectral(k_spec)");
     k_spec_stage<<<gs, 256, 0, ctx.stream>>>(a, mode, in, out);
     X3D_CUDA(cudaGetLastError()); ctx.launches++;
   };
   if (!any) {
-    ProfScope ps(ctx, "poisson_spectral(k_spec)");
-    k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
-    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+    if (nsp > 0) {
+      ProfScope ps(ctx, "poisson_spectral(k_spec)");
+      k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
+      X3D_CUDA(cudaGetLastError()); ctx.launches++;
+    }
   } else if (P->bcx == 1 && P->bcy == 0) {  // poisson_100, :472-635
     stage(S_NORM | S_ROTZ_F | S_ROTY_F | S_POSTX | S_DIVIDE, cw, cwb);
     stage(S_PREX | S_ROTY_B | S_ROTZ_B, cwb, cw);
@@ -374,24 +445,35 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     stage(S_PREX, cw, cwb);
     stage(S_PREY | S_ROTZ_B, cwb, cw);
   }
-  {
+  if (nzhl > 0) {
     ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
     X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_INVERSE));
   }
-  {
+  if (multi) transpose_device(ctx, 1, reinterpret_cast<double *>(cw), reinterpret_cast<double *>(cwz), P->id_sp, 2);  // y -> z
+  double *fft_out = any ? rw : d_rhs;
+  if (static_cast<long long>(nx) * nyl > 0) {
     ProfScope ps(ctx, "fft_z_c2r(cuFFT)");
-    X3D_CUFFT(cufftExecZ2D(P->plan_c2r, reinterpret_cast<cufftDoubleComplex *>(cw), any ? rw : d_rhs));
+    X3D_CUFFT(cufftExecZ2D(P->plan_c2r, reinterpret_cast<cufftDoubleComplex *>(cwz), fft_out));
   }
-  if (any) {
-    k_reorder<<<gr, 256, 0, ctx.stream>>>(rw, d_rhs, nx, ny, nz, P->d_map[1][0], P->d_map[1][1], P->d_map[1][2]);
-    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  if (any && !multi) {
+    reorder_launch(ctx, rw, d_rhs, nx, ny, nz, P->d_map[1][0], P->d_map[1][1], P->d_map[1][2]);
+  } else if (any) {  // src/poisson.f90:1422-1460
+    double *cur = rw;
+    if (P->bcz) { reorder_launch(ctx, cur, (P->bcx || P->bcy) ? rw2 : d_rhs, nx, nyl, nz, P->d_idx, P->d_idx, P->d_map[1][2]); cur = rw2; }
+    if (P->bcx || P->bcy) {
+      double *o1 = (cur == rw) ? rw2 : rw;
+      transpose_device(ctx, 2, cur, o1, P->id_ph, 1);
+      reorder_launch(ctx, o1, cur, nx, ny, nzl, P->d_map[1][0], P->d_map[1][1], P->d_idx);
+      transpose_device(ctx, 1, cur, d_rhs, P->id_ph, 1);
+    }
   }
 }
 
+// local extents of the z-pencil the solver works on
 void poisson_dims(Ctx &ctx, int d[3]) {
   auto *P = dynamic_cast<PoissonImpl *>(ctx.poisson.get());
   if (!P) throw Error("x3d_poisson: not initialised");
-  d[0] = P->nx; d[1] = P->ny; d[2] = P->nz;
+  d[0] = P->nx; d[1] = P->nyl; d[2] = P->nz;
 }
 
 }  // namespace x3d

@@ -11,6 +11,12 @@ namespace x3d {
 
 void poisson_init(Ctx &ctx, const x3d_poisson_params &p);
 void poisson_solve_device(Ctx &ctx, double *d_rhs);
+void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id);
+int decomp_info_init(Ctx &ctx, int nx, int ny, int nz);
+void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out);
+void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem);
+void allreduce(Ctx &ctx, double *d_buf, int n, bool is_max);
+void decomp_shape(Ctx &ctx, int *p_row, int *p_col, int *rank, int *nranks);
 
 namespace {
 
@@ -109,7 +115,13 @@ struct SolverImpl : SolverState {
   double xnu = 0, adt[3]{}, bdt[3]{}, gdt[3]{};
   int iadvance = 1, ntime = 1;
   long long itime = 0;
-  size_t n = 0, n3 = 0;
+  size_t n = 0, n3 = 0;       // local x-pencil points, local pressure z-pencil points
+  // decomposition (slab: p_row = 1, p_col = nranks)
+  int nranks = 1, rank = 0;
+  int id_v = 0, id_p3 = 0, id_p1 = 0;
+  int nzl = 0, z0 = 0;        // local z extent / 0-based offset of the x- and y-pencils
+  int nyl = 0, y0 = 0;        // local y extent / offset of the velocity z-pencil
+  int nyml = 0;               // local y extent of the pressure z-pencils
   // fields
   DevBuf ux, uy, uz, px, py, pz, pp3, dux[2], duy[2], duz[2];
   DevBuf w[16];
@@ -156,10 +168,14 @@ void map(Ctx &ctx, long long n, F f) {
 
 void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   X3D_CUDA(cudaSetDevice(ctx.device));
-  if (p.p_row > 1 || p.p_col > 1) throw Error("x3d_solver_init: multi-rank solver goes through x3d_decomp_init (not wired yet)");
   if (p.istret != 0) throw Error("x3d_solver_init: stretched meshes not implemented in the device solver yet");
   auto S = std::make_unique<SolverImpl>();
   S->p = p;
+  // decomposition: single rank unless x3d_decomp_init was called before with several ranks
+  if (!ctx.decomp) decomp_init(ctx, p.nx, p.ny, p.nz, 1, 1, 0, 1, nullptr);
+  int pr, pc;
+  decomp_shape(ctx, &pr, &pc, &S->rank, &S->nranks);
+  if (S->nranks > 1 && pr != 1) throw Error("x3d_solver_init: the distributed solver uses slabs (p_row = 1, p_col = number of GPUs)");
   SchemeOpts o;
   o.ifirstder = p.ifirstder; o.isecondder = p.isecondder; o.ipinter = p.ipinter; o.nu0nu = p.nu0nu; o.cnu = p.cnu;
   const int nn[3] = {p.nx, p.ny, p.nz};
@@ -187,9 +203,22 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   } else {
     throw Error("x3d_solver_init: itimescheme 1 (Euler) and 5 (RK3) are implemented");
   }
-  S->n = static_cast<size_t>(p.nx) * p.ny * p.nz;
-  S->n3 = static_cast<size_t>(S->nxm) * S->nym * S->nzm;
-  const size_t bytes = S->n * sizeof(double);
+  // local extents (xcompact3d.f90:191-201: main decomposition, ph3 = (nxm,nym,nz), ph1 = (nxm,nym,nzm))
+  S->id_v = 0;
+  S->id_p3 = decomp_info_init(ctx, S->nxm, S->nym, p.nz);
+  S->id_p1 = decomp_info_init(ctx, S->nxm, S->nym, S->nzm);
+  x3d_decomp_info iv{}, i3{}, i1{};
+  decomp_info_get(ctx, S->id_v, &iv); decomp_info_get(ctx, S->id_p3, &i3); decomp_info_get(ctx, S->id_p1, &i1);
+  if (iv.xsz[0] != p.nx || iv.ysz[1] != p.ny || iv.zsz[2] != p.nz) throw Error("x3d_solver_init: decomposition does not match the solver mesh");
+  S->nzl = iv.xsz[2]; S->z0 = iv.xst[2] - 1;
+  S->nyl = iv.zsz[1]; S->y0 = iv.zst[1] - 1;
+  S->nyml = i3.zsz[1];
+  if (i1.zsz[1] != S->nyml) throw Error("x3d_solver_init: inconsistent pressure decompositions");
+  const int nzl = S->nzl, nyl = S->nyl, nyml = S->nyml;
+  S->n = static_cast<size_t>(p.nx) * p.ny * nzl;
+  S->n3 = static_cast<size_t>(S->nxm) * nyml * S->nzm;
+  const size_t nmax = std::max({S->n, static_cast<size_t>(p.nx) * nyl * p.nz, static_cast<size_t>(1)});
+  const size_t bytes = nmax * sizeof(double);
   for (DevBuf *b : {&S->ux, &S->uy, &S->uz, &S->px, &S->py, &S->pz, &S->pp3}) { b->reserve(bytes); X3D_CUDA(cudaMemsetAsync(b->p, 0, bytes, ctx.stream)); }
   for (int q = 0; q < S->ntime; ++q)
     for (DevBuf *b : {&S->dux[q], &S->duy[q], &S->duz[q]}) { b->reserve(bytes); X3D_CUDA(cudaMemsetAsync(b->p, 0, bytes, ctx.stream)); }
@@ -197,23 +226,24 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   S->red_partial.reserve(sizeof(double) * 8 * 4096);
   S->red_out.reserve(sizeof(double) * 16);
   X3D_CUDA(cudaMallocHost(&S->h_red, sizeof(double) * 16));
-  // operators
-  const int dv[3] = {p.nx, p.ny, p.nz};
+  // operators on the local pencils
+  const int dxy[3] = {p.nx, p.ny, nzl}, dzp[3] = {p.nx, nyl, p.nz};
   for (int a = 0; a < 3; ++a) {
-    prep(ctx, S->d1[a][0], D1, a, S->A[a], 0, S->A[a].d1, dv);
-    prep(ctx, S->d1[a][1], D1, a, S->A[a], 1, S->A[a].d1p, dv);
-    prep(ctx, S->d2[a][0], D2, a, S->A[a], 0, S->A[a].d2, dv);
-    prep(ctx, S->d2[a][1], D2, a, S->A[a], 1, S->A[a].d2p, dv);
+    const int *dd = (a == 2) ? dzp : dxy;
+    prep(ctx, S->d1[a][0], D1, a, S->A[a], 0, S->A[a].d1, dd);
+    prep(ctx, S->d1[a][1], D1, a, S->A[a], 1, S->A[a].d1p, dd);
+    prep(ctx, S->d2[a][0], D2, a, S->A[a], 0, S->A[a].d2, dd);
+    prep(ctx, S->d2[a][1], D2, a, S->A[a], 1, S->A[a].d2p, dd);
   }
-  // divergence chain (navier.f90:297-336): x on (nx,ny,nz), y on (nxm,ny,nz), z on (nxm,nym,nz)
-  const int dy[3] = {S->nxm, p.ny, p.nz}, dz[3] = {S->nxm, S->nym, p.nz};
-  const int *dsv[3] = {dv, dy, dz};
+  // divergence chain (navier.f90:297-336): x on (nx,ny,nzl), y on (nxm,ny,nzl), z on (nxm,nyml,nz)
+  const int dy[3] = {S->nxm, p.ny, nzl}, dz[3] = {S->nxm, nyml, p.nz};
+  const int *dsv[3] = {dxy, dy, dz};
   for (int a = 0; a < 3; ++a) {
     prep(ctx, S->dvp[a], DVP, a, S->A[a], 0, S->A[a].vp, dsv[a]);
     prep(ctx, S->ivp[a], IVP, a, S->A[a], 1, S->A[a].ivpp, dsv[a]);
   }
-  // gradp chain (navier.f90:404-431): z on (nxm,nym,nzm), y on (nxm,nym,nz), x on (nxm,ny,nz)
-  const int gz[3] = {S->nxm, S->nym, S->nzm}, gy[3] = {S->nxm, S->nym, p.nz}, gx[3] = {S->nxm, p.ny, p.nz};
+  // gradp chain (navier.f90:404-431): z on (nxm,nyml,nzm), y on (nxm,nym,nzl), x on (nxm,ny,nzl)
+  const int gz[3] = {S->nxm, nyml, S->nzm}, gy[3] = {S->nxm, S->nym, nzl}, gx[3] = {S->nxm, p.ny, nzl};
   const int *gsv[3] = {gx, gy, gz};
   for (int a = 0; a < 3; ++a) {
     const AxisCoeffs &A = S->A[a];
@@ -235,28 +265,37 @@ static SolverImpl &SOL(Ctx &ctx) {
   return *S;
 }
 
+// pencil transposes of the reference; on one rank they are the identity and alias the source
+static const double *TR(Ctx &ctx, SolverImpl &S, int which, const double *src, double *dst, int id) {
+  if (S.nranks == 1) return src;
+  transpose_device(ctx, which, src, dst, id, 1);
+  return dst;
+}
+
 // Case-TGV.f90:90-95
 void solver_init_tgv(Ctx &ctx) {
   SolverImpl &S = SOL(ctx);
-  const int nx = S.p.nx, ny = S.p.ny;
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const int nx = S.p.nx, ny = S.p.ny, z0 = S.z0;
   const double dx = S.A[0].d, dy = S.A[1].d, dz = S.A[2].d;
   double *ux = B(S.ux), *uy = B(S.uy), *uz = B(S.uz);
   map(ctx, S.n, [=] __device__(long long q) {
-    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny));
+    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny)) + z0;
     const double x = static_cast<double>(i) * dx, y = static_cast<double>(j) * dy, z = static_cast<double>(k) * dz;
     ux[q] = sin(x) * cos(y) * cos(z);
     uy[q] = -cos(x) * sin(y) * cos(z);
     uz[q] = 0.0;
   });
   for (int q = 0; q < S.ntime; ++q)
-    for (DevBuf *b : {&S.dux[q], &S.duy[q], &S.duz[q]}) X3D_CUDA(cudaMemsetAsync(b->p, 0, S.n * sizeof(double), ctx.stream));
-  for (DevBuf *b : {&S.px, &S.py, &S.pz, &S.pp3}) X3D_CUDA(cudaMemsetAsync(b->p, 0, S.n * sizeof(double), ctx.stream));
+    for (DevBuf *b : {&S.dux[q], &S.duy[q], &S.duz[q]}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
+  for (DevBuf *b : {&S.px, &S.py, &S.pz, &S.pp3}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
   S.itime = 0;
 }
 
 // transeq.f90:73-591 (incompressible, explicit diffusion, uniform mesh)
 static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, double *duz1) {
-  const long long n = static_cast<long long>(S.n);
+  const long long n = static_cast<long long>(S.n);                                   // x / y pencil
+  const long long nz3 = static_cast<long long>(S.p.nx) * S.nyl * S.p.nz;             // z pencil
   const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   double *ta = B(S.w[0]), *tb = B(S.w[1]), *tc = B(S.w[2]), *td = B(S.w[3]), *te = B(S.w[4]), *tf = B(S.w[5]);
   double *tg1 = B(S.w[6]), *th1 = B(S.w[7]), *ti1 = B(S.w[8]), *tg2 = B(S.w[9]), *th2 = B(S.w[10]), *ti2 = B(S.w[11]);
@@ -272,17 +311,25 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
   run(ctx, S.d1[1][0], td, tg2); run(ctx, S.d1[1][1], te, th2); run(ctx, S.d1[1][0], tf, ti2);
   run(ctx, S.d1[1][1], u, td); run(ctx, S.d1[1][0], v, te); run(ctx, S.d1[1][1], w, tf);
   map(ctx, n, [=] __device__(long long q) { const double a = v[q]; tg2[q] = tg2[q] + a * td[q]; th2[q] = th2[q] + a * te[q]; ti2[q] = ti2[q] + a * tf[q]; });
-  // z, :249-314
-  map(ctx, n, [=] __device__(long long q) { const double a = w[q]; td[q] = u[q] * a; te[q] = v[q] * a; tf[q] = a * a; });
+  // z, :236-314 (transpose_y_to_z of the three velocity components, :236-238)
+  const double *u3 = TR(ctx, S, 1, u, ta, S.id_v), *v3 = TR(ctx, S, 1, v, tb, S.id_v), *w3 = TR(ctx, S, 1, w, tc, S.id_v);
+  {
+    double *pa = td, *pb = te, *pc = tf;
+    map(ctx, nz3, [=] __device__(long long q) { const double a = w3[q]; pa[q] = u3[q] * a; pb[q] = v3[q] * a; pc[q] = a * a; });
+  }
   run(ctx, S.d1[2][0], td, tg3); run(ctx, S.d1[2][0], te, th3); run(ctx, S.d1[2][1], tf, ti3);
-  run(ctx, S.d1[2][1], u, td); run(ctx, S.d1[2][1], v, te); run(ctx, S.d1[2][0], w, tf);
-  run(ctx, S.d2[2][1], u, ta); run(ctx, S.d2[2][1], v, tb); run(ctx, S.d2[2][0], w, tc);
-  map(ctx, n, [=] __device__(long long q) {
-    const double a = w[q];
-    const double cx = tg3[q] + a * td[q], cy = th3[q] + a * te[q], cz = ti3[q] + a * tf[q];
-    const double zx = xnu * ta[q] - half * cx, zy = xnu * tb[q] - half * cy, zz = xnu * tc[q] - half * cz;
-    tg2[q] = zx - half * tg2[q]; th2[q] = zy - half * th2[q]; ti2[q] = zz - half * ti2[q];  // :323-325
+  run(ctx, S.d1[2][1], u3, td); run(ctx, S.d1[2][1], v3, te); run(ctx, S.d1[2][0], w3, tf);
+  map(ctx, nz3, [=] __device__(long long q) {  // convective z terms, :272-274
+    const double a = w3[q];
+    tg3[q] = tg3[q] + a * td[q]; th3[q] = th3[q] + a * te[q]; ti3[q] = ti3[q] + a * tf[q];
   });
+  run(ctx, S.d2[2][1], u3, td); run(ctx, S.d2[2][1], v3, te); run(ctx, S.d2[2][0], w3, tf);  // :301-303
+  map(ctx, nz3, [=] __device__(long long q) {  // :312-314
+    tg3[q] = xnu * td[q] - half * tg3[q]; th3[q] = xnu * te[q] - half * th3[q]; ti3[q] = xnu * tf[q] - half * ti3[q];
+  });
+  // back to y pencils, :318-325
+  const double *zx = TR(ctx, S, 2, tg3, td, S.id_v), *zy = TR(ctx, S, 2, th3, te, S.id_v), *zz = TR(ctx, S, 2, ti3, tf, S.id_v);
+  map(ctx, n, [=] __device__(long long q) { tg2[q] = zx[q] - half * tg2[q]; th2[q] = zy[q] - half * th2[q]; ti2[q] = zz[q] - half * ti2[q]; });
   // y diffusion, :336-433
   run(ctx, S.d2[1][1], u, td); run(ctx, S.d2[1][0], v, te); run(ctx, S.d2[1][1], w, tf);
   // x diffusion and final sum, :442-470
@@ -323,18 +370,19 @@ static void intt3(Ctx &ctx, SolverImpl &S, int itr) {
   }
 }
 
-// navier.f90:599-613,693-711,751-769 (free-slip faces)
+// navier.f90:599-613,693-711,751-769 (free-slip faces); the x/y pencil holds z planes z0 .. z0+nzl-1
 static void pre_correc(Ctx &ctx, SolverImpl &S) {
-  const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
+  const int nx = S.p.nx, ny = S.p.ny, nzl = S.nzl;
   double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
-  const bool x1 = S.p.nclx1 == 1, xn = S.p.nclxn == 1, y1 = S.p.ncly1 == 1, yn = S.p.nclyn == 1, z1 = S.p.nclz1 == 1, zn = S.p.nclzn == 1;
+  const bool x1 = S.p.nclx1 == 1, xn = S.p.nclxn == 1, y1 = S.p.ncly1 == 1, yn = S.p.nclyn == 1;
+  const bool z1 = S.p.nclz1 == 1 && S.z0 == 0, zn = S.p.nclzn == 1 && S.z0 + nzl == S.p.nz;
   if (x1 || xn)
-    map(ctx, static_cast<long long>(ny) * nz, [=] __device__(long long q) {
+    map(ctx, static_cast<long long>(ny) * nzl, [=] __device__(long long q) {
       if (x1) u[q * nx] = 0.0;
       if (xn) u[q * nx + nx - 1] = 0.0;
     });
   if (y1 || yn)
-    map(ctx, static_cast<long long>(nx) * nz, [=] __device__(long long q) {
+    map(ctx, static_cast<long long>(nx) * nzl, [=] __device__(long long q) {
       const long long i = q % nx, k = q / nx;
       if (y1) v[i + static_cast<long long>(nx) * ny * k] = 0.0;
       if (yn) v[i + static_cast<long long>(nx) * (ny - 1 + static_cast<long long>(ny) * k)] = 0.0;
@@ -342,29 +390,34 @@ static void pre_correc(Ctx &ctx, SolverImpl &S) {
   if (z1 || zn)
     map(ctx, static_cast<long long>(nx) * ny, [=] __device__(long long q) {
       if (z1) w[q] = 0.0;
-      if (zn) w[q + static_cast<long long>(nx) * ny * (nz - 1)] = 0.0;
+      if (zn) w[q + static_cast<long long>(nx) * ny * (nzl - 1)] = 0.0;
     });
 }
 
-// navier.f90:257-347 ; result in out (nxm,nym,nzm)
+// navier.f90:257-347 ; result in out: z-pencil of ph1 (nxm, nyml, nzm)
 static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   double *pp1 = B(S.w[0]), *pgy1 = B(S.w[1]), *pgz1 = B(S.w[2]), *upi2 = B(S.w[3]), *duy = B(S.w[4]), *po3 = B(S.w[5]);
+  double *t1 = B(S.w[6]), *t2 = B(S.w[7]);
   run(ctx, S.dvp[0], B(S.ux), pp1);    // :297
   run(ctx, S.ivp[0], B(S.uy), pgy1);   // :313
-  run(ctx, S.ivp[0], B(S.uz), pgz1);   // :314
+  run(ctx, S.ivp[0], B(S.uz), pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
   run(ctx, S.ivp[1], pp1, upi2);       // :321
   run(ctx, S.dvp[1], pgy1, duy);       // :322
-  const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.p.nz;
+  const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.nzl;
   map(ctx, n2, [=] __device__(long long q) { duy[q] = duy[q] + upi2[q]; });  // :325
   run(ctx, S.ivp[1], pgz1, upi2);      // :327
-  run(ctx, S.ivp[2], duy, out);        // :333
-  run(ctx, S.dvp[2], upi2, po3);       // :335
+  const double *duy3 = TR(ctx, S, 1, duy, t1, S.id_p3);    // :329
+  const double *uzp3 = TR(ctx, S, 1, upi2, t2, S.id_p3);   // :330
+  run(ctx, S.ivp[2], duy3, out);       // :333
+  run(ctx, S.dvp[2], uzp3, po3);       // :335
   const long long n3 = static_cast<long long>(S.n3);
-  if (nlock == 2) {                    // :339-347
-    const long long ref = static_cast<long long>(S.nxm) * S.nym * (S.nzm - 1);
+  if (nlock == 2) {                    // :339-347 (each rank subtracts its own corner value)
+    const long long ref = static_cast<long long>(S.nxm) * S.nyml * (S.nzm - 1);
     double *tmp = B(S.red_out) + 8;
-    map(ctx, 1, [=] __device__(long long) { tmp[0] = out[ref] + po3[ref]; });
-    map(ctx, n3, [=] __device__(long long q) { out[q] = (out[q] + po3[q]) - tmp[0]; });
+    if (n3 > 0) {
+      map(ctx, 1, [=] __device__(long long) { tmp[0] = out[ref] + po3[ref]; });
+      map(ctx, n3, [=] __device__(long long q) { out[q] = (out[q] + po3[q]) - tmp[0]; });
+    }
   } else {
     map(ctx, n3, [=] __device__(long long q) { out[q] = out[q] + po3[q]; });
   }
@@ -373,11 +426,14 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
 // navier.f90:386-431
 static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3) {
   double *ppi3 = B(S.w[0]), *pgz3 = B(S.w[1]), *ppi2 = B(S.w[2]), *pgy2 = B(S.w[3]), *pgzi2 = B(S.w[4]);
+  double *t1 = B(S.w[5]), *t2 = B(S.w[6]);
   run(ctx, S.ipv[2], pp3, ppi3);   // :404
   run(ctx, S.dpv[2], pp3, pgz3);   // :406
-  run(ctx, S.ipv[1], ppi3, ppi2);  // :413
-  run(ctx, S.dpv[1], ppi3, pgy2);  // :415
-  run(ctx, S.ipv[1], pgz3, pgzi2); // :417
+  const double *pgz2 = TR(ctx, S, 2, pgz3, t1, S.id_p3);   // :410
+  const double *pp2 = TR(ctx, S, 2, ppi3, t2, S.id_p3);    // :411
+  run(ctx, S.ipv[1], pp2, ppi2);   // :413
+  run(ctx, S.dpv[1], pp2, pgy2);   // :415
+  run(ctx, S.ipv[1], pgz2, pgzi2); // :417  (transpose_y_to_x :422-424 is local)
   run(ctx, S.dpv[0], ppi2, B(S.px));   // :426
   run(ctx, S.ipv[0], pgy2, B(S.py));   // :428
   run(ctx, S.ipv[0], pgzi2, B(S.pz));  // :430
@@ -407,29 +463,38 @@ void solver_step(Ctx &ctx, int nsteps) {
 void solver_diagnostics_tgv(Ctx &ctx, double *out5) {
   SolverImpl &S = SOL(ctx);
   X3D_CUDA(cudaSetDevice(ctx.device));
-  const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
+  const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz, nzl = S.nzl, z0 = S.z0;
   const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   double *ta = B(S.w[0]), *tb = B(S.w[1]), *tc = B(S.w[2]), *td = B(S.w[3]), *te = B(S.w[4]), *tf = B(S.w[5]);
   double *tg = B(S.w[6]), *th = B(S.w[7]), *ti = B(S.w[8]);
+  double *s1 = B(S.w[9]), *s2 = B(S.w[10]), *s3 = B(S.w[11]), *s4 = B(S.w[12]), *s5 = B(S.w[13]), *s6 = B(S.w[14]);
   const int xs1 = S.p.nclx1 == 1 ? nx - 1 : nx, xs2 = S.p.ncly1 == 1 ? ny - 1 : ny, xs3 = S.p.nclz1 == 1 ? nz - 1 : nz;
   const double ncell = static_cast<double>(S.p.nclx1 == 1 ? S.nxm : nx) * (S.p.ncly1 == 1 ? S.nym : ny) * (S.p.nclz1 == 1 ? S.nzm : nz);
-  run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);  // :261-263
-  run(ctx, S.d1[1][1], u, td); run(ctx, S.d1[1][0], v, te); run(ctx, S.d1[1][1], w, tf);  // :265-267
-  run(ctx, S.d1[2][1], u, tg); run(ctx, S.d1[2][1], v, th); run(ctx, S.d1[2][0], w, ti);  // :269-271
   const double xnu = S.xnu;
   const long long n = static_cast<long long>(S.n);
   const int nb = gridn(ctx, n) > 4096 ? 4096 : gridn(ctx, n);
   double *partial = B(S.red_partial), *dout = B(S.red_out);
   auto inside = [=] __device__(long long q) {
-    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny));
+    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny)) + z0;
     return i < xs1 && j < xs2 && k < xs3;
   };
+  auto zder = [&](const PreOp &op, const double *f, double *scratch_in, double *scratch_out, double *back) -> const double * {
+    // derivative along z of an x-pencil field: y->z, operator, z->y (Case-TGV.f90:250-281)
+    const double *f3 = TR(ctx, S, 1, f, scratch_in, S.id_v);
+    double *o3 = (S.nranks == 1) ? back : scratch_out;
+    run(ctx, op, f3, o3);
+    return TR(ctx, S, 2, o3, back, S.id_v);
+  };
+  run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);  // :261-263
+  run(ctx, S.d1[1][1], u, td); run(ctx, S.d1[1][0], v, te); run(ctx, S.d1[1][1], w, tf);  // :265-267
+  zder(S.d1[2][1], u, s1, s2, tg); zder(S.d1[2][1], v, s1, s2, th); zder(S.d1[2][0], w, s1, s2, ti);  // :269-271
+  (void)s3; (void)s4; (void)s5; (void)s6; (void)nzl;
   k_reduce_partial<3><<<nb, 256, 0, ctx.stream>>>(n, [=] __device__(long long q, double *acc) {
     if (!inside(q)) return;
     const double a = tf[q] - th[q], b = tg[q] - tc[q], c = tb[q] - td[q];
     acc[0] += 0.5 * (a * a + b * b + c * c);                                                      // enstrophy :291-293
-    const double s1 = 2.0 * ta[q], s2 = 2.0 * te[q], s3 = 2.0 * ti[q], s4 = td[q] + tb[q], s5 = tg[q] + tc[q], s6 = th[q] + tf[q];
-    acc[1] += 0.5 * xnu * (s1 * s1 + s2 * s2 + s3 * s3 + 2.0 * s4 * s4 + 2.0 * s5 * s5 + 2.0 * s6 * s6);  // eps :305-308
+    const double e1 = 2.0 * ta[q], e2 = 2.0 * te[q], e3 = 2.0 * ti[q], e4 = td[q] + tb[q], e5 = tg[q] + tc[q], e6 = th[q] + tf[q];
+    acc[1] += 0.5 * xnu * (e1 * e1 + e2 * e2 + e3 * e3 + 2.0 * e4 * e4 + 2.0 * e5 * e5 + 2.0 * e6 * e6);  // eps :305-308
     acc[2] += 0.5 * (u[q] * u[q] + v[q] * v[q] + w[q] * w[q]);                                   // eek :323
   }, partial);
   X3D_CUDA(cudaGetLastError()); ctx.launches++;
@@ -437,7 +502,7 @@ void solver_diagnostics_tgv(Ctx &ctx, double *out5) {
   X3D_CUDA(cudaGetLastError()); ctx.launches++;
   run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);  // :332-334
   run(ctx, S.d2[1][1], u, td); run(ctx, S.d2[1][0], v, te); run(ctx, S.d2[1][1], w, tf);  // :336-338
-  run(ctx, S.d2[2][1], u, tg); run(ctx, S.d2[2][1], v, th); run(ctx, S.d2[2][0], w, ti);  // :340-342
+  zder(S.d2[2][1], u, s1, s2, tg); zder(S.d2[2][1], v, s1, s2, th); zder(S.d2[2][0], w, s1, s2, ti);  // :340-342
   k_reduce_partial<1><<<nb, 256, 0, ctx.stream>>>(n, [=] __device__(long long q, double *acc) {
     if (!inside(q)) return;
     acc[0] += (-xnu) * (u[q] * (ta[q] + td[q] + tg[q]) + v[q] * (tb[q] + te[q] + th[q]) + w[q] * (tc[q] + tf[q] + ti[q]));  // :362-365
@@ -445,15 +510,17 @@ void solver_diagnostics_tgv(Ctx &ctx, double *out5) {
   X3D_CUDA(cudaGetLastError()); ctx.launches++;
   k_reduce_final<1><<<1, 256, 0, ctx.stream>>>(nb, partial, dout + 3);
   X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  allreduce(ctx, dout, 4, false);  // MPI_ALLREDUCE(SUM), Case-TGV.f90:297,315,327,369
   // DIV U max of the current field (divergence nlock=2, navier.f90:341-361)
   double *dv = B(S.w[9]);
   divergence(ctx, S, dv, 2);
   const long long n3 = static_cast<long long>(S.n3);
-  const int nb3 = gridn(ctx, n3) > 4096 ? 4096 : gridn(ctx, n3);
+  const int nb3 = std::max(1, gridn(ctx, n3) > 4096 ? 4096 : gridn(ctx, n3));
   k_max_partial<<<nb3, 256, 0, ctx.stream>>>(n3, dv, partial);
   X3D_CUDA(cudaGetLastError()); ctx.launches++;
   k_max_final<<<1, 256, 0, ctx.stream>>>(nb3, partial, dout + 4);
   X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  allreduce(ctx, dout + 4, 1, true);
   X3D_CUDA(cudaMemcpyAsync(S.h_red, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
   out5[0] = S.h_red[2] / ncell;  // eek
@@ -469,19 +536,24 @@ void solver_divergence(Ctx &ctx, double *divmax, double *divmean) {
   double *dv = B(S.w[9]);
   divergence(ctx, S, dv, 2);
   const long long n3 = static_cast<long long>(S.n3);
-  const int nb3 = gridn(ctx, n3) > 4096 ? 4096 : gridn(ctx, n3);
+  const int nb3 = std::max(1, gridn(ctx, n3) > 4096 ? 4096 : gridn(ctx, n3));
   double *partial = B(S.red_partial), *dout = B(S.red_out);
   k_max_partial<<<nb3, 256, 0, ctx.stream>>>(n3, dv, partial);
   k_max_final<<<1, 256, 0, ctx.stream>>>(nb3, partial, dout);
   k_reduce_partial<1><<<nb3, 256, 0, ctx.stream>>>(n3, [=] __device__(long long q, double *acc) { acc[0] += fabs(dv[q]); }, partial);
   k_reduce_final<1><<<1, 256, 0, ctx.stream>>>(nb3, partial, dout + 1);
   X3D_CUDA(cudaGetLastError()); ctx.launches += 4;
+  allreduce(ctx, dout, 1, true);
+  allreduce(ctx, dout + 1, 1, false);
   X3D_CUDA(cudaMemcpyAsync(S.h_red, dout, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
   if (divmax) *divmax = S.h_red[0];
-  if (divmean) *divmean = S.h_red[1] / static_cast<double>(n3);
+  // navier.f90:359-367: local mean, summed over ranks, divided by nproc when printed
+  const double ntot = static_cast<double>(S.nxm) * S.nym * S.nzm;
+  if (divmean) *divmean = S.h_red[1] / ntot;
 }
 
+// x-pencil velocity of this rank: (nx, ny, nzl) -- host or device pointers
 void solver_set_velocity(Ctx &ctx, const double *ux, const double *uy, const double *uz) {
   SolverImpl &S = SOL(ctx);
   X3D_CUDA(cudaSetDevice(ctx.device));
@@ -499,6 +571,11 @@ void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz) {
   X3D_CUDA(cudaMemcpyAsync(uy, S.uy.p, bytes, cudaMemcpyDefault, ctx.stream));
   X3D_CUDA(cudaMemcpyAsync(uz, S.uz.p, bytes, cudaMemcpyDefault, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+void solver_local_shape(Ctx &ctx, int *d3, int *z0) {
+  SolverImpl &S = SOL(ctx);
+  d3[0] = S.p.nx; d3[1] = S.p.ny; d3[2] = S.nzl;
+  *z0 = S.z0;
 }
 
 }  // namespace x3d
