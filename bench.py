@@ -163,27 +163,41 @@ def run_b200(args):
     dt = 0.005 * 64.0 / n
     x = X3D(local)
     if world > 1:
-        raise SystemExit("multi-GPU bench goes through the pencil-decomposed solver (see DESIGN.md); not available in this build")
-    x.solver_init(n, n, n, ncl=(0,) * 6, xlx=length, yly=length, zlz=length, re=1600.0, dt=dt)
+        # 2-D pencil decomposition with p_row=1, p_col=N (slabs): on NVSwitch every byte costs the same
+        # whichever peer it goes to, and 1xN moves the fewest bytes (x<->y transposes become local)
+        from incompact3d_b200 import nccl_unique_id
+        obj = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        x.decomp_init(n, n, n, 1, world, rank, world, obj[0])
+    x.solver_init(n, n, n, ncl=(0,) * 6, xlx=length, yly=length, zlz=length, re=1600.0, dt=dt, p_row=1, p_col=world)
     x.solver_init_tgv()
     stream = torch.cuda.ExternalStream(x.stream)
     npts = n ** 3
 
+    def barrier():
+        x.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
     for _ in range(args.warmup):
         x.solver_step(1)
-    x.sync()
+    barrier()
     clocks = ClockSampler(local)
     clocks.start()
     l0 = x.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(args.steps):
         x.solver_step(1)
     e1.record(stream)
     e1.synchronize()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1)
+    if world > 1:  # device time, max over ranks
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     launches = x.launch_count - l0
     clk = clocks.stop()
     value = npts * args.steps / (ms * 1e-3)
@@ -198,31 +212,39 @@ def run_b200(args):
     peak = peaks.get("hbm_gbs", 6650.0)
     roofline = None
     if roof:
-        k = max(roof, key=lambda r: r["total_ms"])
-        achieved = 16.0 * npts / (k["avg_ms"] * 1e-3) / 1e9
+        comp = [r for r in roof if r["name"].startswith("compact_")]
+        k = max(comp, key=lambda r: r["total_ms"])
+        achieved = 16.0 * (npts / world) / (k["avg_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": k["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
-                    "algorithmic_bytes_per_launch": 16.0 * npts, "launches_per_step": k["count"],
+                    "algorithmic_bytes_per_launch": 16.0 * npts / world,
+                    "note": "dominant compact-operator kernel class; 16 B per output point (SURVEY 8d); per-launch CUDA events "
+                            "on the launching stream during one extra instrumented step", "launches_per_step": k["count"],
                     "share_of_step": k["total_ms"] / sum(r["total_ms"] for r in roof),
                     "classes": roof}
 
     # ---- e2e: the same step driven with HOST velocity arrays through the C ABI -------------------------
     e2e = None
     if not args.no_e2e:
-        hu, hv, hw = (torch.empty((n, n, n), dtype=torch.float64).pin_memory() for _ in range(3))
+        nzl = x._solver_shape[2]
+        hu, hv, hw = (torch.empty((max(nzl, 1), n, n), dtype=torch.float64).pin_memory() for _ in range(3))
         x.solver_get_velocity(hu, hv, hw)
         k2 = max(2, min(args.steps, 5))
         for _ in range(1):
             x.solver_set_velocity(hu, hv, hw); x.solver_step(1); x.solver_get_velocity(hu, hv, hw)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(k2):
             x.solver_set_velocity(hu, hv, hw)   # H2D of the step's inputs (pinned host memory)
             x.solver_step(1)
             x.solver_get_velocity(hu, hv, hw)   # D2H of the step's result
-        torch.cuda.synchronize()
+        barrier()
         te = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
         e2e = {"value": npts * k2 / te, "unit": UNIT, "h2d_bytes_per_step": 3 * npts * 8, "d2h_bytes_per_step": 3 * npts * 8,
                "steps": k2, "note": "x3d_solver_set_velocity(host) + x3d_solver_step + x3d_solver_get_velocity(host) per step"}
 
@@ -242,7 +264,7 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"TGV periodic {n}^3 Re=1600 RK3 dt={dt:g} (BASELINE configs[1])",
-                   "parallelism": f"{world} GPU", "l2": "fields are 1 GiB each, far larger than the 126 MB L2; no flush needed",
+                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), NCCL all-to-all transposes"), "l2": "fields are 1 GiB each, far larger than the 126 MB L2; no flush needed",
                    "diagnostics_after_run": diag},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
