@@ -84,6 +84,12 @@ int x3d_set_filter_coeffs(x3d_ctx *ctx, int axis, const x3d_filter_coeffs *c);
 /* module param flags; nclx/ncly/nclz are the LOGICALs (1 = periodic)       */
 int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit,
                   int nclx, int ncly, int nclz);
+/* stretched-mesh metrics computed by the host's stretching() (src/stretching.f90:96-318), ny entries
+ * each (the ...i arrays are the pressure-mesh ones); needed by x3d_poisson_init when istret != 0
+ * (matrice_refinement, src/poisson.f90:1814-2249) and by the device solver                          */
+int x3d_set_stretching(x3d_ctx *ctx, int ny, const double *yp, const double *ypi,
+                       const double *ppy, const double *pp2y, const double *pp4y,
+                       const double *ppyi, const double *pp2yi, const double *pp4yi);
 
 /* ---- compact operators ------------------------------------------------
  * abstract interfaces DERIVATIVE_X/Y/Z, src/module_param.f90:136-167 and

@@ -109,6 +109,16 @@ int x3d_set_filter_coeffs(x3d_ctx *ctx, int axis, const x3d_filter_coeffs *c) {
     ctx->c.have_fc[axis] = true;
   });
 }
+int x3d_set_stretching(x3d_ctx *ctx, int ny, const double *yp, const double *ypi, const double *ppy, const double *pp2y,
+                       const double *pp4y, const double *ppyi, const double *pp2yi, const double *pp4yi) {
+  return guard([&] {
+    if (ny < 1 || !yp || !ypi || !ppy || !pp2y || !pp4y || !ppyi || !pp2yi || !pp4yi) throw Error("x3d_set_stretching: bad argument");
+    Ctx &c = ctx->c;
+    c.st_yp.assign(yp, yp + ny); c.st_ypi.assign(ypi, ypi + ny);
+    c.st_ppy.assign(ppy, ppy + ny); c.st_pp2y.assign(pp2y, pp2y + ny); c.st_pp4y.assign(pp4y, pp4y + ny);
+    c.st_ppyi.assign(ppyi, ppyi + ny); c.st_pp2yi.assign(pp2yi, pp2yi + ny); c.st_pp4yi.assign(pp4yi, pp4yi + ny);
+  });
+}
 int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit, int nclx, int ncly, int nclz) {
   return guard([&] {
     if (iibm == 2 || iibm == 3)

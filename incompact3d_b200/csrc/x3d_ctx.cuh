@@ -33,13 +33,15 @@ struct Ctx {
   int sm_count = 148;
   long long launches = 0;
   // kernel variants (tuning knobs; X3D_STRIDED_VARIANT / X3D_CONTIG_VARIANT override)
-  int strided_variant = 2, contig_variant = 1;
+  int strided_variant = 6, contig_variant = 1;
   // module state made explicit (x3d_set_deriv_coeffs / x3d_set_filter_coeffs / x3d_set_flags)
   x3d_deriv_coeffs dc[3]{};
   x3d_filter_coeffs fc[3]{};
   bool have_dc[3] = {false, false, false}, have_fc[3] = {false, false, false};
   int iibm = 0, istret = 0, iimplicit = 0;
   bool ncl[3] = {true, true, true};
+  // stretched-mesh metrics of the host's stretching() (x3d_set_stretching); empty when istret == 0
+  std::vector<double> st_yp, st_ypi, st_ppy, st_pp2y, st_pp4y, st_ppyi, st_pp2yi, st_pp4yi;
   // optional per-launch CUDA-event timing (x3d_profile_begin / x3d_profile_end)
   bool profiling = false;
   std::vector<ProfRec> prof;

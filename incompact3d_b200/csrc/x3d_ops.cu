@@ -29,6 +29,7 @@ bool is_device_ptr(const void *p) {
 }
 
 int pick_L_strided(int n, int variant) {
+  if (variant >= 4) return n <= 256 ? 8 : (n <= 512 ? 16 : 32);  // TMA tile kernels: up to 32 chunks per line
   if (n <= 128) return 8;
   if (n <= 256) return 16;
   if (n <= 512 && variant >= 2) return 16;
@@ -76,7 +77,14 @@ static LineGeom make_geom(const OpCall &call, int n_in, int n_out) {
 void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double *d_u, double *d_t) {
   const int n_in = op.n_in, n_out = op.n_out;
   LineGeom g = make_geom(call, n_in, n_out);
-  const int L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out, ctx.strided_variant);
+  int L = -1;
+  if (call.axis != 0 && ctx.strided_variant >= 6) {  // warp-per-lane-pair TMA kernel when the call qualifies
+    PairGeom pg;
+    size_t smem;
+    const int Lp = pick_L_contig(n_out);
+    if (Lp > 0 && Lp <= 17 && pair_plan(op, g, Lp, d_u, d_t, pg, smem)) { L = Lp; g.pair = true; }
+  }
+  if (L < 0) L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out, ctx.strided_variant);
   if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 1056)");
   const TriTable &T = get_tri(ctx, call.f, call.s, call.w, n_out, L, op.periodic != 0, op.alpha, call.post);
   ProfScope ps(ctx, call.axis == 0 ? "compact_x(k_contig)" : (call.axis == 1 ? "compact_y(k_strided)" : "compact_z(k_strided)"));

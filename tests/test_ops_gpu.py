@@ -94,6 +94,9 @@ CASES = [  # (dims, axis letter) -- line lengths of the BASELINE configs, ragged
     ((256, 9, 6), "x"), ((70, 256, 3), "y"), ((16, 9, 32), "z"),
     ((512, 6, 5), "x"), ((48, 512, 2), "y"), ((40, 3, 512), "z"),
     ((769, 4, 3), "x"), ((20, 769, 2), "y"), ((12, 3, 1000), "z"),
+    # even lane extents: the TMA-tiled kernels (16-byte strides), full and ragged lane blocks
+    ((64, 64, 4), "y"), ((32, 16, 64), "z"), ((16, 128, 4), "y"), ((24, 300, 3), "y"), ((6, 5, 130), "z"),
+    ((34, 16, 3), "y"), ((8, 2, 10), "z"),
 ]
 
 
