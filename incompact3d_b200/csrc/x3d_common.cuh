@@ -63,6 +63,7 @@ struct TriTable {
   double *d_rows = nullptr;   // [nc*L][TRI_W]
   double *d_scan = nullptr;   // [10][32] Kogge-Stone multipliers (x kernels), [2][nc] chunk products
   double *d_chunk = nullptr;  // [2][nc]: Af(c) forward chunk product, Ab(c) backward chunk product
+  std::vector<double> h_rows, h_scan;  // host copies (compressed tables of the fused kernels are derived from them)
   ~TriTable();
 };
 

@@ -1,0 +1,115 @@
+// x3d_mom.cu -- host side of the fused momentum-RHS kernels (x3d_mom_kernels.cuh): compressed
+// coefficient tables, tensor maps, eligibility, launch.
+#include <cmath>
+#include "x3d_mom.cuh"
+#include "x3d_mom_kernels.cuh"
+#include "x3d_ops_inst.cuh"
+
+namespace x3d {
+
+MomTable::~MomTable() {
+  if (d_c) cudaFree(d_c);
+  if (d_scan) cudaFree(d_scan);
+}
+
+// Compress the per-row table of a periodic operator into MOM_TABS chunk tables.  Valid when every chunk
+// 3 .. nc-4 has the rows of chunk 3 (the LU recurrence of prepare() has reached its fixed point) and a
+// Sherman-Morrison vector that is zero at double precision relative to its boundary values.
+bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M) {
+  const int L = T.L, nc = T.nc;
+  const int H = mom_head(L), MOM_TABS = mom_tabs(L);
+  M.ok = false;
+  if (nc < MOM_TABS || nc > 32 || T.h_rows.empty()) return false;
+  auto R = [&](int row, int col) { return T.h_rows[static_cast<size_t>(row) * TRI_W + col]; };
+  double rsmax = 0.0;
+  for (int i = 0; i < nc * L; ++i) rsmax = std::max(rsmax, std::fabs(R(i, T_RS)));
+  const int cols[5] = {T_S, T_PF, T_W, T_FW, T_PB};
+  for (int c = H + 1; c <= nc - H - 2; ++c)
+    for (int m = 0; m < L; ++m) {
+      for (int q = 0; q < 5; ++q) {
+        const double a = R(c * L + m, cols[q]), b = R(H * L + m, cols[q]);
+        if (std::fabs(a - b) > 4e-16 * std::max(std::fabs(a), std::fabs(b))) return false;
+      }
+    }
+  for (int c = H; c <= nc - H - 2; ++c)
+    for (int m = 0; m < L; ++m)
+      if (std::fabs(R(c * L + m, T_RS)) > 1e-18 * rsmax) return false;
+  std::vector<double> h(static_cast<size_t>(3) * MOM_TABS * L * 2, 0.0);
+  for (int t = 0; t < MOM_TABS; ++t) {
+    const int c = t < H ? t : (t == H ? H : nc - H - 1 + (t - H - 1));
+    for (int m = 0; m < L; ++m) {
+      const int row = c * L + m;
+      for (int pr = 0; pr < 3; ++pr) {
+        const size_t o = ((static_cast<size_t>(pr) * MOM_TABS + t) * L + m) * 2;
+        h[o] = R(row, 2 * pr);
+        h[o + 1] = (t == H && pr == 2) ? 0.0 : R(row, 2 * pr + 1);  // generic chunk: rs = 0
+      }
+    }
+  }
+  X3D_CUDA(cudaMalloc(&M.d_c, h.size() * sizeof(double)));
+  X3D_CUDA(cudaMalloc(&M.d_scan, T.h_scan.size() * sizeof(double)));
+  X3D_CUDA(cudaMemcpyAsync(M.d_c, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(M.d_scan, T.h_scan.data(), T.h_scan.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  M.L = L; M.nc = nc;
+  M.ok = true;
+  return true;
+}
+
+bool mom_pair_plan(int n, int L, MomGeom &g, size_t &smem) {
+  if (L != 17 && L != 9) return false;
+  if ((n & 7) || n < 64) return false;
+  int nbox, br;
+  if (!pair_boxes(n, true, nbox, br)) return false;
+  g.nbox = nbox; g.br = br;
+  g.n = n;
+  g.nc = (n + L - 1) / L;
+  if (g.nc > 32 || g.nc < mom_tabs(L)) return false;
+  g.slot_rows = 8 + n + 8;
+  const size_t tail = static_cast<size_t>(2) * 3 * mom_tabs(L) * L * 16 + 2 * 320 * 8 + 2 * 3 * 8;
+  const long long overrun = static_cast<long long>(g.nc * L + 8 + HALO - g.slot_rows) * 128;
+  if (overrun > static_cast<long long>(tail)) return false;
+  smem = static_cast<size_t>(3) * g.slot_rows * 128 + tail;
+  return smem <= 227 * 1024;
+}
+
+bool mom_pair_eligible(int n, int L) {
+  MomGeom g{};
+  size_t smem;
+  return mom_pair_plan(n, L, g, smem);
+}
+
+// fields: f[0..2] = ux, uy, uz pencils with the layout described by (n1, nline, nouter, sline, souter);
+// out[0..2] = xnu D2(c) - 1/2 (D1(c a) + a D1(c)) along this axis, a = f[axis]
+void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
+                     const double *const f[3], double *const out[3], long long n1, int nline, long long nouter, long long sline,
+                     long long souter) {
+  MomGeom g{};
+  size_t smem = 0;
+  if (!M1.ok || !M2.ok || M1.L != M2.L || !mom_pair_plan(nline, M1.L, g, smem)) throw Error("fused momentum kernel: ineligible call");
+  g.nbx = static_cast<int>((n1 + 15) / 16);
+  g.npos = static_cast<long long>(g.nbx) * nouter;
+  g.ia = axis; g.ic1 = (axis + 1) % 3; g.ic2 = (axis + 2) % 3;
+  g.xnu = xnu;
+  MomMaps maps;
+  for (int q = 0; q < 3; ++q) {
+    maps.in[q] = make_line_map(f[q], n1, nline, nouter, sline, souter, 16, g.br, true);
+    maps.halo[q] = make_line_map(f[q], n1, nline, nouter, sline, souter, 16, 8, true);
+    maps.out[q] = make_line_map(out[q], n1, nline, nouter, sline, souter, 16, g.br, true);
+  }
+  MomTabs tb{reinterpret_cast<const double2 *>(M1.d_c), reinterpret_cast<const double2 *>(M2.d_c), M1.d_scan, M2.d_scan};
+  const bool nt4 = op2.c[2] != 0.0 || op2.c[3] != 0.0;
+  auto launch = [&](auto kern) {
+    X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    long long blocks = ctx.sm_count;
+    if (blocks > g.npos) blocks = g.npos;
+    kern<<<static_cast<unsigned>(blocks), MOM_THREADS, smem, ctx.stream>>>(op1, op2, maps, tb, g);
+    X3D_CUDA(cudaGetLastError());
+    ctx.launches++;
+  };
+  ProfScope ps(ctx, axis == 1 ? "momentum_fused_y(k_mom_pair)" : "momentum_fused_z(k_mom_pair)");
+  if (M1.L == 17) { if (nt4) launch(k_mom_pair<17, 4>); else launch(k_mom_pair<17, 2>); }
+  else { if (nt4) launch(k_mom_pair<9, 4>); else launch(k_mom_pair<9, 2>); }
+}
+
+}  // namespace x3d

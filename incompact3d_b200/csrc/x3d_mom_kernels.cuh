@@ -1,0 +1,276 @@
+// x3d_mom_kernels.cuh -- fused momentum-RHS kernels for periodic directions (sm_100a).
+//
+// For one direction d with advecting velocity a = u_d, the reference computes for each velocity component c
+//   conv_c = D1(c a) + a D1(c)          (skew-symmetric convection, src/transeq.f90:114-146,188-219,240-274)
+//   diff_c = D2(c)                      (src/transeq.f90:301-303,336-338,442-444)
+// with nine operator calls and three elementwise passes over nine full fields.  Here one kernel does all
+// nine line solves of a direction per tile position and writes  r_c = xnu diff_c - 1/2 conv_c : every
+// velocity component is read once and every result written once (6 array passes instead of ~45).
+//
+// k_mom_pair (y / z lines) has the structure of k_pair: 128B-swizzled TMA tiles of 16 lanes x whole line,
+// warp = lane pair, thread = chunk of L rows, shuffle carries, a TMA producer warp, mbarriers only.  A tile
+// position needs three tiles (a, c1, c2) that fill the three ring slots; they are consumed in the order
+// c1, c2, a (each solved in place and stored), and every slot is refilled for the next position as soon as
+// its store has left shared memory, so loads stay one to two component-times ahead of their use.
+//
+// Coefficient tables are compressed: for a periodic operator the LU rows of prepare() (src/schemes.f90:413-439)
+// reach their floating-point fixed point a few rows away from row 1, so all chunks except the first three and
+// the last three share one table (x3d_mom.cu checks this on the host and otherwise disables the fused path).
+#pragma once
+#include "x3d_ops_kernels.cuh"
+
+namespace x3d {
+
+struct MomMaps {
+  CUtensorMap in[3], halo[3], out[3];
+};
+struct MomGeom {
+  int nbx;
+  long long npos;       // tile positions = nbx * nouter
+  int slot_rows;
+  int nbox, br;         // data boxes per tile
+  int n;                // line length
+  int nc;               // chunks per line
+  int ia, ic1, ic2;     // field index of the advecting velocity and of the two other components
+  double xnu;
+};
+struct MomTabs {        // device: [3][mom_tabs(L) L] double2 each ((s,Pf) (w,fw) (Pb,rs)), and [10][32] scan multipliers
+  const double2 *c1, *c2;
+  const double *scan1, *scan2;
+};
+// chunk tables: H head chunks, 1 generic, H+1 tail chunks (the last chunk may hold a single row); H covers >= 45 rows (the Sherman-Morrison vector of the
+// 6th-order schemes decays by 0.382 per row: 0.382^45 = 1.5e-19)
+__host__ __device__ constexpr int mom_head(int L) { return L >= 15 ? 3 : (L >= 9 ? 5 : 9); }
+__host__ __device__ constexpr int mom_tabs(int L) { return 2 * mom_head(L) + 2; }
+// 8 consumer warps (two warpgroups) + one producer warpgroup (one active thread).  Registers are allocated
+// per warpgroup: the producer group shrinks to 24 registers per thread and the consumers grow to 240
+// (setmaxnreg), which is what lets a thread hold two 17-row chunk pairs without spilling.
+constexpr int MOM_THREADS = 32 * (PAIR_WARPS + 4);
+
+// periodic line solve of one chunk pair held in x[] (as in k_pair)
+template <int L>
+__device__ __forceinline__ void pair_solve_periodic(dd2 (&x)[L], const double2 *__restrict__ cSP, const double2 *__restrict__ cWF,
+                                                    const double2 *__restrict__ cBR, const double *__restrict__ scan, int lane, int nc,
+                                                    bool live, double alpha, int q0, int n) {
+  X3D_UNROLL
+  for (int m = 1; m < L; ++m) x[m] = fma2(-cSP[m].x, x[m - 1], x[m]);
+  dd2 v = x[L - 1];
+  X3D_UNROLL
+  for (int lev = 0; lev < 5; ++lev) {
+    const dd2 o = shfl_up2(v, 1 << lev);
+    v = fma2(scan[lev * 32 + lane], o, v);
+  }
+  dd2 cin = shfl_up2(v, 1);
+  if (lane == 0) cin = {0.0, 0.0};
+  {
+    dd2 xn = {0.0, 0.0};
+    X3D_UNROLL
+    for (int m = L - 1; m >= 0; --m) {
+      const double2 wf = cWF[m];
+      const dd2 tt = fma2(cSP[m].y, cin, x[m]);
+      xn = fma2(-wf.y, xn, wf.x * tt);
+      x[m] = xn;
+    }
+  }
+  v = x[0];
+  if (!live) v = {0.0, 0.0};
+  X3D_UNROLL
+  for (int lev = 0; lev < 5; ++lev) {
+    const dd2 o = shfl_down2(v, 1 << lev);
+    v = fma2(scan[(5 + lev) * 32 + lane], o, v);
+  }
+  dd2 cb = shfl_down2(v, 1);
+  if (lane >= nc - 1) cb = {0.0, 0.0};
+  X3D_UNROLL
+  for (int m = 0; m < L; ++m) x[m] = fma2(cBR[m].x, cb, x[m]);
+  dd2 xl = {0.0, 0.0};
+  X3D_UNROLL
+  for (int m = 0; m < L; ++m)
+    if (q0 + m == n - 1) xl = x[m];
+  const dd2 x0 = shfl2(x[0], 0);
+  const dd2 xe = shfl2(xl, nc - 1);
+  const dd2 sf = {x0.x - alpha * xe.x, x0.y - alpha * xe.y};  // src/derive.f90:55-59
+  X3D_UNROLL
+  for (int m = 0; m < L; ++m) {
+    const double rs = cBR[m].y;
+    x[m].x = fma(-sf.x, rs, x[m].x);
+    x[m].y = fma(-sf.y, rs, x[m].y);
+  }
+}
+
+template <int L, int NT2>
+__global__ void __launch_bounds__(MOM_THREADS, 1)
+    k_mom_pair(const __grid_constant__ DevOp op1, const __grid_constant__ DevOp op2, const __grid_constant__ MomMaps maps,
+               const MomTabs tb, const MomGeom g) {
+  constexpr int NWIN = L + 2 * HALO;
+  constexpr int NB = 3;
+  constexpr int MOM_TABS = mom_tabs(L), MOM_H = mom_head(L);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int slot_bytes = g.slot_rows * 128;
+  double2 *c1 = reinterpret_cast<double2 *>(smem_raw + NB * slot_bytes);  // [3][7 L]
+  double2 *c2 = c1 + 3 * MOM_TABS * L;
+  double *scan1 = reinterpret_cast<double *>(c2 + 3 * MOM_TABS * L);     // [10][32]
+  double *scan2 = scan1 + 320;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(scan2 + 320);
+  unsigned long long *done = full + NB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = g.n, nc = g.nc;
+  for (int idx = threadIdx.x; idx < 3 * MOM_TABS * L; idx += blockDim.x) { c1[idx] = tb.c1[idx]; c2[idx] = tb.c2[idx]; }
+  for (int idx = threadIdx.x; idx < 320; idx += blockDim.x) { scan1[idx] = tb.scan1[idx]; scan2[idx] = tb.scan2[idx]; }
+  if (threadIdx.x == 0) {
+    X3D_UNROLL
+    for (int b = 0; b < NB; ++b) { mbar_init(full + b, 1); mbar_init(done + b, PAIR_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncthreads();
+  const long long first = blockIdx.x, step = gridDim.x;
+  const long long mine = first < g.npos ? (g.npos - first + step - 1) / step : 0;  // positions of this CTA
+  // tile q of position p (q = 0: c1, 1: c2, 2: a, the order of consumption) lives in slot (p + 1 + q) % 3
+  const int fld[3] = {g.ic1, g.ic2, g.ia};
+
+  if (warp >= PAIR_WARPS) {
+    // ---------------- TMA producer ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp != PAIR_WARPS || lane != 0) return;
+    const unsigned in_bytes = (static_cast<unsigned>(g.nbox) * g.br + 16u) * 128u;
+    auto load = [&](long long p, int q) {
+      const long long pos = first + p * step;
+      const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
+      const int slot = static_cast<int>((p + 1 + q) % 3);
+      unsigned char *dst = smem_raw + slot * slot_bytes;
+      const CUtensorMap *tm = &maps.in[fld[q]], *th = &maps.halo[fld[q]];
+      mbar_expect_tx(full + slot, in_bytes);
+      for (int b = 0; b < g.nbox; ++b) tma_load_3d(dst + (8 + b * g.br) * 128, tm, bx * 16, b * g.br, by, full + slot);
+      tma_load_3d(dst, th, bx * 16, n - 8, by, full + slot);
+      tma_load_3d(dst + (8 + n) * 128, th, bx * 16, 0, by, full + slot);
+    };
+    if (mine > 0) { load(0, 2); load(0, 0); load(0, 1); }
+    for (long long p = 0; p < mine; ++p) {
+      const long long pos = first + p * step;
+      const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
+      for (int q = 0; q < 3; ++q) {
+        const int slot = static_cast<int>((p + 1 + q) % 3);
+        mbar_wait(done + slot, static_cast<unsigned>(p & 1));
+        const unsigned char *src = smem_raw + slot * slot_bytes;
+        const CUtensorMap *tm = &maps.out[fld[q]];
+        for (int b = 0; b < g.nbox; ++b) tma_store_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
+        bulk_commit();
+        if (p + 1 < mine) {
+          // the slot is free once the store has left shared memory; for the next position it takes
+          // c1's slot -> a, c2's slot -> c1, a's slot -> c2 (one to two component times ahead of its use)
+          bulk_wait_read<0>();
+          load(p + 1, (q + 2) % 3);
+        }
+      }
+    }
+    bulk_wait_read<0>();
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  const int jw = warp;
+  const int cl = lane < nc ? lane : nc - 1;
+  const bool live = lane < nc;
+  const int q0 = cl * L;
+  const int base = q0 + 8 - HALO;
+  int off[8];
+  X3D_UNROLL
+  for (int p = 0; p < 8; ++p) off[p] = base * 8 + (jw ^ ((base + p) & 7));
+  const int tab = cl < MOM_H ? cl : (cl >= nc - MOM_H - 1 ? MOM_H + 1 + cl - (nc - MOM_H - 1) : MOM_H);
+  const double2 *s1 = c1 + tab * L, *w1 = c1 + MOM_TABS * L + tab * L, *b1 = c1 + 2 * MOM_TABS * L + tab * L;
+  const double2 *s2 = c2 + tab * L, *w2 = c2 + MOM_TABS * L + tab * L, *b2 = c2 + 2 * MOM_TABS * L + tab * L;
+  const double xnu = g.xnu;
+  for (long long p = 0; p < mine; ++p) {
+    const unsigned par = static_cast<unsigned>(p & 1);
+    const int slot_a = static_cast<int>((p + 3) % 3);
+    const dd2 *bufA = reinterpret_cast<const dd2 *>(smem_raw + slot_a * slot_bytes);
+    mbar_wait(full + slot_a, par);
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) {
+      const int slot = static_cast<int>((p + 1 + q) % 3);
+      dd2 *bufC = reinterpret_cast<dd2 *>(smem_raw + slot * slot_bytes);
+      if (q < 2) mbar_wait(full + slot, par);
+      dd2 r[L];
+      {  // xnu * D2(c)
+        dd2 x[L];
+        {
+          dd2 win[NWIN];
+          X3D_UNROLL
+          for (int j = 0; j < NWIN; ++j) win[j] = bufC[off[j & 7] + 8 * j];
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            const dd2 v = rhs_interior<D2, NT2, NWIN, dd2>(op2, win, m);
+            const bool ok = live && q0 + m < n;
+            x[m].x = ok ? v.x : 0.0;
+            x[m].y = ok ? v.y : 0.0;
+          }
+        }
+        pair_solve_periodic<L>(x, s2, w2, b2, scan2, lane, nc, live, op2.alpha, q0, n);
+        X3D_UNROLL
+        for (int m = 0; m < L; ++m) r[m] = xnu * x[m];
+      }
+      __syncwarp();  // also keeps the compiler from hoisting the next section's shared-memory loads (register pressure)
+      {  // - 1/2 a D1(c)
+        dd2 x[L];
+        {
+          dd2 win[NWIN];
+          X3D_UNROLL
+          for (int j = 0; j < NWIN; ++j) win[j] = bufC[off[j & 7] + 8 * j];
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            const dd2 v = rhs_interior<D1, 2, NWIN, dd2>(op1, win, m);
+            const bool ok = live && q0 + m < n;
+            x[m].x = ok ? v.x : 0.0;
+            x[m].y = ok ? v.y : 0.0;
+          }
+        }
+        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, q0, n);
+        X3D_UNROLL
+        for (int m = 0; m < L; ++m) {
+          const dd2 a = bufA[off[(m + HALO) & 7] + 8 * (m + HALO)];
+          r[m].x = fma(-0.5 * a.x, x[m].x, r[m].x);
+          r[m].y = fma(-0.5 * a.y, x[m].y, r[m].y);
+        }
+      }
+      __syncwarp();
+      {  // - 1/2 D1(c a)
+        dd2 x[L];
+        {
+          dd2 win[NWIN];
+          X3D_UNROLL
+          for (int j = 0; j < NWIN; ++j) {
+            const dd2 cc = bufC[off[j & 7] + 8 * j];
+            const dd2 aa = bufA[off[j & 7] + 8 * j];
+            win[j] = {cc.x * aa.x, cc.y * aa.y};
+          }
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            const dd2 v = rhs_interior<D1, 2, NWIN, dd2>(op1, win, m);
+            const bool ok = live && q0 + m < n;
+            x[m].x = ok ? v.x : 0.0;
+            x[m].y = ok ? v.y : 0.0;
+          }
+        }
+        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, q0, n);
+        X3D_UNROLL
+        for (int m = 0; m < L; ++m) {
+          r[m].x = fma(-0.5, x[m].x, r[m].x);
+          r[m].y = fma(-0.5, x[m].y, r[m].y);
+        }
+      }
+      __syncwarp();  // every lane has read its windows of c (and of a when c == a)
+      if (live) {
+        X3D_UNROLL
+        for (int m = 0; m < L; ++m)
+          if (q0 + m < n) bufC[off[(m + HALO) & 7] + 8 * (m + HALO)] = r[m];
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done + slot);
+    }
+  }
+}
+
+}  // namespace x3d

@@ -4,6 +4,8 @@
 // (src/Case-TGV.f90:25,189) chained on one GPU.  Fields never leave HBM; on a single rank every
 // pencil transpose of the reference is the identity and is not executed.
 #include <cmath>
+#include <cstdlib>
+#include "x3d_mom.cuh"
 #include "x3d_schemes.cuh"
 #include "x3d_state.cuh"
 
@@ -130,6 +132,9 @@ struct SolverImpl : SolverState {
   // prepared operators
   PreOp d1[3][2], d2[3][2];                 // [axis][npaire]
   PreOp dvp[3], ivp[3], dpv[3], ipv[3];
+  // fused momentum kernels (periodic directions): compressed tables of D1 / D2 per axis
+  MomTable mt1[3], mt2[3];
+  bool fused[3] = {false, false, false};
   ~SolverImpl() override { if (h_red) cudaFreeHost(h_red); }
 };
 
@@ -250,6 +255,21 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
     prep(ctx, S->dpv[a], DPV, a, A, 1, A.periodic ? A.vp : A.pvp, gsv[a]);
     prep(ctx, S->ipv[a], IPV, a, A, 1, A.periodic ? A.ivp : A.ipvp, gsv[a]);
   }
+  // fused momentum kernels where the direction is periodic and the tile kernel fits (x3d_mom.cu)
+  {
+    const char *e = getenv("X3D_FUSED");
+    const bool want = !(e && atoi(e) == 0);
+    for (int a = 1; a < 3 && want; ++a) {
+      const int n = nn[a];
+      const int L = pick_L_contig(n);
+      const long long lanes = (a == 1) ? p.nx : static_cast<long long>(p.nx) * nyl;
+      if (!S->A[a].periodic || L <= 0 || !mom_pair_eligible(n, L) || (lanes & 1) || (p.nx & 1)) continue;
+      const PreOp &o1 = S->d1[a][0], &o2 = S->d2[a][0];
+      const TriTable &T1 = get_tri(ctx, o1.call.f, o1.call.s, o1.call.w, n, L, true, o1.op.alpha, nullptr);
+      const TriTable &T2 = get_tri(ctx, o2.call.f, o2.call.s, o2.call.w, n, L, true, o2.op.alpha, nullptr);
+      S->fused[a] = build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]);
+    }
+  }
   x3d_poisson_params pp{};
   pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
   pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
@@ -340,6 +360,79 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
     duy1[q] = ay - half * th1[q] + xnu * tb[q];
     duz1[q] = az - half * ti1[q] + xnu * tc[q];
   });
+}
+
+// Fused form of momentum_rhs for periodic y and z: per direction one kernel writes
+// r_c = xnu D2(c) - 1/2 (D1(c a) + a D1(c)); the x direction uses the operator kernels.  The three partial
+// right-hand sides are summed inside intt3 (same terms as transeq.f90:312-314,323-325,460-470, summed in a
+// different order).  rhs[d][c]: direction d, component c.
+static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *rhs[3][3]) {
+  const long long n = static_cast<long long>(S.n);
+  const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  const double xnu = S.xnu, half = 0.5;
+  const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
+  // ---- x (operator kernels + two elementwise passes), transeq.f90:114-146,442-444
+  {
+    double *ta = B(S.w[9]), *tb = B(S.w[10]), *tc = B(S.w[11]), *td = B(S.w[12]), *te = B(S.w[13]), *tf = B(S.w[14]);
+    double *rx = rhs[0][0], *ry = rhs[0][1], *rz = rhs[0][2];
+    map(ctx, n, [=] __device__(long long q) { const double a = u[q]; ta[q] = a * a; tb[q] = a * v[q]; tc[q] = a * w[q]; });
+    run(ctx, S.d1[0][1], ta, td); run(ctx, S.d1[0][0], tb, te); run(ctx, S.d1[0][0], tc, tf);
+    run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);
+    map(ctx, n, [=] __device__(long long q) { const double a = u[q]; td[q] = td[q] + a * ta[q]; te[q] = te[q] + a * tb[q]; tf[q] = tf[q] + a * tc[q]; });
+    run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);
+    map(ctx, n, [=] __device__(long long q) {
+      rx[q] = xnu * ta[q] - half * td[q]; ry[q] = xnu * tb[q] - half * te[q]; rz[q] = xnu * tc[q] - half * tf[q];
+    });
+  }
+  // ---- y, transeq.f90:188-219,336-338
+  {
+    const double *f[3] = {u, v, w};
+    double *o[3] = {rhs[1][0], rhs[1][1], rhs[1][2]};
+    launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, o, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny);
+  }
+  // ---- z, transeq.f90:236-314 (z pencils)
+  {
+    double *t0 = B(S.w[9]), *t1 = B(S.w[10]), *t2 = B(S.w[11]), *o0 = B(S.w[12]), *o1 = B(S.w[13]), *o2 = B(S.w[14]);
+    const double *u3 = TR(ctx, S, 1, u, t0, S.id_v), *v3 = TR(ctx, S, 1, v, t1, S.id_v), *w3 = TR(ctx, S, 1, w, t2, S.id_v);
+    const double *f[3] = {u3, v3, w3};
+    const bool alias = S.nranks == 1;
+    double *o[3] = {alias ? rhs[2][0] : o0, alias ? rhs[2][1] : o1, alias ? rhs[2][2] : o2};
+    const long long lanes = static_cast<long long>(nx) * S.nyl;
+    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, f, o, lanes, nz, 1, lanes, lanes * nz);
+    if (!alias)
+      for (int c = 0; c < 3; ++c) transpose_device(ctx, 2, o[c], rhs[2][c], S.id_v, 1);
+  }
+}
+
+// intt for the fused form: dux1 = r_x + r_y + r_z formed on the fly
+static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *rhs[3][3]) {
+  const long long n = static_cast<long long>(S.n);
+  double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  const double *x0 = rhs[0][0], *x1 = rhs[0][1], *x2 = rhs[0][2], *y0 = rhs[1][0], *y1 = rhs[1][1], *y2 = rhs[1][2];
+  const double *z0 = rhs[2][0], *z1 = rhs[2][1], *z2 = rhs[2][2];
+  if (S.p.itimescheme == 1) {
+    const double g = S.gdt[0];
+    map(ctx, n, [=] __device__(long long q) {
+      u[q] = g * ((z0[q] + y0[q]) + x0[q]) + u[q]; v[q] = g * ((z1[q] + y1[q]) + x1[q]) + v[q]; w[q] = g * ((z2[q] + y2[q]) + x2[q]) + w[q];
+    });
+    return;
+  }
+  double *a2 = B(S.dux[1]), *b2 = B(S.duy[1]), *c2 = B(S.duz[1]);
+  if (itr == 1) {
+    const double g = S.gdt[0];
+    map(ctx, n, [=] __device__(long long q) {
+      const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
+      u[q] = g * x + u[q]; v[q] = g * y + v[q]; w[q] = g * z + w[q];
+      a2[q] = x; b2[q] = y; c2[q] = z;
+    });
+  } else {
+    const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
+    map(ctx, n, [=] __device__(long long q) {
+      const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
+      u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
+      a2[q] = x; b2[q] = y; c2[q] = z;
+    });
+  }
 }
 
 // time_integrators.f90:71-74,151-157 for the three components at once
@@ -446,8 +539,14 @@ void solver_step(Ctx &ctx, int nsteps) {
   for (int st = 0; st < nsteps; ++st) {
     S.itime += 1;
     for (int itr = 1; itr <= S.iadvance; ++itr) {  // xcompact3d.f90:46-88
-      momentum_rhs(ctx, S, B(S.dux[0]), B(S.duy[0]), B(S.duz[0]));
-      intt3(ctx, S, itr);
+      if (S.fused[1] && S.fused[2]) {
+        double *rhs[3][3] = {{B(S.w[0]), B(S.w[1]), B(S.w[2])}, {B(S.w[3]), B(S.w[4]), B(S.w[5])}, {B(S.w[6]), B(S.w[7]), B(S.w[8])}};
+        momentum_rhs_fused(ctx, S, rhs);
+        intt3_fused(ctx, S, itr, rhs);
+      } else {
+        momentum_rhs(ctx, S, B(S.dux[0]), B(S.duy[0]), B(S.duz[0]));
+        intt3(ctx, S, itr);
+      }
       pre_correc(ctx, S);
       divergence(ctx, S, B(S.pp3), 1);
       poisson_solve_device(ctx, B(S.pp3));

@@ -245,6 +245,8 @@ const TriTable &get_tri(Ctx &ctx, const double *f, const double *s, const double
   X3D_CUDA(cudaMemcpyAsync(T->d_scan, scan.data(), scan.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   X3D_CUDA(cudaMemcpyAsync(T->d_chunk, chunk.data(), chunk.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));  // host vectors go out of scope
+  T->h_rows = std::move(rows);
+  T->h_scan = std::move(scan);
   const TriTable &ref = *T;
   ctx.tri_cache[h] = std::move(T);
   return ref;
