@@ -65,12 +65,35 @@ bool mom_pair_plan(int n, int L, MomGeom &g, size_t &smem) {
   g.n = n;
   g.nc = (n + L - 1) / L;
   if (g.nc > 32 || g.nc < mom_tabs(L)) return false;
-  g.slot_rows = 8 + n + 8;
+  const int slot_rows = 8 + n + 8;
+  g.slot_bytes = slot_rows * 128;
   const size_t tail = static_cast<size_t>(2) * 3 * mom_tabs(L) * L * 16 + 2 * 320 * 8 + 2 * 3 * 8;
-  const long long overrun = static_cast<long long>(g.nc * L + 8 + HALO - g.slot_rows) * 128;
+  const long long overrun = static_cast<long long>(g.nc * L + 8 + HALO - slot_rows) * 128;
   if (overrun > static_cast<long long>(tail)) return false;
-  smem = static_cast<size_t>(3) * g.slot_rows * 128 + tail;
+  smem = static_cast<size_t>(3) * g.slot_bytes + tail;
   return smem <= 227 * 1024;
+}
+
+// x lines: 16 lines of pitch n+8 doubles per slot
+bool mom_x_plan(int n, int L, MomGeom &g, size_t &smem) {
+  if (L != 17 && L != 9) return false;
+  if ((n & 1) || n < 64) return false;
+  g.n = n;
+  g.nc = (n + L - 1) / L;
+  if (g.nc > 32 || g.nc < mom_tabs(L)) return false;
+  g.pitch = n + 2 * HALO;
+  g.slot_bytes = ((16 * g.pitch * 8 + 1023) / 1024) * 1024;
+  const size_t tail = static_cast<size_t>(2) * 3 * mom_tabs(L) * L * 16 + 2 * 320 * 8 + 2 * 3 * 8;
+  // the last chunk's window may read up to nc*L + HALO elements of the last line of a slot
+  const long long overrun = (15LL * g.pitch + g.nc * L + 2 * HALO) * 8 - g.slot_bytes;
+  if (overrun > static_cast<long long>(tail)) return false;
+  smem = static_cast<size_t>(3) * g.slot_bytes + tail;
+  return smem <= 227 * 1024;
+}
+bool mom_x_eligible(int n, int L) {
+  MomGeom g{};
+  size_t smem;
+  return mom_x_plan(n, L, g, smem);
 }
 
 bool mom_pair_eligible(int n, int L) {
@@ -108,8 +131,39 @@ void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, con
     ctx.launches++;
   };
   ProfScope ps(ctx, axis == 1 ? "momentum_fused_y(k_mom_pair)" : "momentum_fused_z(k_mom_pair)");
-  if (M1.L == 17) { if (nt4) launch(k_mom_pair<17, 4>); else launch(k_mom_pair<17, 2>); }
-  else { if (nt4) launch(k_mom_pair<9, 4>); else launch(k_mom_pair<9, 2>); }
+  if (M1.L == 17) { if (nt4) launch(k_mom_pair<17, 4, false>); else launch(k_mom_pair<17, 2, false>); }
+  else { if (nt4) launch(k_mom_pair<9, 4, false>); else launch(k_mom_pair<9, 2, false>); }
+}
+
+// x lines: fields are (n, nlines) arrays with contiguous lines
+void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
+                  const double *const f[3], double *const out[3], int n, long long nlines) {
+  MomGeom g{};
+  size_t smem = 0;
+  if (!M1.ok || !M2.ok || M1.L != M2.L || !mom_x_plan(n, M1.L, g, smem)) throw Error("fused x momentum kernel: ineligible call");
+  for (int q = 0; q < 3; ++q) {
+    if ((reinterpret_cast<uintptr_t>(f[q]) | reinterpret_cast<uintptr_t>(out[q])) & 15u) throw Error("fused x momentum kernel: unaligned field");
+    g.fin[q] = f[q]; g.fout[q] = out[q];
+  }
+  g.nlines = nlines;
+  g.npos = (nlines + 15) / 16;
+  g.nbx = 1;
+  g.ia = 0; g.ic1 = 1; g.ic2 = 2;
+  g.xnu = xnu;
+  MomMaps maps{};
+  MomTabs tb{reinterpret_cast<const double2 *>(M1.d_c), reinterpret_cast<const double2 *>(M2.d_c), M1.d_scan, M2.d_scan};
+  const bool nt4 = op2.c[2] != 0.0 || op2.c[3] != 0.0;
+  auto launch = [&](auto kern) {
+    X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    long long blocks = ctx.sm_count;
+    if (blocks > g.npos) blocks = g.npos;
+    kern<<<static_cast<unsigned>(blocks), MOM_THREADS, smem, ctx.stream>>>(op1, op2, maps, tb, g);
+    X3D_CUDA(cudaGetLastError());
+    ctx.launches++;
+  };
+  ProfScope ps(ctx, "momentum_fused_x(k_mom_pair)");
+  if (M1.L == 17) { if (nt4) launch(k_mom_pair<17, 4, true>); else launch(k_mom_pair<17, 2, true>); }
+  else { if (nt4) launch(k_mom_pair<9, 4, true>); else launch(k_mom_pair<9, 2, true>); }
 }
 
 }  // namespace x3d

@@ -17,5 +17,9 @@ void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, con
                      const double *const f[3], double *const out[3], long long n1, int nline, long long nouter, long long sline,
                      long long souter);
 bool mom_pair_eligible(int n, int L);
+// x lines (contiguous): f / out are (n, nlines) arrays
+void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
+                  const double *const f[3], double *const out[3], int n, long long nlines);
+bool mom_x_eligible(int n, int L);
 
 }  // namespace x3d

@@ -26,9 +26,14 @@ struct MomMaps {
 };
 struct MomGeom {
   int nbx;
-  long long npos;       // tile positions = nbx * nouter
-  int slot_rows;
-  int nbox, br;         // data boxes per tile
+  long long npos;       // tile positions = nbx * nouter (y/z) or ceil(nlines / 16) (x)
+  int slot_bytes;
+  int nbox, br;         // data boxes per tile (y/z)
+  // x lines: 16 contiguous lines per tile, moved by 1-D bulk copies
+  const double *fin[3];
+  double *fout[3];
+  long long nlines;
+  int pitch;            // doubles per line in shared memory (n + 8)
   int n;                // line length
   int nc;               // chunks per line
   int ia, ic1, ic2;     // field index of the advecting velocity and of the two other components
@@ -98,7 +103,36 @@ __device__ __forceinline__ void pair_solve_periodic(dd2 (&x)[L], const double2 *
   }
 }
 
-template <int L, int NT2>
+// how a thread reaches element j of its window (two lines at once) inside a ring slot
+template <bool XD>
+struct TileAcc;
+template <>
+struct TileAcc<false> {  // y / z: [row][16 lanes], 128B swizzle, rows 8 .. 8+n-1 hold the data
+  int off[8];
+  __device__ __forceinline__ void init(int jw, int q0, int) {
+    const int base = q0 + 8 - HALO;
+    X3D_UNROLL
+    for (int p = 0; p < 8; ++p) off[p] = base * 8 + (jw ^ ((base + p) & 7));
+  }
+  __device__ __forceinline__ dd2 ld(const unsigned char *slot, int j) const { return reinterpret_cast<const dd2 *>(slot)[off[j & 7] + 8 * j]; }
+  __device__ __forceinline__ void st(unsigned char *slot, int j, dd2 v) const { reinterpret_cast<dd2 *>(slot)[off[j & 7] + 8 * j] = v; }
+};
+template <>
+struct TileAcc<true> {  // x: 16 contiguous lines of pitch n+8 doubles (4 ghosts each side); the pair is two lines
+  int o0, o1;
+  __device__ __forceinline__ void init(int jw, int q0, int pitch) { o0 = 2 * jw * pitch + q0; o1 = o0 + pitch; }
+  __device__ __forceinline__ dd2 ld(const unsigned char *slot, int j) const {
+    const double *d = reinterpret_cast<const double *>(slot);
+    return {d[o0 + j], d[o1 + j]};
+  }
+  __device__ __forceinline__ void st(unsigned char *slot, int j, dd2 v) const {
+    double *d = reinterpret_cast<double *>(slot);
+    d[o0 + j] = v.x;
+    d[o1 + j] = v.y;
+  }
+};
+
+template <int L, int NT2, bool XD>
 __global__ void __launch_bounds__(MOM_THREADS, 1)
     k_mom_pair(const __grid_constant__ DevOp op1, const __grid_constant__ DevOp op2, const __grid_constant__ MomMaps maps,
                const MomTabs tb, const MomGeom g) {
@@ -106,8 +140,8 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
   constexpr int NB = 3;
   constexpr int MOM_TABS = mom_tabs(L), MOM_H = mom_head(L);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const int slot_bytes = g.slot_rows * 128;
-  double2 *c1 = reinterpret_cast<double2 *>(smem_raw + NB * slot_bytes);  // [3][7 L]
+  const int slot_bytes = g.slot_bytes;
+  double2 *c1 = reinterpret_cast<double2 *>(smem_raw + NB * slot_bytes);  // [3][MOM_TABS L]
   double2 *c2 = c1 + 3 * MOM_TABS * L;
   double *scan1 = reinterpret_cast<double *>(c2 + 3 * MOM_TABS * L);     // [10][32]
   double *scan2 = scan1 + 320;
@@ -133,28 +167,46 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
     // ---------------- TMA producer ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp != PAIR_WARPS || lane != 0) return;
-    const unsigned in_bytes = (static_cast<unsigned>(g.nbox) * g.br + 16u) * 128u;
     auto load = [&](long long p, int q) {
       const long long pos = first + p * step;
-      const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
       const int slot = static_cast<int>((p + 1 + q) % 3);
       unsigned char *dst = smem_raw + slot * slot_bytes;
-      const CUtensorMap *tm = &maps.in[fld[q]], *th = &maps.halo[fld[q]];
-      mbar_expect_tx(full + slot, in_bytes);
-      for (int b = 0; b < g.nbox; ++b) tma_load_3d(dst + (8 + b * g.br) * 128, tm, bx * 16, b * g.br, by, full + slot);
-      tma_load_3d(dst, th, bx * 16, n - 8, by, full + slot);
-      tma_load_3d(dst + (8 + n) * 128, th, bx * 16, 0, by, full + slot);
+      if constexpr (XD) {
+        const long long line0 = pos * 16;
+        const int nl = static_cast<int>(g.nlines - line0 < 16 ? g.nlines - line0 : 16);
+        const double *src = g.fin[fld[q]] + line0 * n;
+        mbar_expect_tx(full + slot, static_cast<unsigned>(nl) * n * 8u);
+        for (int l = 0; l < nl; ++l)
+          bulk_g2s(dst + (l * g.pitch + HALO) * 8, src + static_cast<long long>(l) * n, static_cast<unsigned>(n) * 8u, full + slot);
+      } else {
+        const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
+        const CUtensorMap *tm = &maps.in[fld[q]], *th = &maps.halo[fld[q]];
+        mbar_expect_tx(full + slot, (static_cast<unsigned>(g.nbox) * g.br + 16u) * 128u);
+        for (int b = 0; b < g.nbox; ++b) tma_load_3d(dst + (8 + b * g.br) * 128, tm, bx * 16, b * g.br, by, full + slot);
+        tma_load_3d(dst, th, bx * 16, n - 8, by, full + slot);
+        tma_load_3d(dst + (8 + n) * 128, th, bx * 16, 0, by, full + slot);
+      }
     };
     if (mine > 0) { load(0, 2); load(0, 0); load(0, 1); }
     for (long long p = 0; p < mine; ++p) {
       const long long pos = first + p * step;
-      const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
       for (int q = 0; q < 3; ++q) {
         const int slot = static_cast<int>((p + 1 + q) % 3);
         mbar_wait(done + slot, static_cast<unsigned>(p & 1));
         const unsigned char *src = smem_raw + slot * slot_bytes;
-        const CUtensorMap *tm = &maps.out[fld[q]];
-        for (int b = 0; b < g.nbox; ++b) tma_store_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
+        if constexpr (XD) {
+          const long long line0 = pos * 16;
+          const int nl = static_cast<int>(g.nlines - line0 < 16 ? g.nlines - line0 : 16);
+          double *dst = g.fout[fld[q]] + line0 * n;
+          for (int l = 0; l < nl; ++l)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * n),
+                         "r"(smem_u32(src + (l * g.pitch + HALO) * 8)), "r"(static_cast<unsigned>(n) * 8u)
+                         : "memory");
+        } else {
+          const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
+          const CUtensorMap *tm = &maps.out[fld[q]];
+          for (int b = 0; b < g.nbox; ++b) tma_store_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
+        }
         bulk_commit();
         if (p + 1 < mine) {
           // the slot is free once the store has left shared memory; for the next position it takes
@@ -174,31 +226,42 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
   const int cl = lane < nc ? lane : nc - 1;
   const bool live = lane < nc;
   const int q0 = cl * L;
-  const int base = q0 + 8 - HALO;
-  int off[8];
-  X3D_UNROLL
-  for (int p = 0; p < 8; ++p) off[p] = base * 8 + (jw ^ ((base + p) & 7));
+  TileAcc<XD> acc;
+  acc.init(jw, q0, g.pitch);
   const int tab = cl < MOM_H ? cl : (cl >= nc - MOM_H - 1 ? MOM_H + 1 + cl - (nc - MOM_H - 1) : MOM_H);
   const double2 *s1 = c1 + tab * L, *w1 = c1 + MOM_TABS * L + tab * L, *b1 = c1 + 2 * MOM_TABS * L + tab * L;
   const double2 *s2 = c2 + tab * L, *w2 = c2 + MOM_TABS * L + tab * L, *b2 = c2 + 2 * MOM_TABS * L + tab * L;
   const double xnu = g.xnu;
+  // x lines: the wrap ghosts of a freshly loaded tile are copied inside shared memory, each warp for its two lines
+  auto ghosts = [&](unsigned char *slot) {
+    if constexpr (XD) {
+      if (lane < 8) {
+        double *d = reinterpret_cast<double *>(slot) + (2 * jw + (lane >> 2)) * g.pitch + HALO;
+        const int gq = lane & 3;
+        d[-1 - gq] = d[n - 1 - gq];
+        d[n + gq] = d[gq];
+      }
+      __syncwarp();
+    }
+  };
   for (long long p = 0; p < mine; ++p) {
     const unsigned par = static_cast<unsigned>(p & 1);
     const int slot_a = static_cast<int>((p + 3) % 3);
-    const dd2 *bufA = reinterpret_cast<const dd2 *>(smem_raw + slot_a * slot_bytes);
+    unsigned char *bufA = smem_raw + slot_a * slot_bytes;
     mbar_wait(full + slot_a, par);
+    ghosts(bufA);
 #pragma unroll 1
     for (int q = 0; q < 3; ++q) {
       const int slot = static_cast<int>((p + 1 + q) % 3);
-      dd2 *bufC = reinterpret_cast<dd2 *>(smem_raw + slot * slot_bytes);
-      if (q < 2) mbar_wait(full + slot, par);
+      unsigned char *bufC = smem_raw + slot * slot_bytes;
+      if (q < 2) { mbar_wait(full + slot, par); ghosts(bufC); }
       dd2 r[L];
       {  // xnu * D2(c)
         dd2 x[L];
         {
           dd2 win[NWIN];
           X3D_UNROLL
-          for (int j = 0; j < NWIN; ++j) win[j] = bufC[off[j & 7] + 8 * j];
+          for (int j = 0; j < NWIN; ++j) win[j] = acc.ld(bufC, j);
           X3D_UNROLL
           for (int m = 0; m < L; ++m) {
             const dd2 v = rhs_interior<D2, NT2, NWIN, dd2>(op2, win, m);
@@ -217,7 +280,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
         {
           dd2 win[NWIN];
           X3D_UNROLL
-          for (int j = 0; j < NWIN; ++j) win[j] = bufC[off[j & 7] + 8 * j];
+          for (int j = 0; j < NWIN; ++j) win[j] = acc.ld(bufC, j);
           X3D_UNROLL
           for (int m = 0; m < L; ++m) {
             const dd2 v = rhs_interior<D1, 2, NWIN, dd2>(op1, win, m);
@@ -229,7 +292,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
         pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, q0, n);
         X3D_UNROLL
         for (int m = 0; m < L; ++m) {
-          const dd2 a = bufA[off[(m + HALO) & 7] + 8 * (m + HALO)];
+          const dd2 a = acc.ld(bufA, m + HALO);
           r[m].x = fma(-0.5 * a.x, x[m].x, r[m].x);
           r[m].y = fma(-0.5 * a.y, x[m].y, r[m].y);
         }
@@ -241,8 +304,8 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
           dd2 win[NWIN];
           X3D_UNROLL
           for (int j = 0; j < NWIN; ++j) {
-            const dd2 cc = bufC[off[j & 7] + 8 * j];
-            const dd2 aa = bufA[off[j & 7] + 8 * j];
+            const dd2 cc = acc.ld(bufC, j);
+            const dd2 aa = acc.ld(bufA, j);
             win[j] = {cc.x * aa.x, cc.y * aa.y};
           }
           X3D_UNROLL
@@ -264,7 +327,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
       if (live) {
         X3D_UNROLL
         for (int m = 0; m < L; ++m)
-          if (q0 + m < n) bufC[off[(m + HALO) & 7] + 8 * (m + HALO)] = r[m];
+          if (q0 + m < n) acc.st(bufC, m + HALO, r[m]);
       }
       fence_proxy_async();
       __syncwarp();

@@ -259,11 +259,12 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   {
     const char *e = getenv("X3D_FUSED");
     const bool want = !(e && atoi(e) == 0);
-    for (int a = 1; a < 3 && want; ++a) {
+    for (int a = 0; a < 3 && want; ++a) {
       const int n = nn[a];
       const int L = pick_L_contig(n);
       const long long lanes = (a == 1) ? p.nx : static_cast<long long>(p.nx) * nyl;
-      if (!S->A[a].periodic || L <= 0 || !mom_pair_eligible(n, L) || (lanes & 1) || (p.nx & 1)) continue;
+      if (!S->A[a].periodic || L <= 0 || (p.nx & 1)) continue;
+      if (a == 0 ? !mom_x_eligible(n, L) : (!mom_pair_eligible(n, L) || (lanes & 1))) continue;
       const PreOp &o1 = S->d1[a][0], &o2 = S->d2[a][0];
       const TriTable &T1 = get_tri(ctx, o1.call.f, o1.call.s, o1.call.w, n, L, true, o1.op.alpha, nullptr);
       const TriTable &T2 = get_tri(ctx, o2.call.f, o2.call.s, o2.call.w, n, L, true, o2.op.alpha, nullptr);
@@ -371,8 +372,12 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *rhs[3][3]) {
   const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   const double xnu = S.xnu, half = 0.5;
   const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
-  // ---- x (operator kernels + two elementwise passes), transeq.f90:114-146,442-444
-  {
+  // ---- x, transeq.f90:114-146,442-444
+  if (S.fused[0]) {
+    const double *f[3] = {u, v, w};
+    double *o[3] = {rhs[0][0], rhs[0][1], rhs[0][2]};
+    launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, o, nx, static_cast<long long>(ny) * S.nzl);
+  } else {  // operator kernels + three elementwise passes
     double *ta = B(S.w[9]), *tb = B(S.w[10]), *tc = B(S.w[11]), *td = B(S.w[12]), *te = B(S.w[13]), *tf = B(S.w[14]);
     double *rx = rhs[0][0], *ry = rhs[0][1], *rz = rhs[0][2];
     map(ctx, n, [=] __device__(long long q) { const double a = u[q]; ta[q] = a * a; tb[q] = a * v[q]; tc[q] = a * w[q]; });

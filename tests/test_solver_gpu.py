@@ -39,7 +39,7 @@ def test_tgv_65_free_slip_matches_reference_golden(golden_dir):
 
 @pytest.mark.parametrize("nn,ncl", [((64, 64, 64), (0,) * 6), ((48, 40, 56), (0,) * 6), ((33, 33, 40), (1, 1, 1, 1, 0, 0)),
                                     # line lengths for which the fused momentum kernels run (y: L=9, z: L=17; ragged lane blocks)
-                                    ((40, 168, 304), (0,) * 6), ((24, 304, 176), (0,) * 6)])
+                                    ((40, 168, 304), (0,) * 6), ((24, 304, 176), (0,) * 6), ((170, 176, 168), (0,) * 6)])
 def test_solver_matches_oracle(nn, ncl):
     from incompact3d_b200 import X3D
     length = 2 * np.pi
@@ -78,5 +78,6 @@ def test_solver_matches_oracle(nn, ncl):
     if min(nn[1], nn[2]) >= 168 and os.environ.get("X3D_FUSED", "1") != "0":
         names = {r["name"] for r in x.profile_step(1)}   # the fused momentum kernels were the ones that ran
         assert "momentum_fused_y(k_mom_pair)" in names and "momentum_fused_z(k_mom_pair)" in names, names
+        assert ("momentum_fused_x(k_mom_pair)" in names) == (nn[0] >= 168), names
     Ls.x3do_solver_destroy(s)
     x.close()
