@@ -154,6 +154,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     from incompact3d_b200 import X3D
@@ -264,7 +265,7 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"TGV periodic {n}^3 Re=1600 RK3 dt={dt:g} (BASELINE configs[1])",
-                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), NCCL all-to-all transposes"), "l2": "fields are 1 GiB each, far larger than the 126 MB L2; no flush needed",
+                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), transposes = one kernel storing into peer pencils over NVLink (CUDA IPC), device-side flag barriers"), "l2": "fields are 1 GiB each, far larger than the 126 MB L2; no flush needed",
                    "diagnostics_after_run": diag},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }

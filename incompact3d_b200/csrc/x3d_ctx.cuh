@@ -4,18 +4,32 @@
 
 namespace x3d {
 
+// process-wide registry of the library's own device allocations (base -> size): lets the peer-to-peer
+// transposes find the allocation a pointer belongs to (cudaIpcGetMemHandle needs the base)
+void register_alloc(void *p, size_t n);
+void unregister_alloc(void *p);
+bool find_alloc(const void *q, void **base, size_t *size);
+
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
   void reserve(size_t n) {
     if (n <= bytes) return;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
+    release();
+    // whole 2 MiB pages: the allocation is then never carved out of a driver pool page shared with other
+    // allocations, so its CUDA IPC handle maps exactly this buffer in a peer process (peer-to-peer transposes)
+    const size_t page = size_t(2) << 20;
+    n = (n + page - 1) / page * page;
     X3D_CUDA(cudaMalloc(&p, n));
     bytes = n;
+    register_alloc(p, n);
   }
-  ~DevBuf() { if (p) cudaFree(p); }
+  void release() {
+    if (p) { unregister_alloc(p); cudaFree(p); }
+    p = nullptr;
+    bytes = 0;
+  }
+  ~DevBuf() { release(); }
 };
 
 struct ProfRec {

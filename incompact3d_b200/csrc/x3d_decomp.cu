@@ -14,6 +14,8 @@
 // one rank per group) degenerates to a bit-exact device copy.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <array>
+#include <cstdlib>
 #include <cstring>
 #include "x3d_state.cuh"
 
@@ -40,6 +42,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -57,7 +60,7 @@ static NcclApi &nccl() {
   if (!api.field) throw Error(std::string("libnccl lacks ") + name)
   X3D_SYM(GetUniqueId, "ncclGetUniqueId"); X3D_SYM(CommInitRank, "ncclCommInitRank"); X3D_SYM(CommSplit, "ncclCommSplit");
   X3D_SYM(CommDestroy, "ncclCommDestroy"); X3D_SYM(Send, "ncclSend"); X3D_SYM(Recv, "ncclRecv");
-  X3D_SYM(AllReduce, "ncclAllReduce"); X3D_SYM(GroupStart, "ncclGroupStart"); X3D_SYM(GroupEnd, "ncclGroupEnd");
+  X3D_SYM(AllReduce, "ncclAllReduce"); X3D_SYM(AllGather, "ncclAllGather"); X3D_SYM(GroupStart, "ncclGroupStart"); X3D_SYM(GroupEnd, "ncclGroupEnd");
   X3D_SYM(GetErrorString, "ncclGetErrorString");
 #undef X3D_SYM
   return api;
@@ -93,7 +96,25 @@ struct DecompImpl : DecompState {
   std::vector<std::array<TransposePlan, 4>> plans;
   DevBuf sendbuf, recvbuf, meta;
   std::vector<void *> dev_allocs;
+  // ---- peer-to-peer transposes (all ranks on one NVLink/NVSwitch node) ----------------------------
+  // A transpose is ONE kernel that reads the local pencil and stores every element straight into the
+  // destination pencil of the rank that owns it (peer memory mapped through CUDA IPC), bracketed by two
+  // device-side flag barriers of the group; no pack / unpack pass and no staging buffer.
+  struct Group {
+    int np = 1, me = 0;
+    ncclComm_t comm = nullptr;
+    DevBuf flags;                         // my flag array [np] (peers store their epoch here)
+    DevBuf d_peer_flags;                  // device array [np] of pointers to every member's flag array
+    unsigned long long epoch = 0;
+    std::map<const void *, DevBuf> dst_cache;   // local destination pointer -> device array [np] of member pointers
+    std::map<const void *, bool> dst_bad;
+  };
+  Group grp_row, grp_col;
+  bool p2p = false;
+  DevBuf xchg_send, xchg_recv;
+  std::map<std::array<unsigned char, 64>, void *> ipc_opened;
   ~DecompImpl() override {
+    for (auto &kv : ipc_opened) cudaIpcCloseMemHandle(kv.second);
     for (void *p : dev_allocs) cudaFree(p);
     if (have_nccl) {
       if (comm_row) nccl().CommDestroy(comm_row);
@@ -232,6 +253,8 @@ static TransposePlan &get_plan(Ctx &ctx, DecompImpl &D, int id, int which) {
   return T;
 }
 
+static void p2p_setup_group(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, ncclComm_t comm, int np, int me);
+
 void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id) {
   X3D_CUDA(cudaSetDevice(ctx.device));
   if (p_row < 1 || p_col < 1 || p_row * p_col != nranks) throw Error("x3d_decomp_init: p_row*p_col must equal nranks");
@@ -252,6 +275,10 @@ void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int ran
     X3D_NCCL(N.CommSplit(D->world, D->col, D->row, &D->comm_row, nullptr));
     X3D_NCCL(N.CommSplit(D->world, D->row, D->col, &D->comm_col, nullptr));
     D->have_nccl = true;
+    const char *e = getenv("X3D_P2P");
+    D->p2p = !(e && atoi(e) == 0);
+    if (D->p2p) p2p_setup_group(ctx, *D, D->grp_row, D->comm_row, p_row, D->row);
+    if (D->p2p) p2p_setup_group(ctx, *D, D->grp_col, D->comm_col, p_col, D->col);
   }
   ctx.decomp = std::move(D);
 }
@@ -309,6 +336,153 @@ void transpose_unpack(Ctx &ctx, int which, const double *d_packed, double *d_dst
   boxcopy<false>(ctx, get_plan(ctx, D, id, which).recv, const_cast<double *>(d_packed), d_dst, elem);
 }
 
+// ---- peer-to-peer path ---------------------------------------------------------------------------------
+namespace {
+
+struct XchgRec {            // what every member publishes about one of its buffers
+  unsigned char handle[64];
+  unsigned long long offset;
+  unsigned long long valid;
+};
+
+// one thread per group member: publish my epoch in the member's flag array, wait for the member's epoch in mine
+__global__ void k_group_barrier(unsigned long long *const *__restrict__ peer_flags, unsigned long long *my_flags, int me, int np,
+                                unsigned long long epoch) {
+  const int m = threadIdx.x;
+  if (m >= np) return;
+  __threadfence_system();
+  unsigned long long *theirs = peer_flags[m] + me;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+  unsigned long long seen;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flags + m) : "memory");
+    if (clock64() - t0 > 20000000000LL) asm volatile("trap;");  // ~10 s: a member never arrived -> fail instead of hanging
+  } while (seen < epoch);
+}
+
+// element (i,j,k) of the local source pencil -> destination pencil of the member that owns it
+template <typename T>
+__global__ void k_p2p_transpose(const T *__restrict__ src, T *const *__restrict__ dst, int d0, int d1, int d2, int as, int ar,
+                                const int *__restrict__ blk_of, const int *__restrict__ blk_start, const int *__restrict__ blk_size,
+                                int my_off, int R0, int R1, int R2) {
+  const long long tot = static_cast<long long>(d0) * d1 * d2;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < tot;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int c[3];
+    c[0] = static_cast<int>(idx % d0);
+    c[1] = static_cast<int>((idx / d0) % d1);
+    c[2] = static_cast<int>(idx / (static_cast<long long>(d0) * d1));
+    const int cs = as == 0 ? c[0] : (as == 1 ? c[1] : c[2]);
+    const int m = blk_of[cs];
+    int D[3] = {R0, R1, R2};
+    const int bs = blk_size[m], cl = cs - blk_start[m];
+    if (as == 0) { c[0] = cl; D[0] = bs; } else if (as == 1) { c[1] = cl; D[1] = bs; } else { c[2] = cl; D[2] = bs; }
+    if (ar == 0) c[0] += my_off; else if (ar == 1) c[1] += my_off; else c[2] += my_off;
+    dst[m][c[0] + static_cast<long long>(D[0]) * (c[1] + static_cast<long long>(D[1]) * c[2])] = src[idx];
+  }
+}
+
+}  // namespace
+
+static void group_barrier(Ctx &ctx, DecompImpl::Group &G) {
+  G.epoch++;
+  k_group_barrier<<<1, 32, 0, ctx.stream>>>(static_cast<unsigned long long *const *>(G.d_peer_flags.p),
+                                             static_cast<unsigned long long *>(G.flags.p), G.me, G.np, G.epoch);
+  X3D_CUDA(cudaGetLastError());
+  ctx.launches++;
+}
+
+// all members publish (IPC handle, offset) of one local buffer; returns the members' mapped pointers, or false
+// when any member cannot export its buffer (then every member falls back to the NCCL path)
+static bool exchange_pointers(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, const void *local, std::vector<void *> &out) {
+  XchgRec mine{};
+  void *base = nullptr;
+  size_t size = 0;
+  if (local && find_alloc(local, &base, &size)) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, base) == cudaSuccess) {
+      static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+      std::memcpy(mine.handle, &h, 64);
+      mine.offset = static_cast<unsigned long long>(static_cast<const char *>(local) - static_cast<const char *>(base));
+      mine.valid = 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  D.xchg_send.reserve(sizeof(XchgRec));
+  D.xchg_recv.reserve(sizeof(XchgRec) * G.np);
+  X3D_CUDA(cudaMemcpyAsync(D.xchg_send.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_NCCL(nccl().AllGather(D.xchg_send.p, D.xchg_recv.p, sizeof(XchgRec), ncclChar, G.comm, ctx.stream));
+  std::vector<XchgRec> all(G.np);
+  X3D_CUDA(cudaMemcpyAsync(all.data(), D.xchg_recv.p, sizeof(XchgRec) * G.np, cudaMemcpyDeviceToHost, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int m = 0; m < G.np; ++m)
+    if (!all[m].valid) return false;
+  out.assign(G.np, nullptr);
+  bool ok = true;
+  for (int m = 0; m < G.np; ++m) {
+    if (m == G.me) { out[m] = const_cast<void *>(local); continue; }
+    std::array<unsigned char, 64> key;
+    std::memcpy(key.data(), all[m].handle, 64);
+    auto it = D.ipc_opened.find(key);
+    void *mapped = nullptr;
+    if (it != D.ipc_opened.end()) {
+      mapped = it->second;
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, all[m].handle, 64);
+      if (cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; mapped = nullptr; }
+      else D.ipc_opened[key] = mapped;
+    }
+    out[m] = mapped ? static_cast<char *>(mapped) + all[m].offset : nullptr;
+  }
+  // agreement: a member that failed to map makes everybody fall back
+  unsigned long long flag = ok ? 1 : 0;
+  XchgRec v{};
+  v.valid = flag;
+  X3D_CUDA(cudaMemcpyAsync(D.xchg_send.p, &v, sizeof(v), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_NCCL(nccl().AllGather(D.xchg_send.p, D.xchg_recv.p, sizeof(XchgRec), ncclChar, G.comm, ctx.stream));
+  X3D_CUDA(cudaMemcpyAsync(all.data(), D.xchg_recv.p, sizeof(XchgRec) * G.np, cudaMemcpyDeviceToHost, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int m = 0; m < G.np; ++m)
+    if (!all[m].valid) return false;
+  return true;
+}
+
+static void p2p_setup_group(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, ncclComm_t comm, int np, int me) {
+  G.np = np; G.me = me; G.comm = comm;
+  if (np <= 1) return;
+  G.flags.reserve(sizeof(unsigned long long) * 32);
+  X3D_CUDA(cudaMemsetAsync(G.flags.p, 0, sizeof(unsigned long long) * 32, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  std::vector<void *> ptrs;
+  if (!exchange_pointers(ctx, D, G, G.flags.p, ptrs)) { D.p2p = false; return; }
+  G.d_peer_flags.reserve(sizeof(void *) * np);
+  X3D_CUDA(cudaMemcpyAsync(G.d_peer_flags.p, ptrs.data(), sizeof(void *) * np, cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+// member pointers of a destination buffer (device array), exchanged once per buffer; nullptr -> use NCCL
+static void *const *p2p_dst(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, const void *dst) {
+  // Only buffers the library allocated itself take this path: they are allocated by the same code on every
+  // member, so cache hits and misses (= collective pointer exchanges) happen on all members together.  A
+  // caller-owned buffer (e.g. a framework tensor) has no such symmetry and always uses the NCCL exchange.
+  void *base = nullptr;
+  size_t size = 0;
+  if (!find_alloc(dst, &base, &size)) return nullptr;
+  auto it = G.dst_cache.find(dst);
+  if (it != G.dst_cache.end()) return static_cast<void *const *>(it->second.p);
+  if (G.dst_bad.count(dst)) return nullptr;
+  std::vector<void *> ptrs;
+  if (!exchange_pointers(ctx, D, G, dst, ptrs)) { G.dst_bad[dst] = true; return nullptr; }
+  DevBuf &b = G.dst_cache[dst];
+  b.reserve(sizeof(void *) * G.np);
+  X3D_CUDA(cudaMemcpyAsync(b.p, ptrs.data(), sizeof(void *) * G.np, cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  return static_cast<void *const *>(b.p);
+}
+
 // device pointers; src and dst pencils of decomposition `id`
 void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem) {
   DecompImpl &D = DEC(ctx);
@@ -320,6 +494,33 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
     return;
   }
   if (!D.have_nccl) throw Error("transpose: this context was initialised without a NCCL id (pack/unpack only)");
+  if (D.p2p) {
+    DecompImpl::Group &G = (which == 0 || which == 3) ? D.grp_row : D.grp_col;
+    void *const *peers = p2p_dst(ctx, D, G, d_dst);
+    if (peers) {
+      const SidePlan &S = T.send;
+      const int ext = S.dims[S.axis], np = T.npeers;
+      const int *blk_of = S.d_meta, *bst = S.d_meta + ext, *bsz = S.d_meta + ext + np;
+      const int my_off = T.recv.blk_start[G.me];
+      group_barrier(ctx, G);  // every member has finished with its destination pencil
+      if (ns > 0) {
+        ProfScope ps(ctx, "transpose_p2p(k_p2p_transpose)");
+        if (elem == 1)
+          k_p2p_transpose<double><<<grid_for(ctx, ns), 256, 0, ctx.stream>>>(d_src, reinterpret_cast<double *const *>(peers), S.dims[0], S.dims[1],
+                                                                          S.dims[2], S.axis, T.recv.axis, blk_of, bst, bsz, my_off,
+                                                                          T.recv.dims[0], T.recv.dims[1], T.recv.dims[2]);
+        else
+          k_p2p_transpose<double2><<<grid_for(ctx, ns), 256, 0, ctx.stream>>>(reinterpret_cast<const double2 *>(d_src),
+                                                                           reinterpret_cast<double2 *const *>(peers), S.dims[0], S.dims[1], S.dims[2],
+                                                                           S.axis, T.recv.axis, blk_of, bst, bsz, my_off, T.recv.dims[0],
+                                                                           T.recv.dims[1], T.recv.dims[2]);
+        X3D_CUDA(cudaGetLastError());
+        ctx.launches++;
+      }
+      group_barrier(ctx, G);  // every member's stores into my pencil have landed
+      return;
+    }
+  }
   D.sendbuf.reserve(ns * elem * sizeof(double));
   D.recvbuf.reserve(nr * elem * sizeof(double));
   double *sb = static_cast<double *>(D.sendbuf.p), *rb = static_cast<double *>(D.recvbuf.p);

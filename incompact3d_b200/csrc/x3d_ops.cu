@@ -1,6 +1,7 @@
 // x3d_ops.cu -- host side of the compact operators: context, pointer classification,
 // staging of host fields (drop-in mode), geometry and kernel dispatch.
 #include <cstring>
+#include <mutex>
 #include "x3d_ctx.cuh"
 #include "x3d_ops_inst.cuh"
 #include "x3d_state.cuh"
@@ -19,6 +20,29 @@ Ctx::Ctx() {}
 Ctx::~Ctx() {
   tri_cache.clear();
   if (stream) cudaStreamDestroy(stream);
+}
+
+// ---- registry of library-owned device allocations -------------------------------------------------
+static std::mutex g_alloc_mu;
+static std::map<uintptr_t, size_t> g_allocs;
+void register_alloc(void *p, size_t n) {
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  g_allocs[reinterpret_cast<uintptr_t>(p)] = n;
+}
+void unregister_alloc(void *p) {
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  g_allocs.erase(reinterpret_cast<uintptr_t>(p));
+}
+bool find_alloc(const void *q, void **base, size_t *size) {
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+  auto it = g_allocs.upper_bound(a);
+  if (it == g_allocs.begin()) return false;
+  --it;
+  if (a >= it->first + it->second) return false;
+  *base = reinterpret_cast<void *>(it->first);
+  *size = it->second;
+  return true;
 }
 
 bool is_device_ptr(const void *p) {
