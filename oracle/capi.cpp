@@ -96,8 +96,64 @@ int x3do_op(const char *name, const int *dims_in, int npaire, const double *u, d
 // ---- Poisson -----------------------------------------------------------------------
 struct PoissonBox {
   AxisScheme X, Y, Z;
+  Stretch st;
   Poisson po;
 };
+// stretching_full (stretching.f90:96-318): out8 = yp, ypi, ppy, pp2y, pp4y, ppyi, pp2yi, pp4yi (ny each)
+int x3do_stretching(int istret, double beta, double yly, int ny, int nym, double *out8, double *alpha) {
+  try {
+    Stretch s;
+    s.istret = istret; s.beta = beta; s.yly = yly;
+    stretching(s, ny, nym, 0, 0, false);
+    const vec *v[8] = {&s.yp, &s.ypi, &s.ppy, &s.pp2y, &s.pp4y, &s.ppyi, &s.pp2yi, &s.pp4yi};
+    for (int q = 0; q < 8; ++q) std::memcpy(out8 + static_cast<size_t>(q) * ny, v[q]->data(), ny * sizeof(double));
+    if (alpha) *alpha = s.alpha;
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void *x3do_poisson_create_stretched(int nx, int ny, int nz, const int *ncl6, double xlx, double yly, double zlz, int ifirstder,
+                                    int ipinter, int istret, double beta) {
+  try {
+    SchemeOptions o; o.ifirstder = ifirstder; o.ipinter = ipinter;
+    auto *b = new PoissonBox();
+    b->X = make_axis(nx, ncl6[0], ncl6[1], xlx, o);
+    b->Y = make_axis(ny, ncl6[2], ncl6[3], yly, o);
+    b->Z = make_axis(nz, ncl6[4], ncl6[5], zlz, o);
+    if (istret != 0) {
+      b->st.istret = istret; b->st.beta = beta; b->st.yly = yly;
+      stretching(b->st, ny, b->Y.nm, ncl6[2], ncl6[3], b->Y.periodic);
+    }
+    b->po.init(b->X, b->Y, b->Z, istret ? &b->st : nullptr);
+    return b;
+  } catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+// tables of the solver by name; complex arrays are returned as (re,im) pairs; returns the number of doubles
+long x3do_poisson_get(void *p, const char *name, double *out, long cap) {
+  auto &po = static_cast<PoissonBox *>(p)->po;
+  const std::string n = name;
+  const vec *rv = nullptr;
+  const std::vector<cplx> *cv = nullptr;
+  if (n == "ax") rv = &po.ax; else if (n == "bx") rv = &po.bx; else if (n == "ay") rv = &po.ay; else if (n == "by") rv = &po.by;
+  else if (n == "az") rv = &po.az; else if (n == "bz") rv = &po.bz;
+  else if (n == "xkx") cv = &po.xkx; else if (n == "xk2") cv = &po.xk2; else if (n == "exs") cv = &po.exs;
+  else if (n == "yky") cv = &po.yky; else if (n == "yk2") cv = &po.yk2; else if (n == "eys") cv = &po.eys;
+  else if (n == "zkz") cv = &po.zkz; else if (n == "zk2") cv = &po.zk2; else if (n == "ezs") cv = &po.ezs;
+  else if (n == "kxyz") cv = &po.kxyz; else if (n == "a") cv = &po.a; else if (n == "a2") cv = &po.a2; else if (n == "a3") cv = &po.a3;
+  else return -1;
+  const long cnt = rv ? static_cast<long>(rv->size()) : 2 * static_cast<long>(cv->size());
+  if (out && cap >= cnt) std::memcpy(out, rv ? static_cast<const void *>(rv->data()) : static_cast<const void *>(cv->data()), cnt * sizeof(double));
+  return cnt;
+}
+// inversion5_v1 (version 1) / inversion5_v2 (version 2) on caller arrays: aaa (nx,n,nz,5) complex, eee (nx,n,nz) complex
+int x3do_inversion5(int version, double *aaa, double *eee, int nx, int n, int nz) {
+  try {
+    const size_t cnt = static_cast<size_t>(nx) * n * nz * 5;
+    std::vector<cplx> a(reinterpret_cast<cplx *>(aaa), reinterpret_cast<cplx *>(aaa) + cnt);
+    if (version == 1) inversion5_v1(a, reinterpret_cast<cplx *>(eee), nx, n, nz);
+    else { inversion5_v2(a, reinterpret_cast<cplx *>(eee), nx, n, nz); std::memcpy(aaa, a.data(), cnt * sizeof(cplx)); }
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
 void *x3do_poisson_create(int nx, int ny, int nz, const int *ncl6, double xlx, double yly, double zlz, int ifirstder,
                           int ipinter) {
   try {

@@ -163,10 +163,14 @@ class Transpiler:
         self.arrays_hint = set(arrays_hint)
 
     # -- expressions ------------------------------------------------------
-    def expr(self, s, arrays):
+    def expr(self, s, arrays, intctx=False):
+        """intctx: the expression is an array subscript or a do-loop bound, where Fortran's `/` between
+        integers is an integer division"""
         s = s.strip()
         for pat, rep in _OPS:
             s = re.sub(pat, rep, s)
+        if intctx:
+            s = re.sub(r"(?<![/!=<>])/(?![/=])", "//", s)
         # kind suffixes and d-exponents
         s = re.sub(r"(\d\.?)_mytype\b", r"\1", s)
         s = re.sub(r"(\d\.?\d*)d([+-]?\d+)", r"\1e\2", s)
@@ -183,7 +187,7 @@ class Transpiler:
                 if k < len(s) and s[k] == "(" and name not in ("and", "or", "not"):
                     e = _match_paren(s, k)
                     inner = s[k + 1:e]
-                    args = [self.index_arg(a, arrays) for a in _split_args(inner)]
+                    args = [self.index_arg(a, arrays, intctx=(name in arrays)) for a in _split_args(inner)]
                     pyname = name.replace("%", "__")
                     if name in arrays:
                         out += f"{pyname}[{', '.join(args)}]"
@@ -202,19 +206,19 @@ class Transpiler:
             i += 1
         return out
 
-    def index_arg(self, a, arrays):
+    def index_arg(self, a, arrays, intctx=False):
         a = a.strip()
         if a == ":":
             return "ALL"
         m = re.match(r"^(.*?):(.*)$", a)
         if m and "(" not in a:
-            lo = self.expr(m.group(1), arrays) if m.group(1).strip() else "None"
-            hi = self.expr(m.group(2), arrays) if m.group(2).strip() else "None"
+            lo = self.expr(m.group(1), arrays, intctx) if m.group(1).strip() else "None"
+            hi = self.expr(m.group(2), arrays, intctx) if m.group(2).strip() else "None"
             return f"slice({lo}, {hi})"
         a = re.sub(r"^kind\s*=\s*mytype$", "None", a)
         if a in ("mytype",):
             return "None"
-        return self.expr(a, arrays)
+        return self.expr(a, arrays, intctx)
 
     # -- a subroutine -----------------------------------------------------
     def subroutine(self, text, vector_vars=(), extra_arrays=()):
@@ -237,7 +241,7 @@ class Transpiler:
                 if dim:
                     k0 = decl.index("(", dim.start())
                     dimspec = decl[k0 + 1:_match_paren(decl, k0)]
-                is_cplx = decl.strip().startswith("complex")
+                is_cplx = "int" if decl.strip().startswith("integer") else decl.strip().startswith("complex")
                 for item in _split_args(names):
                     nm = re.match(r"(\w+)", item).group(1)
                     spec = dimspec
@@ -283,14 +287,22 @@ class Transpiler:
                 else:
                     emit(f"pass  # call {cname}")
                 return
-            if re.match(r"(write|print|flush|open|close|read)\b", ln):
+            if re.match(r"(write|print|flush|open|close|read|deallocate)\b", ln):
                 emit("pass")
+                return
+            m = re.match(r"allocate\s*\((.*)\)$", ln)
+            if m:
+                for item in _split_args(m.group(1)):
+                    k0 = item.index("(")
+                    nm = item[:k0].strip()
+                    dims = [self.expr(d, arrays, True) for d in _split_args(item[k0 + 1:_match_paren(item, k0)])]
+                    emit(f"{nm} = farr(({', '.join(dims)},))")
                 return
             m = re.match(r"do\s+(\w+)\s*=\s*(.*)$", ln)
             if m:
                 var = m.group(1)
                 parts = _split_args(m.group(2))
-                lo, hi = self.expr(parts[0], arrays), self.expr(parts[1], arrays)
+                lo, hi = self.expr(parts[0], arrays, True), self.expr(parts[1], arrays, True)
                 if var in vec:
                     emit(f"for {var} in (ALL,):")
                 elif len(parts) == 3:
@@ -346,7 +358,9 @@ class Transpiler:
                 raise ValueError("cannot parse: " + ln)
             lhs, rhs = ln[:pos].strip(), ln[pos + 1:].strip()
             r = self.expr(rhs, arrays)
-            if lhs in arrays:
+            if lhs in arrays and rhs in arrays:
+                emit(f"{lhs}.a[...] = {rhs}.a")
+            elif lhs in arrays:
                 emit(f"{lhs}[...] = {r}")
             else:
                 emit(f"{self.expr(lhs, arrays)} = {r}")
@@ -359,13 +373,13 @@ class Transpiler:
             for d in dims:
                 if ":" in d:
                     lo, hi = d.split(":", 1)
-                    lo, hi = self.expr(lo, arrays), self.expr(hi, arrays)
+                    lo, hi = self.expr(lo, arrays, True), self.expr(hi, arrays, True)
                     shp.append(f"({hi})-({lo})+1")
                     lbs.append(lo)
                 else:
-                    shp.append(self.expr(d, arrays))
+                    shp.append(self.expr(d, arrays, True))
                     lbs.append("1")
-            emit(f"{nm} = farr(({', '.join(shp)},), {'complex' if is_cplx else 'float'}, ({', '.join(lbs)},))")
+            emit(f"{nm} = farr(({', '.join(shp)},), {'int' if is_cplx == 'int' else ('complex' if is_cplx else 'float')}, ({', '.join(lbs)},))")
         for ln in body:
             stmt(ln)
         emit("return locals()")
@@ -391,6 +405,7 @@ def base_namespace():
           "max": lambda *a: np.maximum.reduce(a) if any(isinstance(x, np.ndarray) for x in a) else max(a),
           "min": lambda *a: np.minimum.reduce(a) if any(isinstance(x, np.ndarray) for x in a) else min(a),
           "mod": lambda a, b: a % b,
+          "present": lambda x: x is not None, "allocated": lambda x: True,
           "rl": lambda z: np.real(z), "iy": lambda z: np.imag(z), "aimag": lambda z: np.imag(z),
           "cx": lambda a, b: a + 1j * b if isinstance(a, np.ndarray) or isinstance(b, np.ndarray) else complex(a, b),
           "conjg": np.conj}
