@@ -43,6 +43,10 @@ struct PoissonImpl : PoissonState {
   // device table layout (doubles): ax,bx[nx] ay,by[ny] az,bz[nzh] | xk2[nx] yk2[ny] zk2[nzh][2] | tx[nx] ty[ny] tz[nzh][2]
   double *d_ax = nullptr, *d_bx = nullptr, *d_ay = nullptr, *d_by = nullptr, *d_az = nullptr, *d_bz = nullptr;
   double *d_xk2 = nullptr, *d_yk2 = nullptr, *d_zk2 = nullptr, *d_tx = nullptr, *d_ty = nullptr, *d_tz = nullptr;
+  // stretched y mesh (matrice_refinement + inversion5_v1/v2): pre-eliminated pentadiagonal systems
+  int istret = 0;
+  int pen_nsys = 0, pen_rows = 0;     // istret 1,2: two systems (odd / even modes) of ny/2 rows; istret 3: one of nym rows
+  DevBuf pen;                         // [nsys][7][rows][nzh][nx] double2: L1 L2 INV A1 B1, and the last-block terms
   ~PoissonImpl() override {
     if (plans) { cufftDestroy(plan_r2c); cufftDestroy(plan_c2r); cufftDestroy(plan_xy); }
   }
@@ -191,6 +195,8 @@ struct AxisTables {
   std::vector<double> a, b;    // sin/cos twiddles
   std::vector<double> k2;      // squared modified wavenumber (re[,im])
   std::vector<double> tf;      // interpolator transfer function (re[,im])
+  std::vector<double> es;      // exs / eys / ezs of waves() (re[,im])
+  std::vector<double> kraw;    // n k'(w), the modified wavenumber before the division by the length (yky when istret /= 0)
 };
 
 // one direction; n = pressure-mesh points (nm), nv = velocity nodes, per = periodic,
@@ -218,20 +224,24 @@ AxisTables axis_tables(int nm, int nv, bool per, double len, const x3d_deriv_coe
   const int w2 = half ? 2 : 1;
   T.k2.assign(static_cast<size_t>(na) * w2, 0.0);
   T.tf.assign(static_cast<size_t>(na) * w2, 0.0);
-  std::vector<double> es(static_cast<size_t>(na) * w2, 0.0);
+  std::vector<double> &es = T.es;
+  es.assign(static_cast<size_t>(na) * w2, 0.0);
+  T.kraw.assign(static_cast<size_t>(na) * w2, 0.0);
   if (!half) {
     if (per) {
       for (int i = 0; i <= nm / 2; ++i) {
         const double w = twopi * i / nv;
         const double v = nv * kmod(w) / len;
         T.k2[i] = v * v; es[i] = nv * w / len;
+        T.kraw[i] = nv * kmod(w);
       }
-      for (int i = nm / 2 + 1; i < nm; ++i) { T.k2[i] = T.k2[nm - i]; es[i] = es[nm - i]; }
+      for (int i = nm / 2 + 1; i < nm; ++i) { T.k2[i] = T.k2[nm - i]; es[i] = es[nm - i]; T.kraw[i] = T.kraw[nm - i]; }
     } else {
       for (int i = 1; i < nm; ++i) {
         const double w = twopi * 0.5 * i / nm;
         const double v = nm * kmod(w) / len;
         T.k2[i] = v * v; es[i] = nm * w / len;
+        T.kraw[i] = nm * kmod(w);
       }
     }
     for (int i = 0; i < nm; ++i) T.tf[i] = transfer(es[i] * d);
@@ -275,13 +285,266 @@ int grid_for(long long n, int sm) {
 
 }  // namespace
 
+// ---- stretched y mesh ---------------------------------------------------------------------------------
+// matrice_refinement (src/poisson.f90:1814-2249) builds, for every (kx,kz), a pentadiagonal matrix in y whose
+// real and imaginary parts are two independent real systems; inversion5_v1/v2 (src/tools.f90:1225-1498)
+// eliminate it without pivoting on EVERY solve.  The matrix depends on the mesh only, so here the elimination is
+// done once on the host, in the reference's loop order (including its carried-over multipliers when a pivot is
+// exactly zero), and the solve becomes a banded forward/backward substitution on the device.
+namespace {
+
+constexpr int PEN_PLANES = 7;  // L1 L2 INV A1 B1 | (T, b1) | (PI, A1l)
+constexpr double PEN_EPS = 1.e-16;  // src/tools.f90:1240
+
+struct PentaHost {
+  int nx, rows, nk;
+  std::vector<double> band[5];  // [row][k][i][2]
+  size_t idx(int i, int row, int k) const { return ((static_cast<size_t>(row) * nk + k) * nx + i) * 2; }
+};
+
+// in-place elimination of one set of systems; fills the device table planes
+void penta_eliminate(PentaHost &H, std::vector<double> &planes) {
+  const int nx = H.nx, n = H.rows, nk = H.nk;
+  const size_t PS = static_cast<size_t>(n) * nk * nx * 2;
+  planes.assign(PS * PEN_PLANES, 0.0);
+  auto P = [&](int pl, int i, int row, int k, int c) -> double & { return planes[pl * PS + H.idx(i, row, k) + c]; };
+  auto A = [&](int b, int i, int row, int k, int c) -> double & { return H.band[b - 1][H.idx(i, row, k) + c]; };  // b = 1..5
+  double tmp[2] = {0.0, 0.0};
+  for (int m = 0; m < n - 2; ++m)            // tools.f90:1263-1287
+    for (int ii = 1; ii <= 2; ++ii) {
+      const int mi = m + ii;
+      for (int k = 0; k < nk; ++k)
+        for (int i = 0; i < nx; ++i)
+          for (int c = 0; c < 2; ++c) {
+            if (A(3, i, m, k, c) != 0.0) tmp[c] = A(3 - ii, i, mi, k, c) / A(3, i, m, k, c);
+            P(ii - 1, i, m, k, c) = tmp[c];
+            for (int jc = 4 - ii; jc <= 5 - ii; ++jc) A(jc, i, mi, k, c) -= tmp[c] * A(jc + ii, i, m, k, c);
+          }
+    }
+  for (int k = 0; k < nk; ++k)                // tools.f90:1289-1333
+    for (int i = 0; i < nx; ++i)
+      for (int c = 0; c < 2; ++c) {
+        const double piv = A(3, i, n - 2, k, c);
+        const double s = std::fabs(piv) > PEN_EPS ? A(2, i, n - 1, k, c) / piv : 0.0;
+        const double b1 = A(3, i, n - 1, k, c) - s * A(4, i, n - 2, k, c);
+        P(5, i, 0, k, c) = std::fabs(b1) > PEN_EPS ? s / b1 : 0.0;
+        P(5, i, 1, k, c) = b1;
+        const double pinv = std::fabs(piv) > PEN_EPS ? 1.0 / piv : 0.0;
+        P(6, i, 0, k, c) = pinv;
+        P(6, i, 1, k, c) = A(4, i, n - 2, k, c) * pinv;
+      }
+  for (int row = n - 3; row >= 0; --row)      // tools.f90:1335-1357
+    for (int k = 0; k < nk; ++k)
+      for (int i = 0; i < nx; ++i)
+        for (int c = 0; c < 2; ++c) {
+          const double piv = A(3, i, row, k, c);
+          const double inv = std::fabs(piv) > PEN_EPS ? 1.0 / piv : 0.0;
+          P(2, i, row, k, c) = inv;
+          P(3, i, row, k, c) = A(4, i, row, k, c) * inv;
+          P(4, i, row, k, c) = A(5, i, row, k, c) * inv;
+        }
+}
+
+__global__ void k_penta(double2 *__restrict__ e, long long off0, long long srow, long long sk, int rows, int nx, int nk,
+                        const double2 *__restrict__ C, int zero_i, int zero_k) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(nx) * nk) return;
+  const int i = static_cast<int>(idx % nx), k = static_cast<int>(idx / nx);
+  const long long PS = static_cast<long long>(rows) * nk * nx;
+  const double2 *c0 = C + static_cast<long long>(k) * nx + i;
+  const long long cs = static_cast<long long>(nk) * nx;  // coefficient row stride
+  double2 *e0p = e + off0 + i + sk * k;
+  auto mul = [](double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); };
+  double2 x0 = e0p[0], x1 = e0p[srow];
+  for (int m = 0; m < rows - 2; ++m) {
+    double2 x2 = e0p[srow * (m + 2)];
+    const double2 l1 = c0[0 * PS + cs * m], l2 = c0[1 * PS + cs * m];
+    x1.x -= l1.x * x0.x; x1.y -= l1.y * x0.y;
+    x2.x -= l2.x * x0.x; x2.y -= l2.y * x0.y;
+    e0p[srow * m] = x0;
+    x0 = x1; x1 = x2;
+  }
+  const double2 T = c0[5 * PS], b1 = c0[5 * PS + cs], PI = c0[6 * PS], A1l = c0[6 * PS + cs];
+  double2 en, em;
+  en.x = fabs(b1.x) > PEN_EPS ? x1.x / b1.x - T.x * x0.x : 0.0;
+  en.y = fabs(b1.y) > PEN_EPS ? x1.y / b1.y - T.y * x0.y : 0.0;
+  em.x = x0.x * PI.x - A1l.x * en.x;
+  em.y = x0.y * PI.y - A1l.y * en.y;
+  const bool zero = (i == zero_i && k == zero_k);  // src/poisson.f90:901-908
+  const double2 z = make_double2(0.0, 0.0);
+  e0p[srow * (rows - 1)] = zero ? z : en;
+  e0p[srow * (rows - 2)] = zero ? z : em;
+  double2 y2 = en, y1 = em;
+  for (int row = rows - 3; row >= 0; --row) {
+    const double2 inv = c0[2 * PS + cs * row], a1 = c0[3 * PS + cs * row], bb = c0[4 * PS + cs * row];
+    const double2 ev = e0p[srow * row];
+    double2 r;
+    r.x = ev.x * inv.x - a1.x * y1.x - bb.x * y2.x;
+    r.y = ev.y * inv.y - a1.y * y1.y - bb.y * y2.y;
+    e0p[srow * row] = zero ? z : r;
+    y2 = y1; y1 = r;
+  }
+  (void)mul;
+}
+
+}  // namespace
+
+// builds and pre-eliminates the systems for the local spectral planes [k0, k0+nk)
+static void penta_init(Ctx &ctx, PoissonImpl &P, const AxisTables &TX, const AxisTables &TY, const AxisTables &TZ, double dz,
+                       const x3d_deriv_coeffs &cz) {
+  const int nx = P.nx, ny = P.ny, nk = P.nzhl, k0 = P.k0;
+  const int istret = P.istret;
+  const double pi = std::acos(-1.0);
+  const double alpha = P.p.alpha, beta = P.p.beta;
+  if (!(beta > 0.0)) throw Error("x3d_poisson_init: istret != 0 needs beta > 0 and the alpha computed by stretching()");
+  // transfer functions and wavenumbers per direction (matrice_refinement :1860-1926)
+  std::vector<double> tzr(nk), tzi(nk);
+  for (int kl = 0; kl < nk; ++kl) {
+    const int k = kl + k0;
+    if (P.bcz == 0) { tzr[kl] = TZ.tf[2 * k]; tzi[kl] = TZ.tf[2 * k]; }
+    else {  // the bcz=1 branch of matrice_refinement has no dici6 term (:1910-1915)
+      auto tr = [&](double e) {
+        const double tt = 2.0 * (cz.bici6 * std::cos(e * 1.5) + cz.cici6 * std::cos(e * 2.5));
+        const double tt1 = 2.0 * cz.aici6 * std::cos(e * 0.5);
+        return (tt1 + tt) / (1.0 + 2.0 * cz.ailcai6 * std::cos(e));
+      };
+      tzr[kl] = tr(TZ.es[2 * k] * dz);
+      tzi[kl] = tr(TZ.es[2 * k + 1] * dz);
+    }
+  }
+  // cw(i,jy,k) = transx(i) * (yky(jy) * transz(k)) per component; yky has equal parts (jy 0-based pressure-mesh mode)
+  auto cw = [&](int i, int jy, int kl, int c) { return TX.tf[i] * (TY.kraw[jy] * (c == 0 ? tzr[kl] : tzi[kl])); };
+  auto xk2 = [&](int i) { return TX.k2[i]; };
+  auto zk2 = [&](int kl, int c) { return TZ.k2[2 * (kl + k0) + c]; };
+  auto base = [&](int i, int jy, int kl, int c) {
+    const double tz2 = (c == 0 ? tzr[kl] * tzr[kl] : tzi[kl] * tzi[kl]);
+    const double ty2 = TY.tf[jy] * TY.tf[jy], tx2 = TX.tf[i] * TX.tf[i];
+    return xk2(i) * ty2 * tz2 + zk2(kl, c) * ty2 * tx2;
+  };
+  const double xa0 = alpha / pi + 0.5 / beta / pi;
+  std::vector<double> planes;
+  if (istret == 1 || istret == 2) {
+    const double xa1 = (istret == 1) ? +1.0 / 4.0 / beta / pi : -1.0 / 4.0 / beta / pi;
+    const double xa0_2 = xa0 * xa0, xa1_2 = xa1 * xa1, xa01 = xa0 * xa1, xa0p1_2 = (xa0 + xa1) * (xa0 + xa1);
+    const int n = ny / 2;  // ny is even (checked by poisson_init)
+    if (n < 4) throw Error("x3d_poisson_init: stretched mesh needs ny/2 >= 4");
+    P.pen_nsys = 2; P.pen_rows = n;
+    const size_t PS = static_cast<size_t>(n) * nk * nx * 2 * PEN_PLANES;
+    P.pen.reserve(2 * PS * sizeof(double));
+    for (int sys = 0; sys < 2; ++sys) {  // sys 0: a (modes 2j-1), sys 1: a2 (modes 2j)
+      PentaHost H{nx, n, nk, {}};
+      for (auto &b : H.band) b.assign(static_cast<size_t>(n) * nk * nx * 2, 0.0);
+      auto W = [&](int i, int j, int kl, int c) { return cw(i, 2 * j + sys, kl, c); };  // j 0-based row
+      for (int kl = 0; kl < nk; ++kl)
+        for (int i = 0; i < nx; ++i)
+          for (int c = 0; c < 2; ++c) {
+            auto A = [&](int b, int row) -> double & { return H.band[b - 1][H.idx(i, row, kl) + c]; };
+            for (int j = 0; j < n; ++j) {
+              const double w = W(i, j, kl, c);
+              // modes: row j of a is pressure mode 2j (0-based), of a2 mode 2j+1; the last row of a uses
+              // transy(ny-2) (1-based, velocity ny), i.e. the same mode 2(n-1) (:1993), of a2 transy(ny-1)
+              const int jy = 2 * j + sys;
+              double d = base(i, jy, kl, c);
+              if (j > 0 && j < n - 1) d += xa0_2 * w * w + xa1_2 * w * (W(i, j - 1, kl, c) + W(i, j + 1, kl, c));   // :1957-1975
+              else if (j == 0) d += (sys == 0 ? xa0_2 : xa0_2 - xa1_2) * w * w + xa1_2 * w * W(i, 1, kl, c);         // :1980-1987,2002-2009
+              else d += (sys == 0 ? xa0_2 : xa0p1_2) * w * w + xa1_2 * w * W(i, n - 2, kl, c);                       // :1991-1998,2013-2020
+              A(3, j) = -d;
+            }
+            for (int j = 1; j < n - 1; ++j) A(4, j) = xa01 * (W(i, j + 1, kl, c) * (W(i, j, kl, c) + W(i, j + 1, kl, c)));  // :2027-2036
+            if (sys == 0) {
+              A(4, 0) = 2.0 * xa01 * (W(i, 0, kl, c) * W(i, 1, kl, c) + W(i, 1, kl, c) * W(i, 1, kl, c));  // :2040
+            } else {
+              A(4, 0) = (xa0 - xa1) * xa1 * (W(i, 0, kl, c) * W(i, 1, kl, c)) + xa0 * xa1 * (W(i, 1, kl, c) * W(i, 1, kl, c));        // :2043
+              A(4, n - 2) = xa0 * xa1 * W(i, n - 2, kl, c) * W(i, n - 1, kl, c) + (xa0 + xa1) * xa1 * (W(i, n - 1, kl, c) * W(i, n - 1, kl, c));  // :2046
+              A(4, n - 1) = 0.0;
+            }
+            for (int j = 0; j < n - 2; ++j) A(5, j) = xa1_2 * (-W(i, j + 1, kl, c) * W(i, j + 2, kl, c));  // :2058-2063
+            if (sys == 0) A(5, 0) = 2.0 * A(5, 0);                                                          // :2067
+            A(5, n - 2) = 0.0; A(5, n - 1) = 0.0;
+            for (int j = 1; j < n; ++j) A(2, j) = xa01 * (W(i, j - 1, kl, c) * (W(i, j, kl, c) + W(i, j - 1, kl, c)));  // :2078-2085
+            A(2, 0) = 0.0;
+            if (sys == 1) {
+              A(2, 1) = xa0 * xa1 * (W(i, 1, kl, c) * W(i, 0, kl, c)) + (xa0 + xa1) * xa1 * (W(i, 0, kl, c) * W(i, 0, kl, c));          // :2090
+              A(2, n - 1) = (xa0 + xa1) * xa1 * (W(i, n - 1, kl, c) * W(i, n - 2, kl, c)) + xa0 * xa1 * (W(i, n - 2, kl, c) * W(i, n - 2, kl, c));  // :2096
+            }
+            for (int j = 2; j < n; ++j) A(1, j) = xa1_2 * (-W(i, j - 1, kl, c) * W(i, j - 2, kl, c));  // :2108-2113
+            A(1, 0) = 0.0; A(1, 1) = 0.0;
+          }
+      if (sys == 0)  // not to have a singular matrix, :2120-2129
+        for (int kl = 0; kl < nk; ++kl)
+          for (int i = 0; i < nx; ++i)
+            if (TX.k2[i] == 0.0 && TZ.k2[2 * (kl + k0)] == 0.0)
+              for (int c = 0; c < 2; ++c) {
+                H.band[2][H.idx(i, 0, kl) + c] = 1.0; H.band[3][H.idx(i, 0, kl) + c] = 0.0; H.band[4][H.idx(i, 0, kl) + c] = 0.0;
+              }
+      penta_eliminate(H, planes);
+      X3D_CUDA(cudaMemcpyAsync(static_cast<double *>(P.pen.p) + sys * PS, planes.data(), PS * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+      X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+  } else {  // istret = 3, :2131-2246
+    const double xa1 = -1.0 / 4.0 / beta / pi;
+    const double xa0_2 = xa0 * xa0, xa1_2 = xa1 * xa1, xa01 = xa0 * xa1;
+    const int n = ny;
+    if (n < 4) throw Error("x3d_poisson_init: stretched mesh needs nym >= 4");
+    P.pen_nsys = 1; P.pen_rows = n;
+    const size_t PS = static_cast<size_t>(n) * nk * nx * 2 * PEN_PLANES;
+    P.pen.reserve(PS * sizeof(double));
+    PentaHost H{nx, n, nk, {}};
+    for (auto &b : H.band) b.assign(static_cast<size_t>(n) * nk * nx * 2, 0.0);
+    for (int kl = 0; kl < nk; ++kl)
+      for (int i = 0; i < nx; ++i)
+        for (int c = 0; c < 2; ++c) {
+          auto A = [&](int b, int row) -> double & { return H.band[b - 1][H.idx(i, row, kl) + c]; };
+          auto W = [&](int j) { return cw(i, j, kl, c); };
+          for (int j = 0; j < n; ++j) {
+            const double w = W(j);
+            double d = base(i, j, kl, c) + xa0_2 * w * w;
+            if (j == 0) d += xa1_2 * w * W(1);
+            else if (j == n - 1) d += xa1_2 * w * W(n - 2);
+            else d += xa1_2 * w * (W(j - 1) + W(j + 1));
+            A(3, j) = -d;
+          }
+          for (int j = 0; j < n - 1; ++j) A(4, j) = xa01 * (W(j + 1) * (W(j) + W(j + 1)));
+          for (int j = 0; j < n - 2; ++j) A(5, j) = -xa1_2 * (W(j + 1) * W(j + 2));
+          for (int j = 1; j < n; ++j) A(2, j) = xa01 * (W(j - 1) * (W(j) + W(j - 1)));
+          for (int j = 2; j < n; ++j) A(1, j) = -xa1_2 * (W(j - 1) * W(j - 2));
+        }
+    if (k0 == 0)  // :2240-2245: element (1,1,1) of the rank that owns it
+      for (int c = 0; c < 2; ++c) { H.band[2][H.idx(0, 0, 0) + c] = 1.0; H.band[3][H.idx(0, 0, 0) + c] = 0.0; H.band[4][H.idx(0, 0, 0) + c] = 0.0; }
+    penta_eliminate(H, planes);
+    X3D_CUDA(cudaMemcpyAsync(P.pen.p, planes.data(), PS * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+}
+
+// in-place solve of the spectral y-pencil cw (nx, ny, nk)
+static void penta_solve(Ctx &ctx, PoissonImpl &P, double2 *cw, bool zero010) {
+  const int nx = P.nx, ny = P.ny, nk = P.nzhl, rows = P.pen_rows;
+  const long long tot = static_cast<long long>(nx) * nk;
+  if (tot == 0) return;
+  const size_t PS = static_cast<size_t>(rows) * nk * nx * PEN_PLANES;  // double2 per system
+  int zi = -1, zk = -1;
+  if (zero010) { zi = nx / 2; zk = P.nz / 2 - P.k0; }
+  ProfScope ps(ctx, "poisson_penta(k_penta)");
+  for (int sys = 0; sys < P.pen_nsys; ++sys) {
+    const long long off0 = (P.pen_nsys == 2) ? static_cast<long long>(sys) * nx : 0;
+    const long long srow = (P.pen_nsys == 2) ? 2LL * nx : nx;
+    k_penta<<<static_cast<unsigned>((tot + 127) / 128), 128, 0, ctx.stream>>>(cw, off0, srow, static_cast<long long>(nx) * ny, rows, nx, nk,
+                                                                              static_cast<const double2 *>(P.pen.p) + sys * PS, zi, zk);
+    X3D_CUDA(cudaGetLastError());
+    ctx.launches++;
+  }
+}
+
 void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   X3D_CUDA(cudaSetDevice(ctx.device));
-  if (p.istret != 0) throw Error("x3d_poisson_init: stretched-mesh Poisson (matrice_refinement/inversion5) not implemented yet");
+  if (p.istret != 0 && p.bcy == 0) throw Error("x3d_poisson_init: a stretched y mesh needs non-periodic y (src/poisson.f90:225)");
+  if (p.istret < 0 || p.istret > 3) throw Error("x3d_poisson_init: istret must be 0..3");
   for (int a = 0; a < 3; ++a)
     if (!ctx.have_dc[a]) throw Error("x3d_poisson_init: call x3d_set_deriv_coeffs for the three axes first (waves() reads derivX/Y/Z)");
   auto P = std::make_unique<PoissonImpl>();
   P->p = p;
+  P->istret = p.istret;
   P->bcx = p.bcx; P->bcy = p.bcy; P->bcz = p.bcz;
   const bool ok = (p.bcx == 0 && p.bcy == 0 && p.bcz == 0) || (p.bcx == 1 && p.bcy == 0 && p.bcz == 0) ||
                   (p.bcx == 0 && p.bcy == 1 && p.bcz == 0) || (p.bcx == 1 && p.bcy == 1);
@@ -368,6 +631,7 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   if (p.bcx || p.bcy) P->cwb.reserve(nsp_y * 16);
   if (p.bcx || p.bcy || p.bcz) P->rwork.reserve(std::max(nr_z, nr_y) * 8);
   if (P->nranks > 1 && (p.bcx || p.bcy)) P->rwork2.reserve(std::max(nr_z, nr_y) * 8);
+  if (P->istret != 0) penta_init(ctx, *P, TX, TY, TZ, p.zlz / static_cast<double>(nz), ctx.dc[2]);
   ctx.poisson = std::move(P);
 }
 
@@ -437,11 +701,21 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     stage(S_NORM | S_ROTZ_F | S_ROTY_F | S_POSTX | S_DIVIDE, cw, cwb);
     stage(S_PREX | S_ROTY_B | S_ROTZ_B, cwb, cw);
   } else if (P->bcx == 0 && P->bcy == 1) {  // poisson_010, :724-991
-    stage(S_NORM | S_ROTZ_F | S_ROTX_F | S_POSTY | S_DIVIDE | S_ZERO010, cw, cwb);
+    if (P->istret == 0) {
+      stage(S_NORM | S_ROTZ_F | S_ROTX_F | S_POSTY | S_DIVIDE | S_ZERO010, cw, cwb);
+    } else {  // :822-893: pentadiagonal systems in y instead of the division
+      stage(S_NORM | S_ROTZ_F | S_ROTX_F | S_POSTY, cw, cwb);
+      penta_solve(ctx, *P, cwb, true);
+    }
     stage(S_PREY | S_ROTX_B | S_ROTZ_B, cwb, cw);
   } else {  // poisson_11x, :1118-1407
     stage(S_NORM | S_ROTZ_F | S_POSTY, cw, cwb);
-    stage(S_POSTX | S_DIVIDE, cwb, cw);
+    if (P->istret == 0) {
+      stage(S_POSTX | S_DIVIDE, cwb, cw);
+    } else {  // :1232-1330
+      stage(S_POSTX, cwb, cw);
+      penta_solve(ctx, *P, cw, false);
+    }
     stage(S_PREX, cw, cwb);
     stage(S_PREY | S_ROTZ_B, cwb, cw);
   }
