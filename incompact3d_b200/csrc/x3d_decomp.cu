@@ -505,7 +505,15 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
       group_barrier(ctx, G);  // every member has finished with its destination pencil
       if (ns > 0) {
         ProfScope ps(ctx, "transpose_p2p(k_p2p_transpose)");
-        if (elem == 1)
+        // rows stay whole when neither the cut axis nor the gathered axis is x: move them as 16-byte pairs
+        const bool pairs = elem == 1 && S.axis != 0 && T.recv.axis != 0 && (S.dims[0] % 2 == 0) &&
+                           (reinterpret_cast<uintptr_t>(d_src) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_dst) % 16 == 0);
+        if (pairs)
+          k_p2p_transpose<double2><<<grid_for(ctx, ns / 2), 256, 0, ctx.stream>>>(reinterpret_cast<const double2 *>(d_src),
+                                                                               reinterpret_cast<double2 *const *>(peers), S.dims[0] / 2, S.dims[1],
+                                                                               S.dims[2], S.axis, T.recv.axis, blk_of, bst, bsz, my_off,
+                                                                               T.recv.dims[0] / 2, T.recv.dims[1], T.recv.dims[2]);
+        else if (elem == 1)
           k_p2p_transpose<double><<<grid_for(ctx, ns), 256, 0, ctx.stream>>>(d_src, reinterpret_cast<double *const *>(peers), S.dims[0], S.dims[1],
                                                                           S.dims[2], S.axis, T.recv.axis, blk_of, bst, bsz, my_off,
                                                                           T.recv.dims[0], T.recv.dims[1], T.recv.dims[2]);

@@ -53,6 +53,7 @@ bool is_device_ptr(const void *p) {
 }
 
 int pick_L_strided(int n, int variant) {
+  if (n > 1024) return n <= 1536 ? 48 : 64;                      // long lines (e.g. 1536^3 on 8 GPUs): 32 chunks of 48 / 64 rows
   if (variant >= 4) return n <= 256 ? 8 : (n <= 512 ? 16 : 32);  // TMA tile kernels: up to 32 chunks per line
   if (n <= 128) return 8;
   if (n <= 256) return 16;
@@ -60,7 +61,7 @@ int pick_L_strided(int n, int variant) {
   return 32;
 }
 int pick_L_contig(int n) {
-  const int cand[5] = {5, 9, 17, 25, 33};
+  const int cand[7] = {5, 9, 17, 25, 33, 49, 65};
   for (int L : cand)
     if (32 * L >= n) return L;
   return -1;
@@ -109,7 +110,7 @@ void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double 
     if (Lp > 0 && Lp <= 17 && pair_plan(op, g, Lp, d_u, d_t, pg, smem)) { L = Lp; g.pair = true; }
   }
   if (L < 0) L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out, ctx.strided_variant);
-  if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 1056)");
+  if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 2080)");
   const TriTable &T = get_tri(ctx, call.f, call.s, call.w, n_out, L, op.periodic != 0, op.alpha, call.post);
   ProfScope ps(ctx, call.axis == 0 ? "compact_x(k_contig)" : (call.axis == 1 ? "compact_y(k_strided)" : "compact_z(k_strided)"));
   switch (op.kind) {

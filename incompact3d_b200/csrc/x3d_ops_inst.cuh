@@ -185,6 +185,7 @@ static void launch_strided(Ctx &ctx, const DevOp &op, const LineGeom &g, const T
     if (T.L == 16 && v == 5) return launch_tile_one<KIND, NT, 16, 16, 3, 1>(ctx, op, g, T, u, t);
     if (T.L == 16) return launch_tile_one<KIND, NT, 16, 8, 3, 2>(ctx, op, g, T, u, t);
     if (T.L == 32) return launch_tile_one<KIND, NT, 32, 8, 3, 1>(ctx, op, g, T, u, t);
+    if (T.L == 48) return launch_tile_one<KIND, NT, 48, 8, 2, 1>(ctx, op, g, T, u, t);
   }
   if (T.L == 8 && T.nc <= 16) launch_strided_one<KIND, NT, 8, 32, 16, 2>(ctx, op, g, T, u, t);
   else if (T.L == 8 && T.nc <= 32) launch_strided_one<KIND, NT, 8, 32, 32, 1>(ctx, op, g, T, u, t);
@@ -192,7 +193,9 @@ static void launch_strided(Ctx &ctx, const DevOp &op, const LineGeom &g, const T
   else if (T.L == 16 && T.nc <= 32) launch_strided_one<KIND, NT, 16, 16, 32, 2>(ctx, op, g, T, u, t);
   else if (T.L == 32 && T.nc <= 16) launch_strided_one<KIND, NT, 32, 16, 16, 2>(ctx, op, g, T, u, t);
   else if (T.L == 32 && T.nc <= 32) launch_strided_one<KIND, NT, 32, 16, 32, 1>(ctx, op, g, T, u, t);
-  else throw Error("no strided kernel for this line length (n <= 1024 supported)");
+  else if (T.L == 48 && T.nc <= 32) launch_strided_one<KIND, NT, 48, 8, 32, 1>(ctx, op, g, T, u, t);
+  else if (T.L == 64 && T.nc <= 32) launch_strided_one<KIND, NT, 64, 8, 32, 1>(ctx, op, g, T, u, t);
+  else throw Error("no strided kernel for this line length (n <= 2048 supported)");
 }
 
 template <int KIND, int NT, int L, int WPB, int NB, int MINB, bool TMA>
@@ -227,7 +230,8 @@ static void launch_contig_L(Ctx &ctx, const DevOp &op, const LineGeom &g, const 
     if (v == 3) return launch_contig_one<KIND, NT, L, 4, 3, 3, true>(ctx, op, g, T, u, t);
   }
   if constexpr (L <= 17) launch_contig_one<KIND, NT, L, 8, 1, 2, false>(ctx, op, g, T, u, t);
-  else launch_contig_one<KIND, NT, L, 8, 1, 1, false>(ctx, op, g, T, u, t);
+  else if constexpr (L <= 33) launch_contig_one<KIND, NT, L, 8, 1, 1, false>(ctx, op, g, T, u, t);
+  else launch_contig_one<KIND, NT, L, 4, 1, 1, false>(ctx, op, g, T, u, t);  // long lines: 4 warps, up to 255 registers
 }
 
 template <int KIND, int NT>
@@ -238,7 +242,9 @@ static void launch_contig(Ctx &ctx, const DevOp &op, const LineGeom &g, const Tr
     case 17: launch_contig_L<KIND, NT, 17>(ctx, op, g, T, u, t); break;
     case 25: launch_contig_L<KIND, NT, 25>(ctx, op, g, T, u, t); break;
     case 33: launch_contig_L<KIND, NT, 33>(ctx, op, g, T, u, t); break;
-    default: throw Error("no contiguous kernel for this line length (n <= 1056 supported)");
+    case 49: launch_contig_L<KIND, NT, 49>(ctx, op, g, T, u, t); break;
+    case 65: launch_contig_L<KIND, NT, 65>(ctx, op, g, T, u, t); break;
+    default: throw Error("no contiguous kernel for this line length (n <= 2080 supported)");
   }
 }
 

@@ -97,6 +97,8 @@ CASES = [  # (dims, axis letter) -- line lengths of the BASELINE configs, ragged
     # even lane extents: the TMA-tiled kernels (16-byte strides), full and ragged lane blocks
     ((64, 64, 4), "y"), ((32, 16, 64), "z"), ((16, 128, 4), "y"), ((24, 300, 3), "y"), ((6, 5, 130), "z"),
     ((34, 16, 3), "y"), ((8, 2, 10), "z"),
+    # long lines (BASELINE config #5: 1536^3 over 8 GPUs) and beyond
+    ((1536, 3, 2), "x"), ((8, 1536, 2), "y"), ((6, 2, 1537), "z"), ((1100, 2, 2), "x"), ((5, 2, 2048), "z"), ((2050, 2, 1), "x"),
 ]
 
 
