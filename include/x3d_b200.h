@@ -263,9 +263,13 @@ typedef struct x3d_solver_params {
   int istret; double beta;
   double nu0nu, cnu;
   int p_row, p_col;
+  int itype;                      /* 0: box without forcing (TGV); 3: channel (itype_channel, src/module_param.f90):
+                                     constant flow rate channel_cfr, src/Case-Channel.f90:150-170,220-261 */
 } x3d_solver_params;
 int x3d_solver_init(x3d_ctx *ctx, const x3d_solver_params *p);
 int x3d_solver_init_tgv(x3d_ctx *ctx);
+/* init_channel with iin = 0 (src/Case-Channel.f90:71-94): ux = 1 - y^2, uz = sin(x) + cos(z) */
+int x3d_solver_init_channel(x3d_ctx *ctx);
 /* set / get the x-pencil velocity fields (host or device pointers) */
 int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, const double *uz);
 int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz);

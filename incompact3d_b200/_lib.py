@@ -50,7 +50,7 @@ class SolverParams(C.Structure):
                 ("re", C.c_double), ("dt", C.c_double),
                 ("ifirstder", C.c_int), ("isecondder", C.c_int), ("ipinter", C.c_int), ("itimescheme", C.c_int),
                 ("istret", C.c_int), ("beta", C.c_double), ("nu0nu", C.c_double), ("cnu", C.c_double),
-                ("p_row", C.c_int), ("p_col", C.c_int)]
+                ("p_row", C.c_int), ("p_col", C.c_int), ("itype", C.c_int)]
 
 
 _lib = None

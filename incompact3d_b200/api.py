@@ -254,10 +254,10 @@ def _make_transpose(name):
 
 def _solver_init(self, nx, ny, nz, ncl=(0, 0, 0, 0, 0, 0), xlx=2 * np.pi, yly=2 * np.pi, zlz=2 * np.pi, re=1600.0,
                  dt=0.005, ifirstder=4, isecondder=4, ipinter=3, itimescheme=5, istret=0, beta=0.0, nu0nu=4.0,
-                 cnu=0.44, p_row=1, p_col=1):
+                 cnu=0.44, p_row=1, p_col=1, itype=0):
     p = _lib.SolverParams(int(nx), int(ny), int(nz), *[int(v) for v in ncl], float(xlx), float(yly), float(zlz),
                           float(re), float(dt), int(ifirstder), int(isecondder), int(ipinter), int(itimescheme),
-                          int(istret), float(beta), float(nu0nu), float(cnu), int(p_row), int(p_col))
+                          int(istret), float(beta), float(nu0nu), float(cnu), int(p_row), int(p_col), int(itype))
     fn = self._L.x3d_solver_init
     fn.argtypes = [C.c_void_p, C.POINTER(_lib.SolverParams)]
     self._check(fn(self._h, C.byref(p)))
@@ -271,6 +271,12 @@ def _solver_init(self, nx, ny, nz, ncl=(0, 0, 0, 0, 0, 0), xlx=2 * np.pi, yly=2 
 
 def _solver_init_tgv(self):
     fn = self._L.x3d_solver_init_tgv
+    fn.argtypes = [C.c_void_p]
+    self._check(fn(self._h))
+
+
+def _solver_init_channel(self):
+    fn = self._L.x3d_solver_init_channel
     fn.argtypes = [C.c_void_p]
     self._check(fn(self._h))
 
@@ -341,6 +347,7 @@ for _n in ("transpose_x_to_y", "transpose_y_to_z", "transpose_z_to_y", "transpos
     setattr(X3D, _n, _make_transpose(_n))
 X3D.solver_init = _solver_init
 X3D.solver_init_tgv = _solver_init_tgv
+X3D.solver_init_channel = _solver_init_channel
 X3D.solver_step = _solver_step
 X3D.solver_diagnostics_tgv = _solver_diag
 X3D.solver_divergence = _solver_divergence

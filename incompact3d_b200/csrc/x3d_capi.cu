@@ -13,6 +13,7 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs);
 void poisson_dims(Ctx &ctx, int d[3]);
 void solver_init(Ctx &ctx, const x3d_solver_params &p);
 void solver_init_tgv(Ctx &ctx);
+void solver_init_channel(Ctx &ctx);
 void solver_step(Ctx &ctx, int nsteps);
 void solver_diagnostics_tgv(Ctx &ctx, double *out5);
 void solver_divergence(Ctx &ctx, double *divmax, double *divmean);
@@ -369,6 +370,9 @@ int x3d_poisson(x3d_ctx *ctx, double *rhs) {
 // ---- device-resident solver -----------------------------------------------------------------------
 int x3d_solver_init(x3d_ctx *ctx, const x3d_solver_params *p) {
   return guard([&] { if (!p) throw Error("null params"); solver_init(ctx->c, *p); });
+}
+int x3d_solver_init_channel(x3d_ctx *ctx) {
+  return guard([&] { solver_init_channel(ctx->c); });
 }
 int x3d_solver_init_tgv(x3d_ctx *ctx) { return guard([&] { solver_init_tgv(ctx->c); }); }
 int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, const double *uz) {

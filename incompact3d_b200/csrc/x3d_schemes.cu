@@ -163,4 +163,57 @@ AxisCoeffs make_axis_coeffs(int n, int ncl1, int ncln, double len, const SchemeO
   return A;
 }
 
+// src/stretching.f90:96-318: node (yp) and mid-point (ypi) coordinates of the mapped mesh and the metric
+// factors that multiply the y derivatives
+StretchY make_stretching(int istret, double beta, double yly, int ny, int nym) {
+  if (istret < 1 || istret > 3 || !(beta > 0.0)) throw Error("stretching: istret must be 1..3 and beta > 0");
+  StretchY S;
+  S.istret = istret; S.beta = beta;
+  const double pi = std::acos(-1.0);
+  for (auto *v : {&S.yp, &S.ypi, &S.ppy, &S.pp2y, &S.pp4y, &S.ppyi, &S.pp2yi, &S.pp4yi}) v->assign(ny, 0.0);
+  const double yinf = -yly / 2.0;
+  const double alpha = std::fabs((-yinf - std::sqrt(pi * pi * beta * beta + yinf * yinf)) / (2.0 * beta * yinf));
+  S.alpha = alpha;
+  if (alpha == 0.0) throw Error("stretching: alpha = 0 is not supported");
+  const double scale = (istret == 3) ? 0.5 / nym : 1.0 / nym;
+  const double shift = (istret == 1) ? 0.0 : -0.5;
+  // mapped coordinate of eta, :126-152 / :165-190
+  auto coord = [&](double eta) {
+    const double den1 = std::sqrt(alpha * beta + 1.0);
+    const double xnum = den1 / std::sqrt(alpha / pi) / std::sqrt(beta) / std::sqrt(pi);
+    const double den = 2.0 * std::sqrt(alpha / pi) * std::sqrt(beta) * pi * std::sqrt(pi);
+    const double den3 = ((std::sin(pi * eta)) * (std::sin(pi * eta)) / beta / pi) + alpha / pi;
+    const double den4 = 2.0 * alpha * beta - std::cos(2.0 * pi * eta) + 1.0;
+    const double xnum1 = (std::atan(xnum * std::tan(pi * eta))) * den4 / den1 / den3 / den;
+    const double cst = std::sqrt(beta) * pi / (2.0 * std::sqrt(alpha) * std::sqrt(alpha * beta + 1.0));
+    const double off = (istret == 1) ? -yinf : yly;
+    double y = 0.0;
+    if (eta < 0.5) y = xnum1 - cst + off;
+    if (eta == 0.5) y = 0.0 + off;
+    if (eta > 0.5) y = xnum1 + cst + off;
+    return (istret == 3) ? y * 2.0 : y;
+  };
+  std::vector<double> eta(ny), etai(ny);
+  eta[0] = (istret == 1) ? 0.0 : -0.5;
+  S.yp[0] = 0.0;
+  for (int j = 1; j < ny; ++j) {
+    eta[j] = static_cast<double>(j) * scale + shift;
+    S.yp[j] = coord(eta[j]);
+  }
+  for (int j = 0; j < ny; ++j) {
+    etai[j] = (static_cast<double>(j + 1) - 0.5) * scale + shift;
+    S.ypi[j] = coord(etai[j]);
+  }
+  for (int j = 0; j < ny; ++j) {  // :262-286
+    S.ppy[j] = yly * (alpha / pi + (1.0 / pi / beta) * std::sin(pi * eta[j]) * std::sin(pi * eta[j]));
+    S.pp2y[j] = S.ppy[j] * S.ppy[j];
+    S.pp4y[j] = (-2.0 / beta * std::cos(pi * eta[j]) * std::sin(pi * eta[j]));
+    S.ppyi[j] = yly * (alpha / pi + (1.0 / pi / beta) * std::sin(pi * etai[j]) * std::sin(pi * etai[j]));
+    S.pp2yi[j] = S.ppyi[j] * S.ppyi[j];
+    S.pp4yi[j] = (-2.0 / beta * std::cos(pi * etai[j]) * std::sin(pi * etai[j]));
+    if (istret == 3) { S.pp4y[j] /= 2.0; S.pp4yi[j] /= 2.0; }
+  }
+  return S;
+}
+
 }  // namespace x3d

@@ -30,4 +30,12 @@ struct SchemeOpts {
 
 AxisCoeffs make_axis_coeffs(int n, int ncl1, int ncln, double len, const SchemeOpts &o);
 
+// stretched y mesh of stretching() (src/stretching.f90:96-318) for hosts that do not bring their own
+struct StretchY {
+  int istret = 0;
+  double beta = 0.0, alpha = 0.0;
+  std::vector<double> yp, ypi, ppy, pp2y, pp4y, ppyi, pp2yi, pp4yi;
+};
+StretchY make_stretching(int istret, double beta, double yly, int ny, int nym);
+
 }  // namespace x3d

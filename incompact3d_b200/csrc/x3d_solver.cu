@@ -132,6 +132,12 @@ struct SolverImpl : SolverState {
   // prepared operators
   PreOp d1[3][2], d2[3][2];                 // [axis][npaire]
   PreOp dvp[3], ivp[3], dpv[3], ipv[3];
+  // stretched y mesh and wall (Dirichlet) data
+  StretchY st;
+  DevBuf d_pp;                // device: pp2y[ny] | pp4y[ny] | ppy[ny]
+  DevBuf dpd;                 // wall pressure gradients kept between gradp and pre_correc (navier.f90:439-496):
+                              // x faces 4 x (ny,nzl) | y faces 4 x (nx,nzl) | z faces 4 x (nx,ny)
+  PreOp d1s[2];               // dery with the ppy multiply (istret /= 0), npaire 0 / 1
   // fused momentum kernels (periodic directions): compressed tables of D1 / D2 per axis
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
@@ -142,14 +148,15 @@ namespace {
 
 double *B(DevBuf &b) { return static_cast<double *>(b.p); }
 
-void prep(Ctx &ctx, PreOp &P, Kind kind, int axis, const AxisCoeffs &A, int npaire, const LU3 &lu, const int dims_in[3]) {
+void prep(Ctx &ctx, PreOp &P, Kind kind, int axis, const AxisCoeffs &A, int npaire, const LU3 &lu, const int dims_in[3],
+          const double *post = nullptr) {
   OpCall &c = P.call;
   c = OpCall{};
   c.kind = kind; c.axis = axis; c.ncl1 = A.ncl1; c.ncln = A.ncln; c.periodic = A.periodic; c.npaire = npaire;
   c.n = A.n; c.nm = A.nm;
   for (int d = 0; d < 3; ++d) c.dims_in[d] = dims_in[d];
   c.f = lu.f.data(); c.s = lu.s.data(); c.w = lu.w.data();
-  c.post = nullptr; c.rhs_only = false;
+  c.post = post; c.rhs_only = false;
   build_devop(ctx, c, P.op);
   if (P.op.untouched) throw Error("solver: operator variant not implemented by the reference");
   P.ready = true;
@@ -173,7 +180,6 @@ void map(Ctx &ctx, long long n, F f) {
 
 void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   X3D_CUDA(cudaSetDevice(ctx.device));
-  if (p.istret != 0) throw Error("x3d_solver_init: stretched meshes not implemented in the device solver yet");
   auto S = std::make_unique<SolverImpl>();
   S->p = p;
   // decomposition: single rank unless x3d_decomp_init was called before with several ranks
@@ -191,10 +197,13 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
     ctx.dc[a] = S->A[a].c;
     ctx.have_dc[a] = true;
     ctx.ncl[a] = S->A[a].periodic;
-    for (int e = 0; e < 2; ++e)
-      if (ncl[a][e] == 2) throw Error("x3d_solver_init: Dirichlet faces need the case boundary data (Channel/Cylinder glue, SURVEY 8f-3)");
   }
-  ctx.iibm = 0; ctx.istret = 0; ctx.iimplicit = 0;
+  // Dirichlet faces (ncl = 2) are no-slip walls (zero wall velocity, Case-Channel.f90:67); inflow / outflow planes
+  // would need the case arrays b?? (cylinder glue)
+  if (p.istret != 0 && S->A[1].periodic) throw Error("x3d_solver_init: a stretched y mesh needs non-periodic y");
+  if (p.itype != 0 && p.itype != 3) throw Error("x3d_solver_init: itype 0 (box) and 3 (channel) are implemented");
+  ctx.iibm = 0; ctx.istret = p.istret; ctx.iimplicit = 0;
+  if (p.istret != 0) S->st = make_stretching(p.istret, p.beta, p.yly, p.ny, S->A[1].nm);
   S->nxm = S->A[0].nm; S->nym = S->A[1].nm; S->nzm = S->A[2].nm;
   S->xnu = 1.0 / p.re;  // parameters.f90:302
   const double dt = p.dt;
@@ -233,10 +242,13 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   X3D_CUDA(cudaMallocHost(&S->h_red, sizeof(double) * 16));
   // operators on the local pencils
   const int dxy[3] = {p.nx, p.ny, nzl}, dzp[3] = {p.nx, nyl, p.nz};
+  const bool stretched = p.istret != 0;
+  const double *ppy = stretched ? S->st.ppy.data() : nullptr, *ppyi = stretched ? S->st.ppyi.data() : nullptr;
   for (int a = 0; a < 3; ++a) {
     const int *dd = (a == 2) ? dzp : dxy;
-    prep(ctx, S->d1[a][0], D1, a, S->A[a], 0, S->A[a].d1, dd);
-    prep(ctx, S->d1[a][1], D1, a, S->A[a], 1, S->A[a].d1p, dd);
+    // dery multiplies by ppy when the mesh is stretched (derive.f90:409-417)
+    prep(ctx, S->d1[a][0], D1, a, S->A[a], 0, S->A[a].d1, dd, a == 1 ? ppy : nullptr);
+    prep(ctx, S->d1[a][1], D1, a, S->A[a], 1, S->A[a].d1p, dd, a == 1 ? ppy : nullptr);
     prep(ctx, S->d2[a][0], D2, a, S->A[a], 0, S->A[a].d2, dd);
     prep(ctx, S->d2[a][1], D2, a, S->A[a], 1, S->A[a].d2p, dd);
   }
@@ -244,7 +256,7 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   const int dy[3] = {S->nxm, p.ny, nzl}, dz[3] = {S->nxm, nyml, p.nz};
   const int *dsv[3] = {dxy, dy, dz};
   for (int a = 0; a < 3; ++a) {
-    prep(ctx, S->dvp[a], DVP, a, S->A[a], 0, S->A[a].vp, dsv[a]);
+    prep(ctx, S->dvp[a], DVP, a, S->A[a], 0, S->A[a].vp, dsv[a], a == 1 ? ppyi : nullptr);   // deryvp * ppyi, derive.f90:4572-4580
     prep(ctx, S->ivp[a], IVP, a, S->A[a], 1, S->A[a].ivpp, dsv[a]);
   }
   // gradp chain (navier.f90:404-431): z on (nxm,nyml,nzm), y on (nxm,nym,nzl), x on (nxm,ny,nzl)
@@ -252,7 +264,7 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   const int *gsv[3] = {gx, gy, gz};
   for (int a = 0; a < 3; ++a) {
     const AxisCoeffs &A = S->A[a];
-    prep(ctx, S->dpv[a], DPV, a, A, 1, A.periodic ? A.vp : A.pvp, gsv[a]);
+    prep(ctx, S->dpv[a], DPV, a, A, 1, A.periodic ? A.vp : A.pvp, gsv[a], a == 1 ? ppy : nullptr);  // derypv * ppy, :4905-4913
     prep(ctx, S->ipv[a], IPV, a, A, 1, A.periodic ? A.ivp : A.ipvp, gsv[a]);
   }
   // fused momentum kernels where the direction is periodic and the tile kernel fits (x3d_mom.cu)
@@ -274,8 +286,21 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   x3d_poisson_params pp{};
   pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
   pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
-  pp.xlx = p.xlx; pp.yly = p.yly; pp.zlz = p.zlz; pp.istret = 0;
+  pp.xlx = p.xlx; pp.yly = p.yly; pp.zlz = p.zlz; pp.istret = p.istret;
+  pp.alpha = S->st.alpha; pp.beta = p.beta;
   poisson_init(ctx, pp);
+  if (stretched) {
+    std::vector<double> h(3 * static_cast<size_t>(p.ny));
+    for (int j = 0; j < p.ny; ++j) { h[j] = S->st.pp2y[j]; h[p.ny + j] = S->st.pp4y[j]; h[2 * p.ny + j] = S->st.ppy[j]; }
+    S->d_pp.reserve(h.size() * sizeof(double));
+    X3D_CUDA(cudaMemcpyAsync(S->d_pp.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  {
+    const size_t ndpd = 4 * (static_cast<size_t>(p.ny) * nzl + static_cast<size_t>(p.nx) * nzl + static_cast<size_t>(p.nx) * p.ny);
+    S->dpd.reserve(std::max<size_t>(ndpd, 1) * sizeof(double));
+    X3D_CUDA(cudaMemsetAsync(S->dpd.p, 0, S->dpd.bytes, ctx.stream));
+  }
   ctx.solver = std::move(S);
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
 }
@@ -311,6 +336,56 @@ void solver_init_tgv(Ctx &ctx) {
     for (DevBuf *b : {&S.dux[q], &S.duy[q], &S.duz[q]}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
   for (DevBuf *b : {&S.px, &S.py, &S.pz, &S.pp3}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
   S.itime = 0;
+}
+
+// init_channel with iin = 0, Case-Channel.f90:71-94
+void solver_init_channel(Ctx &ctx) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const int nx = S.p.nx, ny = S.p.ny, z0 = S.z0;
+  const double dx = S.A[0].d, dy = S.A[1].d, dz = S.A[2].d, yly = S.p.yly;
+  double *ux = B(S.ux), *uy = B(S.uy), *uz = B(S.uz);
+  DevBuf ypd;
+  ypd.reserve(sizeof(double) * ny);
+  std::vector<double> yh(ny);
+  for (int j = 0; j < ny; ++j) yh[j] = (S.p.istret == 0) ? static_cast<double>(j) * dy - yly * 0.5 : S.st.yp[j] - yly * 0.5;
+  X3D_CUDA(cudaMemcpyAsync(ypd.p, yh.data(), sizeof(double) * ny, cudaMemcpyHostToDevice, ctx.stream));
+  const double *yp = B(ypd);
+  map(ctx, S.n, [=] __device__(long long q) {
+    const int i = static_cast<int>(q % nx), j = static_cast<int>((q / nx) % ny), k = static_cast<int>(q / (static_cast<long long>(nx) * ny)) + z0;
+    const double y = yp[j];
+    ux[q] = 1.0 - y * y;
+    uy[q] = 0.0;
+    uz[q] = sin(static_cast<double>(i) * dx) + cos(static_cast<double>(k) * dz);
+  });
+  for (int q = 0; q < S.ntime; ++q)
+    for (DevBuf *b : {&S.dux[q], &S.duy[q], &S.duz[q]}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
+  for (DevBuf *b : {&S.px, &S.py, &S.pz, &S.pp3, &S.dpd}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));  // ypd goes out of scope
+  S.itime = 0;
+}
+
+// boundary_conditions_channel (Case-Channel.f90:150-170, cpg = F, idir_stream = 1): channel_cfr(ux, 2/3), :220-261
+static void boundary_conditions(Ctx &ctx, SolverImpl &S) {
+  if (S.p.itype != 3) return;
+  const long long n = static_cast<long long>(S.n);
+  const int nx = S.p.nx, ny = S.p.ny;
+  double *u = B(S.ux);
+  const double *ippy = S.p.istret ? B(S.d_pp) + 2 * ny : nullptr;
+  double *partial = B(S.red_partial), *dout = B(S.red_out);
+  const int nb = gridn(ctx, n) > 4096 ? 4096 : gridn(ctx, n);
+  k_reduce_partial<1><<<nb, 256, 0, ctx.stream>>>(n, [=] __device__(long long q, double *acc) {
+    const int j = static_cast<int>((q / nx) % ny);
+    acc[0] += ippy ? u[q] / ippy[j] : u[q];
+  }, partial);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  k_reduce_final<1><<<1, 256, 0, ctx.stream>>>(nb, partial, dout + 12);
+  X3D_CUDA(cudaGetLastError()); ctx.launches++;
+  allreduce(ctx, dout + 12, 1, false);
+  const double coeff = S.A[1].d / (S.p.yly * static_cast<double>(nx) * static_cast<double>(S.p.nz));
+  const double constant = 2.0 / 3.0;
+  const double *ub = dout + 12;
+  map(ctx, n, [=] __device__(long long q) { u[q] = u[q] - (-(constant - ub[0] * coeff)); });
 }
 
 // transeq.f90:73-591 (incompressible, explicit diffusion, uniform mesh)
@@ -353,6 +428,22 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
   map(ctx, n, [=] __device__(long long q) { tg2[q] = zx[q] - half * tg2[q]; th2[q] = zy[q] - half * th2[q]; ti2[q] = zz[q] - half * ti2[q]; });
   // y diffusion, :336-433
   run(ctx, S.d2[1][1], u, td); run(ctx, S.d2[1][0], v, te); run(ctx, S.d2[1][1], w, tf);
+  if (S.p.istret != 0) {  // td = td pp2y - pp4y dery(u), :339-372 (the dery carries its ppy factor)
+    const double *pp2 = B(S.d_pp), *pp4 = B(S.d_pp) + S.p.ny;
+    const int nx_ = S.p.nx, ny_ = S.p.ny;
+    double *tj = B(S.w[15]);
+    const PreOp *ops[3] = {&S.d1[1][1], &S.d1[1][0], &S.d1[1][1]};
+    const double *fld[3] = {u, v, w};
+    double *dst[3] = {td, te, tf};
+    for (int c = 0; c < 3; ++c) {
+      run(ctx, *ops[c], fld[c], tj);
+      double *t2 = dst[c];
+      map(ctx, n, [=] __device__(long long q) {
+        const int j = static_cast<int>((q / nx_) % ny_);
+        t2[q] = t2[q] * pp2[j] - pp4[j] * tj[q];
+      });
+    }
+  }
   // x diffusion and final sum, :442-470
   run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);
   map(ctx, n, [=] __device__(long long q) {
@@ -469,11 +560,42 @@ static void intt3(Ctx &ctx, SolverImpl &S, int itr) {
 }
 
 // navier.f90:599-613,693-711,751-769 (free-slip faces); the x/y pencil holds z planes z0 .. z0+nzl-1
-static void pre_correc(Ctx &ctx, SolverImpl &S) {
+static void pre_correc(Ctx &ctx, SolverImpl &S, int itr) {
   const int nx = S.p.nx, ny = S.p.ny, nzl = S.nzl;
   double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   const bool x1 = S.p.nclx1 == 1, xn = S.p.nclxn == 1, y1 = S.p.ncly1 == 1, yn = S.p.nclyn == 1;
   const bool z1 = S.p.nclz1 == 1 && S.z0 == 0, zn = S.p.nclzn == 1 && S.z0 + nzl == S.p.nz;
+  // ---- Dirichlet (no-slip) faces, navier.f90:560-589,616-689,712-745: wall velocity 0, tangential components
+  //      + wall pressure gradient of the previous gradp times gdt(itr)
+  {
+    const double g = S.gdt[itr - 1];
+    double *d = B(S.dpd);
+    const long long nyz = static_cast<long long>(ny) * nzl, nxz = static_cast<long long>(nx) * nzl, nxy = static_cast<long long>(nx) * ny;
+    double *dx_ = d, *dy_ = d + 4 * nyz, *dz_ = d + 4 * nyz + 4 * nxz;
+    const bool dx1 = S.p.nclx1 == 2, dxn = S.p.nclxn == 2, dy1 = S.p.ncly1 == 2, dyn = S.p.nclyn == 2;
+    const bool dz1 = S.p.nclz1 == 2 && S.z0 == 0, dzn = S.p.nclzn == 2 && S.z0 + nzl == S.p.nz;
+    if (dx1 || dxn)
+      map(ctx, nyz, [=] __device__(long long q) {  // q = j + ny k ; planes: dpdyx1, dpdzx1, dpdyxn, dpdzxn
+        if (dx1) { const double a = dx_[q] * g, b = dx_[nyz + q] * g; dx_[q] = a; dx_[nyz + q] = b; u[q * nx] = 0.0; v[q * nx] = a; w[q * nx] = b; }
+        if (dxn) { const double a = dx_[2 * nyz + q] * g, b = dx_[3 * nyz + q] * g; dx_[2 * nyz + q] = a; dx_[3 * nyz + q] = b;
+                   u[q * nx + nx - 1] = 0.0; v[q * nx + nx - 1] = a; w[q * nx + nx - 1] = b; }
+      });
+    if (dy1 || dyn)
+      map(ctx, nxz, [=] __device__(long long q) {  // q = i + nx k ; planes: dpdxy1, dpdzy1, dpdxyn, dpdzyn
+        const long long i = q % nx, k = q / nx;
+        if (dy1) { const long long p = i + static_cast<long long>(nx) * ny * k; const double a = dy_[q] * g, b = dy_[nxz + q] * g;
+                   dy_[q] = a; dy_[nxz + q] = b; u[p] = a; v[p] = 0.0; w[p] = b; }
+        if (dyn) { const long long p = i + static_cast<long long>(nx) * (ny - 1 + static_cast<long long>(ny) * k);
+                   const double a = dy_[2 * nxz + q] * g, b = dy_[3 * nxz + q] * g; dy_[2 * nxz + q] = a; dy_[3 * nxz + q] = b;
+                   u[p] = a; v[p] = 0.0; w[p] = b; }
+      });
+    if (dz1 || dzn)
+      map(ctx, nxy, [=] __device__(long long q) {  // planes: dpdxz1, dpdyz1, dpdxzn, dpdyzn
+        if (dz1) { const double a = dz_[q] * g, b = dz_[nxy + q] * g; dz_[q] = a; dz_[nxy + q] = b; u[q] = a; v[q] = b; w[q] = 0.0; }
+        if (dzn) { const long long p = q + nxy * (nzl - 1); const double a = dz_[2 * nxy + q] * g, b = dz_[3 * nxy + q] * g;
+                   dz_[2 * nxy + q] = a; dz_[3 * nxy + q] = b; u[p] = a; v[p] = b; w[p] = 0.0; }
+      });
+  }
   if (x1 || xn)
     map(ctx, static_cast<long long>(ny) * nzl, [=] __device__(long long q) {
       if (x1) u[q * nx] = 0.0;
@@ -522,7 +644,7 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
 }
 
 // navier.f90:386-431
-static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3) {
+static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
   double *ppi3 = B(S.w[0]), *pgz3 = B(S.w[1]), *ppi2 = B(S.w[2]), *pgy2 = B(S.w[3]), *pgzi2 = B(S.w[4]);
   double *t1 = B(S.w[5]), *t2 = B(S.w[6]);
   run(ctx, S.ipv[2], pp3, ppi3);   // :404
@@ -535,6 +657,33 @@ static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3) {
   run(ctx, S.dpv[0], ppi2, B(S.px));   // :426
   run(ctx, S.ipv[0], pgy2, B(S.py));   // :428
   run(ctx, S.ipv[0], pgzi2, B(S.pz));  // :430
+  // wall pressure gradients for the next pre_correc, :439-496 (the z faces keep py / pz, as the reference does)
+  {
+    const int nx = S.p.nx, ny = S.p.ny, nzl = S.nzl;
+    const double g = S.gdt[itr - 1];
+    const double *px = B(S.px), *py = B(S.py), *pz = B(S.pz);
+    double *d = B(S.dpd);
+    const long long nyz = static_cast<long long>(ny) * nzl, nxz = static_cast<long long>(nx) * nzl, nxy = static_cast<long long>(nx) * ny;
+    double *dx_ = d, *dy_ = d + 4 * nyz, *dz_ = d + 4 * nyz + 4 * nxz;
+    const bool dx1 = S.p.nclx1 == 2, dxn = S.p.nclxn == 2, dy1 = S.p.ncly1 == 2, dyn = S.p.nclyn == 2;
+    const bool dz1 = S.p.nclz1 == 2 && S.z0 == 0, dzn = S.p.nclzn == 2 && S.z0 + nzl == S.p.nz;
+    if (dx1 || dxn)
+      map(ctx, nyz, [=] __device__(long long q) {
+        if (dx1) { dx_[q] = py[q * nx] / g; dx_[nyz + q] = pz[q * nx] / g; }
+        if (dxn) { dx_[2 * nyz + q] = py[q * nx + nx - 1] / g; dx_[3 * nyz + q] = pz[q * nx + nx - 1] / g; }
+      });
+    if (dy1 || dyn)
+      map(ctx, nxz, [=] __device__(long long q) {
+        const long long i = q % nx, k = q / nx;
+        if (dy1) { const long long p = i + static_cast<long long>(nx) * ny * k; dy_[q] = px[p] / g; dy_[nxz + q] = pz[p] / g; }
+        if (dyn) { const long long p = i + static_cast<long long>(nx) * (ny - 1 + static_cast<long long>(ny) * k); dy_[2 * nxz + q] = px[p] / g; dy_[3 * nxz + q] = pz[p] / g; }
+      });
+    if (dz1 || dzn)
+      map(ctx, nxy, [=] __device__(long long q) {
+        if (dz1) { dz_[q] = py[q] / g; dz_[nxy + q] = pz[q] / g; }
+        if (dzn) { const long long p = q + nxy * (nzl - 1); dz_[2 * nxy + q] = py[p] / g; dz_[3 * nxy + q] = pz[p] / g; }
+      });
+  }
 }
 
 void solver_step(Ctx &ctx, int nsteps) {
@@ -544,6 +693,7 @@ void solver_step(Ctx &ctx, int nsteps) {
   for (int st = 0; st < nsteps; ++st) {
     S.itime += 1;
     for (int itr = 1; itr <= S.iadvance; ++itr) {  // xcompact3d.f90:46-88
+      boundary_conditions(ctx, S);
       if (S.fused[1] && S.fused[2]) {
         double *rhs[3][3] = {{B(S.w[0]), B(S.w[1]), B(S.w[2])}, {B(S.w[3]), B(S.w[4]), B(S.w[5])}, {B(S.w[6]), B(S.w[7]), B(S.w[8])}};
         momentum_rhs_fused(ctx, S, rhs);
@@ -552,10 +702,10 @@ void solver_step(Ctx &ctx, int nsteps) {
         momentum_rhs(ctx, S, B(S.dux[0]), B(S.duy[0]), B(S.duz[0]));
         intt3(ctx, S, itr);
       }
-      pre_correc(ctx, S);
+      pre_correc(ctx, S, itr);
       divergence(ctx, S, B(S.pp3), 1);
       poisson_solve_device(ctx, B(S.pp3));
-      gradp(ctx, S, B(S.pp3));
+      gradp(ctx, S, B(S.pp3), itr);
       double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
       const double *px = B(S.px), *py = B(S.py), *pz = B(S.pz);
       map(ctx, n, [=] __device__(long long q) { u[q] = u[q] - px[q]; v[q] = v[q] - py[q]; w[q] = w[q] - pz[q]; });  // cor_vel

@@ -192,6 +192,23 @@ void *x3do_solver_create(int nx, int ny, int nz, const int *ncl6, double xlx, do
     return s;
   } catch (std::exception &e) { g_err = e.what(); return nullptr; }
 }
+// channel flow (BASELINE config #3): Dirichlet walls in y, constant flow rate, optional stretched mesh
+void *x3do_solver_create_case(int nx, int ny, int nz, const int *ncl6, double xlx, double yly, double zlz, double re, double dt,
+                              int itimescheme, int ifirstder, int isecondder, int ipinter, int istret, double beta, int itype,
+                              double nu0nu, double cnu) {
+  try {
+    auto *s = new Solver();
+    s->p.nx = nx; s->p.ny = ny; s->p.nz = nz;
+    for (int a = 0; a < 3; ++a) { s->p.ncl[a][0] = ncl6[2 * a]; s->p.ncl[a][1] = ncl6[2 * a + 1]; }
+    s->p.xlx = xlx; s->p.yly = yly; s->p.zlz = zlz; s->p.re = re; s->p.dt = dt; s->p.itimescheme = itimescheme;
+    s->p.opt.ifirstder = ifirstder; s->p.opt.isecondder = isecondder; s->p.opt.ipinter = ipinter;
+    s->p.opt.nu0nu = nu0nu; s->p.opt.cnu = cnu;
+    s->p.istret = istret; s->p.beta = beta; s->p.itype = itype;
+    s->init();
+    return s;
+  } catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void x3do_solver_init_channel(void *s) { static_cast<Solver *>(s)->init_channel(); }
 void x3do_solver_destroy(void *s) { delete static_cast<Solver *>(s); }
 void x3do_solver_init_tgv(void *s) { static_cast<Solver *>(s)->init_tgv(); }
 int x3do_solver_step(void *s, int nsteps) {

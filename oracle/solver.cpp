@@ -63,7 +63,47 @@ void Solver::init() {
   px.assign(n, 0.0); py.assign(n, 0.0); pz.assign(n, 0.0);
   pp3.assign(static_cast<size_t>(nxm) * nym * nzm, 0.0);
   for (int q = 0; q < ntime; ++q) { dux[q].assign(n, 0.0); duy[q].assign(n, 0.0); duz[q].assign(n, 0.0); }
+  const size_t nyz = static_cast<size_t>(p.ny) * p.nz, nxz = static_cast<size_t>(p.nx) * p.nz, nxy = static_cast<size_t>(p.nx) * p.ny;
+  for (auto *v : {&dpdyx1, &dpdzx1, &dpdyxn, &dpdzxn}) v->assign(nyz, 0.0);
+  for (auto *v : {&dpdxy1, &dpdzy1, &dpdxyn, &dpdzyn}) v->assign(nxz, 0.0);
+  for (auto *v : {&dpdxz1, &dpdyz1, &dpdxzn, &dpdyzn}) v->assign(nxy, 0.0);
   itime = 0;
+}
+
+// Case-Channel.f90:71-94 (iin = 0): ux = 1 - y^2, uz = sin(x) + cos(z), walls at y = -+ yly/2
+void Solver::init_channel() {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  const double dx = X.d, dy = Y.d, dz = Z.d;
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j) {
+      const double y = (p.istret == 0) ? static_cast<double>(j) * dy - p.yly * 0.5 : st.yp[j] - p.yly * 0.5;
+      for (int i = 0; i < nx; ++i) {
+        const size_t id = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
+        ux[id] = 1.0 - y * y;
+        uy[id] = 0.0;
+        uz[id] = std::sin(static_cast<double>(i) * dx) + std::cos(static_cast<double>(k) * dz);
+      }
+    }
+}
+
+// Case-Channel.f90:220-261
+void Solver::channel_cfr(std::vector<double> &u, double constant) {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  double ub = 0.0;
+  const double coeff = Y.d / (p.yly * static_cast<double>(nx) * static_cast<double>(nz));
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j) {
+      const double pj = p.istret ? st.ppy[j] : 1.0;
+      for (int i = 0; i < nx; ++i) ub = ub + u[i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k)] / pj;
+    }
+  ub = ub * coeff;
+  const double can = -(constant - ub);
+  for (double &v : u) v = v - can;
+}
+
+// boundary_conditions_channel, Case-Channel.f90:150-170 (cpg = F, idir_stream = 1)
+void Solver::boundary_conditions() {
+  if (p.itype == 3) channel_cfr(ux, 2.0 / 3.0);
 }
 
 // Case-TGV.f90:58-100 (iin=1, no noise)
@@ -182,18 +222,52 @@ void Solver::intt(std::vector<double> &var, std::vector<double> *dvar) {
   }
 }
 
-// navier.f90:502-789 -- only the free-slip (ncl=1) planes matter for the restated cases; Dirichlet
-// planes of TGV-type boxes would need the case's b?? arrays (Channel/Cylinder glue)
+// navier.f90:502-789.  Dirichlet faces (ncl = 2) are no-slip walls here: the case arrays b?? are zero
+// (Case-Channel.f90:67); the tangential components get the wall pressure gradient stored by gradp.
 void Solver::pre_correc() {
   const int nx = p.nx, ny = p.ny, nz = p.nz;
   auto id = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
-  for (int a = 0; a < 3; ++a)
-    for (int e = 0; e < 2; ++e)
-      if (p.ncl[a][e] == 2) throw std::runtime_error("oracle pre_correc: Dirichlet planes need case boundary data");
+  const double g = gdt[itr - 1];
+  if (p.ncl[0][0] == 2)  // :560-574
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
+      const size_t q = j + static_cast<size_t>(ny) * k;
+      dpdyx1[q] *= g; dpdzx1[q] *= g;
+      ux[id(0, j, k)] = 0.0; uy[id(0, j, k)] = 0.0 + dpdyx1[q]; uz[id(0, j, k)] = 0.0 + dpdzx1[q];
+    }
+  if (p.ncl[0][1] == 2)  // :575-589
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
+      const size_t q = j + static_cast<size_t>(ny) * k;
+      dpdyxn[q] *= g; dpdzxn[q] *= g;
+      ux[id(nx - 1, j, k)] = 0.0; uy[id(nx - 1, j, k)] = 0.0 + dpdyxn[q]; uz[id(nx - 1, j, k)] = 0.0 + dpdzxn[q];
+    }
   if (p.ncl[0][0] == 1) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) ux[id(0, j, k)] = 0.0;        // :600-606
   if (p.ncl[0][1] == 1) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) ux[id(nx - 1, j, k)] = 0.0;   // :607-613
+  if (p.ncl[1][0] == 2)  // :616-642
+    for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * k;
+      dpdxy1[q] *= g; dpdzy1[q] *= g;
+      ux[id(i, 0, k)] = 0.0 + dpdxy1[q]; uy[id(i, 0, k)] = 0.0; uz[id(i, 0, k)] = 0.0 + dpdzy1[q];
+    }
+  if (p.ncl[1][1] == 2)  // :644-689
+    for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * k;
+      dpdxyn[q] *= g; dpdzyn[q] *= g;
+      ux[id(i, ny - 1, k)] = 0.0 + dpdxyn[q]; uy[id(i, ny - 1, k)] = 0.0; uz[id(i, ny - 1, k)] = 0.0 + dpdzyn[q];
+    }
   if (p.ncl[1][0] == 1) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) uy[id(i, 0, k)] = 0.0;        // :693-701
   if (p.ncl[1][1] == 1) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) uy[id(i, ny - 1, k)] = 0.0;   // :703-711
+  if (p.ncl[2][0] == 2)  // :712-728
+    for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * j;
+      dpdxz1[q] *= g; dpdyz1[q] *= g;
+      ux[id(i, j, 0)] = 0.0 + dpdxz1[q]; uy[id(i, j, 0)] = 0.0 + dpdyz1[q]; uz[id(i, j, 0)] = 0.0;
+    }
+  if (p.ncl[2][1] == 2)  // :729-745
+    for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+      const size_t q = i + static_cast<size_t>(nx) * j;
+      dpdxzn[q] *= g; dpdyzn[q] *= g;
+      ux[id(i, j, nz - 1)] = 0.0 + dpdxzn[q]; uy[id(i, j, nz - 1)] = 0.0 + dpdyzn[q]; uz[id(i, j, nz - 1)] = 0.0;
+    }
   if (p.ncl[2][0] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, 0)] = 0.0;        // :751-759
   if (p.ncl[2][1] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, nz - 1)] = 0.0;   // :761-769
 }
@@ -254,6 +328,15 @@ void Solver::gradp(double *px1, double *py1, double *pz1, const double *pp3in) {
   apply_op(pv(DPV, X, nullptr), 0, dxx, ppi2, px1);   // :426
   apply_op(pv(IPV, X, nullptr), 0, dxx, pgy2, py1);   // :428
   apply_op(pv(IPV, X, nullptr), 0, dxx, pgzi2, pz1);  // :430
+  // wall pressure gradients for the next pre_correc, :439-496 (the z faces store py1 / pz1 as the reference does)
+  auto id = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
+  const double g = gdt[itr - 1];
+  if (p.ncl[0][0] == 2) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) { dpdyx1[j + static_cast<size_t>(ny) * k] = py1[id(0, j, k)] / g; dpdzx1[j + static_cast<size_t>(ny) * k] = pz1[id(0, j, k)] / g; }
+  if (p.ncl[0][1] == 2) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) { dpdyxn[j + static_cast<size_t>(ny) * k] = py1[id(nx - 1, j, k)] / g; dpdzxn[j + static_cast<size_t>(ny) * k] = pz1[id(nx - 1, j, k)] / g; }
+  if (p.ncl[1][0] == 2) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) { dpdxy1[i + static_cast<size_t>(nx) * k] = px1[id(i, 0, k)] / g; dpdzy1[i + static_cast<size_t>(nx) * k] = pz1[id(i, 0, k)] / g; }
+  if (p.ncl[1][1] == 2) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) { dpdxyn[i + static_cast<size_t>(nx) * k] = px1[id(i, ny - 1, k)] / g; dpdzyn[i + static_cast<size_t>(nx) * k] = pz1[id(i, ny - 1, k)] / g; }
+  if (p.ncl[2][0] == 2) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) { dpdxz1[i + static_cast<size_t>(nx) * j] = py1[id(i, j, 0)] / g; dpdyz1[i + static_cast<size_t>(nx) * j] = pz1[id(i, j, 0)] / g; }
+  if (p.ncl[2][1] == 2) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) { dpdxzn[i + static_cast<size_t>(nx) * j] = py1[id(i, j, nz - 1)] / g; dpdyzn[i + static_cast<size_t>(nx) * j] = pz1[id(i, j, nz - 1)] / g; }
 }
 
 // navier.f90:242-244
@@ -267,6 +350,7 @@ void Solver::cor_vel() {
 void Solver::step() {
   itime += 1;
   for (itr = 1; itr <= iadvance_time; ++itr) {
+    boundary_conditions();                         // xcompact3d.f90:52
     momentum_rhs_eq(dux[0].data(), duy[0].data(), duz[0].data());
     intt(ux, dux); intt(uy, duy); intt(uz, duz);
     pre_correc();

@@ -123,6 +123,7 @@ struct SolverParams {
   SchemeOptions opt;
   int istret = 0;
   double beta = 0.259065151;
+  int itype = 0;  // 0: TGV-type box; 3: channel (itype_channel): constant flow rate channel_cfr, Case-Channel.f90:150-170
 };
 struct Solver {
   SolverParams p;
@@ -137,8 +138,13 @@ struct Solver {
   std::vector<double> ux, uy, uz, px, py, pz, pp3;
   std::vector<double> dux[3], duy[3], duz[3];
   std::vector<std::vector<double>> work;
+  // wall pressure-gradient terms captured by gradp and used by pre_correc (navier.f90:439-496, 560-746)
+  std::vector<double> dpdyx1, dpdzx1, dpdyxn, dpdzxn, dpdxy1, dpdzy1, dpdxyn, dpdzyn, dpdxz1, dpdyz1, dpdxzn, dpdyzn;
   void init();
   void init_tgv();
+  void init_channel();        // Case-Channel.f90:25-107, iin = 0 (laminar profile + deterministic perturbation)
+  void boundary_conditions(); // case.f90 boundary_conditions -> boundary_conditions_channel
+  void channel_cfr(std::vector<double> &u, double constant);
   void step();  // one full time step (iadvance_time sub-steps)
   void momentum_rhs_eq(double *dux1, double *duy1, double *duz1);
   void intt(std::vector<double> &var, std::vector<double> *dvar);

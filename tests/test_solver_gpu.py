@@ -81,3 +81,47 @@ def test_solver_matches_oracle(nn, ncl):
         assert ("momentum_fused_x(k_mom_pair)" in names) == (nn[0] >= 168), names
     Ls.x3do_solver_destroy(s)
     x.close()
+
+
+@pytest.mark.parametrize("nn,istret,second", [((32, 33, 16), 0, 4), ((32, 33, 16), 2, 5), ((24, 41, 20), 1, 4), ((16, 33, 12), 3, 4)])
+def test_channel_matches_oracle(nn, istret, second):
+    """BASELINE config #3 at reduced size: channel with no-slip walls in y (ncly = 2), constant flow rate,
+    stretched mesh (istret) and stretched Poisson, hyperviscous second derivative (isecondder = 5) -- velocity
+    fields against the oracle after every step."""
+    from incompact3d_b200 import X3D
+    ncl = (0, 0, 2, 2, 0, 0)
+    lx, ly, lz = 8.0, 2.0, 3.0
+    beta = 0.259065151
+    L = ol.lib()
+    L.x3do_solver_create_case.restype = C.c_void_p
+    L.x3do_solver_create_case.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] + [C.c_double] * 5 + [C.c_int] * 5 + [C.c_double, C.c_int,
+                                                                                                                 C.c_double, C.c_double]
+    L.x3do_solver_init_channel.argtypes = [C.c_void_p]
+    s = L.x3do_solver_create_case(*nn, (C.c_int * 6)(*ncl), lx, ly, lz, 4200.0, 0.002, 5, 4, second, 3, istret, beta, 3, 4.0, 0.44)
+    assert s, L.x3do_last_error()
+    s = C.c_void_p(s)
+    L.x3do_solver_init_channel(s)
+    x = X3D(0)
+    x.solver_init(*nn, ncl=ncl, xlx=lx, yly=ly, zlz=lz, re=4200.0, dt=0.002, isecondder=second, istret=istret, beta=beta, itype=3)
+    x.solver_init_channel()
+    dp = C.POINTER(C.c_double)
+    for it in range(4):
+        x.solver_step(1)
+        assert L.x3do_solver_step(s, 1) == 0, L.x3do_last_error()
+        gu, gv, gw = x.solver_get_velocity()
+        ru, rv, rw = (np.zeros(nn, order="F") for _ in range(3))
+        L.x3do_solver_get_velocity(s, ru.ctypes.data_as(dp), rv.ctypes.data_as(dp), rw.ctypes.data_as(dp))
+        scale = max(np.abs(ru).max(), np.abs(rv).max(), np.abs(rw).max())
+        for a, b in ((gu, ru), (gv, rv), (gw, rw)):
+            assert np.abs(a - b).max() / scale < 1e-10, (it, np.abs(a - b).max() / scale)
+    dmax, dmean = x.solver_divergence()
+    omax, omean = C.c_double(), C.c_double()
+    L.x3do_solver_divergence.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    assert L.x3do_solver_divergence(s, C.byref(omax), C.byref(omean)) == 0
+    # the projection leaves a machine-level divergence for istret 0-2; for the one-sided mapping (istret = 3) it does
+    # not, in the oracle as in the product: compare with the oracle's value instead
+    if istret != 3:
+        assert abs(dmax) < 1e-10
+    assert abs(dmax - omax.value) < 1e-9 * max(1.0, abs(omax.value) * 1e3)
+    L.x3do_solver_destroy(s)
+    x.close()
