@@ -547,6 +547,50 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
   boxcopy<false>(ctx, T.recv, rb, d_dst, elem);
 }
 
+// several fields through the same transpose: one pair of group barriers around all the peer-store kernels
+void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_src, double *const *d_dst, int id, int elem) {
+  DecompImpl &D = DEC(ctx);
+  TransposePlan &T = get_plan(ctx, D, id, which);
+  bool p2p = D.p2p && D.have_nccl && T.npeers > 1 && nf > 1;
+  DecompImpl::Group &G = (which == 0 || which == 3) ? D.grp_row : D.grp_col;
+  std::vector<void *const *> peers(nf, nullptr);
+  if (p2p)
+    for (int f = 0; f < nf; ++f) {  // every member resolves every field (collective on a first use), then all agree
+      peers[f] = p2p_dst(ctx, D, G, d_dst[f]);
+      if (!peers[f]) p2p = false;
+    }
+  if (!p2p) {
+    for (int f = 0; f < nf; ++f) transpose_device(ctx, which, d_src[f], d_dst[f], id, elem);
+    return;
+  }
+  const SidePlan &S = T.send;
+  const long long ns = static_cast<long long>(S.dims[0]) * S.dims[1] * S.dims[2];
+  const int ext = S.dims[S.axis], np = T.npeers;
+  const int *blk_of = S.d_meta, *bst = S.d_meta + ext, *bsz = S.d_meta + ext + np;
+  const int my_off = T.recv.blk_start[G.me];
+  group_barrier(ctx, G);
+  if (ns > 0) {
+    ProfScope ps(ctx, "transpose_p2p(k_p2p_transpose)");
+    for (int f = 0; f < nf; ++f) {
+      const bool pairs = elem == 1 && S.axis != 0 && T.recv.axis != 0 && (S.dims[0] % 2 == 0) &&
+                         (reinterpret_cast<uintptr_t>(d_src[f]) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_dst[f]) % 16 == 0);
+      if (pairs || elem == 2) {
+        const int half = pairs ? 2 : 1;
+        k_p2p_transpose<double2><<<grid_for(ctx, ns / half), 256, 0, ctx.stream>>>(
+            reinterpret_cast<const double2 *>(d_src[f]), reinterpret_cast<double2 *const *>(peers[f]), S.dims[0] / half, S.dims[1], S.dims[2],
+            S.axis, T.recv.axis, blk_of, bst, bsz, my_off, T.recv.dims[0] / half, T.recv.dims[1], T.recv.dims[2]);
+      } else {
+        k_p2p_transpose<double><<<grid_for(ctx, ns), 256, 0, ctx.stream>>>(d_src[f], reinterpret_cast<double *const *>(peers[f]), S.dims[0],
+                                                                          S.dims[1], S.dims[2], S.axis, T.recv.axis, blk_of, bst, bsz, my_off,
+                                                                          T.recv.dims[0], T.recv.dims[1], T.recv.dims[2]);
+      }
+      X3D_CUDA(cudaGetLastError());
+      ctx.launches++;
+    }
+  }
+  group_barrier(ctx, G);
+}
+
 // host-or-device entry of the C ABI
 void transpose(Ctx &ctx, int which, const double *src, double *dst, int id, int elem) {
   DecompImpl &D = DEC(ctx);

@@ -61,6 +61,7 @@ struct SpecArgs {
   int k0;
   int bcx, bcy, bcz;
   double norm_x, norm_y, norm_z;
+  double inv_norm;   // 1 / (nx ny nz): the reference divides three times (src/poisson.f90:333); exact for powers of two
   const double *ax, *bx, *ay, *by, *az, *bz;
   const double *xk2, *yk2, *zk2, *tx, *ty, *tz;
 };
@@ -103,8 +104,8 @@ __global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
     const int kl = static_cast<int>(idx / (static_cast<long long>(a.nx) * a.ny));
     const int k = kl + a.k0;
     double2 c = cw[idx];
-    c.x = c.x / a.norm_x / a.norm_y / a.norm_z;
-    c.y = c.y / a.norm_x / a.norm_y / a.norm_z;
+    c.x = c.x * a.inv_norm;
+    c.y = c.y * a.inv_norm;
     c = rot_fwd(c, a.az[k], a.bz[k]);
     c = rot_fwd(c, a.ay[j], a.by[j]);
     if (j + 1 > a.ny / 2 + 1) c = neg(c);
@@ -130,7 +131,7 @@ enum : unsigned { S_NORM = 1, S_ROTZ_F = 2, S_ROTY_F = 4, S_ROTX_F = 8, S_POSTY 
 
 __device__ __forceinline__ double2 pointwise_fwd(const SpecArgs &a, unsigned mode, double2 c, int i, int j, int kl) {
   const int k = kl + a.k0;
-  if (mode & S_NORM) { c.x = c.x / a.norm_x / a.norm_y / a.norm_z; c.y = c.y / a.norm_x / a.norm_y / a.norm_z; }
+  if (mode & S_NORM) { c.x = c.x * a.inv_norm; c.y = c.y * a.inv_norm; }
   if (mode & S_ROTZ_F) c = rot_fwd(c, a.az[k], a.bz[k]);
   if (mode & S_ROTY_F) { c = rot_fwd(c, a.ay[j], a.by[j]); if (j + 1 > a.ny / 2 + 1) c = neg(c); }
   if (mode & S_ROTX_F) { c = rot_fwd(c, a.ax[i], a.bx[i]); if (i + 1 > a.nx / 2 + 1) c = neg(c); }
@@ -651,7 +652,7 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
   const bool multi = P->nranks > 1;
   const long long nsp = static_cast<long long>(nx) * ny * nzhl;
   SpecArgs a{nx, ny, nzhl, nz, P->k0, P->bcx, P->bcy, P->bcz, static_cast<double>(nx), static_cast<double>(ny), static_cast<double>(nz),
-             P->d_ax, P->d_bx, P->d_ay, P->d_by, P->d_az, P->d_bz, P->d_xk2, P->d_yk2, P->d_zk2, P->d_tx, P->d_ty, P->d_tz};
+             1.0 / (static_cast<double>(nx) * static_cast<double>(ny) * static_cast<double>(nz)), P->d_ax, P->d_bx, P->d_ay, P->d_by, P->d_az, P->d_bz, P->d_xk2, P->d_yk2, P->d_zk2, P->d_tx, P->d_ty, P->d_tz};
   double2 *cw = static_cast<double2 *>(P->cw.p), *cwb = static_cast<double2 *>(P->cwb.p);
   double2 *cwz = multi ? static_cast<double2 *>(P->cwz.p) : cw;   // spectral z-pencil (aliases the y-pencil on one rank)
   double *rw = static_cast<double *>(P->rwork.p), *rw2 = static_cast<double *>(P->rwork2.p);

@@ -17,6 +17,7 @@ void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int ran
 int decomp_info_init(Ctx &ctx, int nx, int ny, int nz);
 void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out);
 void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem);
+void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_src, double *const *d_dst, int id, int elem);
 void allreduce(Ctx &ctx, double *d_buf, int n, bool is_max);
 void decomp_shape(Ctx &ctx, int *p_row, int *p_col, int *rank, int *nranks);
 
@@ -489,14 +490,17 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *rhs[3][3]) {
   // ---- z, transeq.f90:236-314 (z pencils)
   {
     double *t0 = B(S.w[9]), *t1 = B(S.w[10]), *t2 = B(S.w[11]), *o0 = B(S.w[12]), *o1 = B(S.w[13]), *o2 = B(S.w[14]);
-    const double *u3 = TR(ctx, S, 1, u, t0, S.id_v), *v3 = TR(ctx, S, 1, v, t1, S.id_v), *w3 = TR(ctx, S, 1, w, t2, S.id_v);
-    const double *f[3] = {u3, v3, w3};
     const bool alias = S.nranks == 1;
+    const double *f[3] = {u, v, w};
+    if (!alias) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
+      double *dst[3] = {t0, t1, t2};
+      transpose_device_multi(ctx, 1, 3, f, dst, S.id_v, 1);
+      f[0] = t0; f[1] = t1; f[2] = t2;
+    }
     double *o[3] = {alias ? rhs[2][0] : o0, alias ? rhs[2][1] : o1, alias ? rhs[2][2] : o2};
     const long long lanes = static_cast<long long>(nx) * S.nyl;
     launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, f, o, lanes, nz, 1, lanes, lanes * nz);
-    if (!alias)
-      for (int c = 0; c < 3; ++c) transpose_device(ctx, 2, o[c], rhs[2][c], S.id_v, 1);
+    if (!alias) transpose_device_multi(ctx, 2, 3, o, rhs[2], S.id_v, 1);  // transeq.f90:318-320
   }
 }
 
@@ -626,8 +630,13 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.nzl;
   map(ctx, n2, [=] __device__(long long q) { duy[q] = duy[q] + upi2[q]; });  // :325
   run(ctx, S.ivp[1], pgz1, upi2);      // :327
-  const double *duy3 = TR(ctx, S, 1, duy, t1, S.id_p3);    // :329
-  const double *uzp3 = TR(ctx, S, 1, upi2, t2, S.id_p3);   // :330
+  const double *duy3 = duy, *uzp3 = upi2;
+  if (S.nranks > 1) {  // :329-330, both fields between one pair of barriers
+    const double *src[2] = {duy, upi2};
+    double *dst[2] = {t1, t2};
+    transpose_device_multi(ctx, 1, 2, src, dst, S.id_p3, 1);
+    duy3 = t1; uzp3 = t2;
+  }
   run(ctx, S.ivp[2], duy3, out);       // :333
   run(ctx, S.dvp[2], uzp3, po3);       // :335
   const long long n3 = static_cast<long long>(S.n3);
@@ -649,8 +658,13 @@ static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
   double *t1 = B(S.w[5]), *t2 = B(S.w[6]);
   run(ctx, S.ipv[2], pp3, ppi3);   // :404
   run(ctx, S.dpv[2], pp3, pgz3);   // :406
-  const double *pgz2 = TR(ctx, S, 2, pgz3, t1, S.id_p3);   // :410
-  const double *pp2 = TR(ctx, S, 2, ppi3, t2, S.id_p3);    // :411
+  const double *pgz2 = pgz3, *pp2 = ppi3;
+  if (S.nranks > 1) {  // :410-411
+    const double *src[2] = {pgz3, ppi3};
+    double *dst[2] = {t1, t2};
+    transpose_device_multi(ctx, 2, 2, src, dst, S.id_p3, 1);
+    pgz2 = t1; pp2 = t2;
+  }
   run(ctx, S.ipv[1], pp2, ppi2);   // :413
   run(ctx, S.dpv[1], pp2, pgy2);   // :415
   run(ctx, S.ipv[1], pgz2, pgzi2); // :417  (transpose_y_to_x :422-424 is local)
