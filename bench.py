@@ -216,8 +216,14 @@ def run_b200(args):
         comp = [r for r in roof if r["name"].startswith("compact_")]
         k = max(comp, key=lambda r: r["total_ms"])
         achieved = 16.0 * (npts / world) / (k["avg_ms"] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel class at 512^3 on one GPU, from the
+        # `ncu --set full` capture summarised in profiles/r1f_ops_ncu_summary.txt (k_pair: 1.0738 GB + 1.0290 GB;
+        # k_contig: 1.0739 + 1.0279).  It equals the algorithmic 2 x 8 B x 512^3 = 2.147 GB to within the write-back
+        # still in L2 at kernel end: no re-reads.
+        traffic = 2.1029e9 if (n == 512 and world == 1) else None
         roofline = {"bound": "hbm", "kernel": k["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "ncu --set full, profiles/r1f_ops_ncu_summary.txt" if traffic else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                     "algorithmic_bytes_per_launch": 16.0 * npts / world,
                     "note": "dominant compact-operator kernel class; 16 B per output point (SURVEY 8d); per-launch CUDA events "

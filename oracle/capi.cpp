@@ -209,6 +209,36 @@ void *x3do_solver_create_case(int nx, int ny, int nz, const int *ncl6, double xl
   } catch (std::exception &e) { g_err = e.what(); return nullptr; }
 }
 void x3do_solver_init_channel(void *s) { static_cast<Solver *>(s)->init_channel(); }
+// pieces of the step on caller data (tests/test_oracle_step_golden.py): wall pressure gradients in the order
+// dpdyx1 dpdzx1 dpdyxn dpdzxn | dpdxy1 dpdzy1 dpdxyn dpdzyn | dpdxz1 dpdyz1 dpdxzn dpdyzn
+static std::vector<double> *dpd_array(Solver *s, int q) {
+  std::vector<double> *v[12] = {&s->dpdyx1, &s->dpdzx1, &s->dpdyxn, &s->dpdzxn, &s->dpdxy1, &s->dpdzy1, &s->dpdxyn, &s->dpdzyn,
+                                &s->dpdxz1, &s->dpdyz1, &s->dpdxzn, &s->dpdyzn};
+  return v[q];
+}
+void x3do_solver_set_wall_gradient(void *sv, int q, const double *in) { auto *v = dpd_array(static_cast<Solver *>(sv), q); std::memcpy(v->data(), in, v->size() * 8); }
+void x3do_solver_get_wall_gradient(void *sv, int q, double *out) { auto *v = dpd_array(static_cast<Solver *>(sv), q); std::memcpy(out, v->data(), v->size() * 8); }
+int x3do_solver_pre_correc(void *sv, int itr, const double *gdt3) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    for (int q = 0; q < 3; ++q) s->gdt[q] = gdt3[q];
+    s->itr = itr;
+    s->pre_correc();
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_capture_wall_gradients(void *sv, int itr, const double *gdt3, const double *px, const double *py, const double *pz) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    for (int q = 0; q < 3; ++q) s->gdt[q] = gdt3[q];
+    s->itr = itr;
+    s->capture_wall_gradients(px, py, pz);
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void x3do_channel_cfr(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant) {
+  channel_cfr_apply(u, nx, ny, nz, ppy, dy, yly, constant);
+}
 void x3do_solver_destroy(void *s) { delete static_cast<Solver *>(s); }
 void x3do_solver_init_tgv(void *s) { static_cast<Solver *>(s)->init_tgv(); }
 int x3do_solver_step(void *s, int nsteps) {

@@ -86,19 +86,22 @@ void Solver::init_channel() {
     }
 }
 
-// Case-Channel.f90:220-261
-void Solver::channel_cfr(std::vector<double> &u, double constant) {
-  const int nx = p.nx, ny = p.ny, nz = p.nz;
+// Case-Channel.f90:220-261; ppy = nullptr on a uniform mesh (ppy = 1)
+void channel_cfr_apply(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant) {
   double ub = 0.0;
-  const double coeff = Y.d / (p.yly * static_cast<double>(nx) * static_cast<double>(nz));
+  const double coeff = dy / (yly * static_cast<double>(nx * nz));
   for (int k = 0; k < nz; ++k)
     for (int j = 0; j < ny; ++j) {
-      const double pj = p.istret ? st.ppy[j] : 1.0;
+      const double pj = ppy ? ppy[j] : 1.0;
       for (int i = 0; i < nx; ++i) ub = ub + u[i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k)] / pj;
     }
   ub = ub * coeff;
   const double can = -(constant - ub);
-  for (double &v : u) v = v - can;
+  const size_t n = static_cast<size_t>(nx) * ny * nz;
+  for (size_t q = 0; q < n; ++q) u[q] = u[q] - can;
+}
+void Solver::channel_cfr(std::vector<double> &u, double constant) {
+  channel_cfr_apply(u.data(), p.nx, p.ny, p.nz, p.istret ? st.ppy.data() : nullptr, Y.d, p.yly, constant);
 }
 
 // boundary_conditions_channel, Case-Channel.f90:150-170 (cpg = F, idir_stream = 1)
@@ -328,7 +331,12 @@ void Solver::gradp(double *px1, double *py1, double *pz1, const double *pp3in) {
   apply_op(pv(DPV, X, nullptr), 0, dxx, ppi2, px1);   // :426
   apply_op(pv(IPV, X, nullptr), 0, dxx, pgy2, py1);   // :428
   apply_op(pv(IPV, X, nullptr), 0, dxx, pgzi2, pz1);  // :430
-  // wall pressure gradients for the next pre_correc, :439-496 (the z faces store py1 / pz1 as the reference does)
+  capture_wall_gradients(px1, py1, pz1);
+}
+
+// wall pressure gradients for the next pre_correc, navier.f90:439-496 (the z faces store py1 / pz1 as the reference does)
+void Solver::capture_wall_gradients(const double *px1, const double *py1, const double *pz1) {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
   auto id = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
   const double g = gdt[itr - 1];
   if (p.ncl[0][0] == 2) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) { dpdyx1[j + static_cast<size_t>(ny) * k] = py1[id(0, j, k)] / g; dpdzx1[j + static_cast<size_t>(ny) * k] = pz1[id(0, j, k)] / g; }

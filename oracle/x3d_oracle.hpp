@@ -145,6 +145,7 @@ struct Solver {
   void init_channel();        // Case-Channel.f90:25-107, iin = 0 (laminar profile + deterministic perturbation)
   void boundary_conditions(); // case.f90 boundary_conditions -> boundary_conditions_channel
   void channel_cfr(std::vector<double> &u, double constant);
+  void capture_wall_gradients(const double *px1, const double *py1, const double *pz1);
   void step();  // one full time step (iadvance_time sub-steps)
   void momentum_rhs_eq(double *dux1, double *duy1, double *duz1);
   void intt(std::vector<double> &var, std::vector<double> *dvar);
@@ -155,5 +156,7 @@ struct Solver {
   void postprocess_tgv(double out[4]);  // eek, eps, eps2, enst
   double *W(int i, size_t n);
 };
+
+void channel_cfr_apply(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant);
 
 }  // namespace x3do
