@@ -525,12 +525,20 @@ static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *rhs[3][3]) {
       u[q] = g * x + u[q]; v[q] = g * y + v[q]; w[q] = g * z + w[q];
       a2[q] = x; b2[q] = y; c2[q] = z;
     });
-  } else {
+  } else if (itr < S.iadvance) {
     const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
     map(ctx, n, [=] __device__(long long q) {
       const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
       u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
       a2[q] = x; b2[q] = y; c2[q] = z;
+    });
+  } else {
+    // last sub-step: the next one (itr = 1 of the following step) has bdt = 0 and never reads the stored
+    // right-hand side (time_integrators.f90:151-154), so it is not written
+    const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
+    map(ctx, n, [=] __device__(long long q) {
+      const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
+      u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
     });
   }
 }
