@@ -51,6 +51,8 @@ struct DevOp {
   int rhs_only;         // deryy with iimplicit>=1: no solve
   int has_post;
   int untouched;        // unsupported npaire: reference leaves t untouched (only post applied)
+  int store_mode;       // 0: t = result | 1: t += result | 2: t -= result  (TMA reduce-add; fuses the elementwise
+                        //    sums of divergence, navier.f90:325,339, and cor_vel, :242-244, into the operator)
   double c0, c[4];      // interior stencil coefficients
   double alpha;         // Sherman-Morrison alpha (alfai, alsai, alcai6, ...)
   double wstart[NBROW][NBCOL];  // row r = sum_q wstart[r][q] * u[q]

@@ -112,7 +112,11 @@ void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double 
   if (L < 0) L = call.axis == 0 ? pick_L_contig(n_out) : pick_L_strided(n_out, ctx.strided_variant);
   if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 2080)");
   const TriTable &T = get_tri(ctx, call.f, call.s, call.w, n_out, L, op.periodic != 0, op.alpha, call.post);
-  ProfScope ps(ctx, call.axis == 0 ? "compact_x(k_contig)" : (call.axis == 1 ? "compact_y(k_strided)" : "compact_z(k_strided)"));
+  // operators that accumulate into their destination move 24 B per point, not 16: they get their own class
+  static const char *names[2][3] = {{"compact_x(k_contig)", "compact_y(k_strided)", "compact_z(k_strided)"},
+                                    {"accumulate_x(k_contig, TMA reduce-add)", "accumulate_y(k_strided, TMA reduce-add)",
+                                     "accumulate_z(k_strided, TMA reduce-add)"}};
+  ProfScope ps(ctx, names[op.store_mode != 0][call.axis]);
   switch (op.kind) {
     case D1: launch_kind_D1(ctx, op, g, T, d_u, d_t); break;
     case D2: launch_kind_D2(ctx, op, g, T, d_u, d_t); break;

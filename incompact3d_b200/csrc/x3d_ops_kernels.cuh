@@ -168,9 +168,16 @@ __global__ void __launch_bounds__(LX *NCMAX, MINB)
     }
   }
   if (active) {
-    X3D_UNROLL
-    for (int m = 0; m < L; ++m)
-      if (q0 + m < n_out) tp[(q0 + m) * sout] = x[m];
+    if (op.store_mode == 0) {
+      X3D_UNROLL
+      for (int m = 0; m < L; ++m)
+        if (q0 + m < n_out) tp[(q0 + m) * sout] = x[m];
+    } else {
+      const double sg = op.store_mode == 1 ? 1.0 : -1.0;
+      X3D_UNROLL
+      for (int m = 0; m < L; ++m)
+        if (q0 + m < n_out) tp[(q0 + m) * sout] += sg * x[m];
+    }
   }
 }
 
@@ -203,6 +210,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// destination += shared (element-wise f64 add performed by the TMA unit; SASS UBLKRED.ADD.F64)
+__device__ __forceinline__ void bulk_red_add_s2g(void *dst, const void *src, unsigned bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 template <int N>
@@ -360,18 +373,23 @@ __global__ void __launch_bounds__(32 * WPB, MINB)
     }
     __syncwarp();  // every lane has read its window
     if (live) {
+      const double sg = op.store_mode == 2 ? -1.0 : 1.0;
       X3D_UNROLL
       for (int m = 0; m < L; ++m)
-        if (q0 + m < n_out) buf[HALO + q0 + m] = x[m];
+        if (q0 + m < n_out) buf[HALO + q0 + m] = sg * x[m];
     }
     if constexpr (TMA) {
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) bulk_s2g(t + line * n_out, buf + HALO, out_bytes);
+      if (lane == 0) {
+        if (op.store_mode == 0) bulk_s2g(t + line * n_out, buf + HALO, out_bytes);
+        else bulk_red_add_s2g(t + line * n_out, buf + HALO, out_bytes);
+      }
     } else {
       __syncwarp();
       double *tp = t + line * n_out;
-      for (int q = lane; q < n_out; q += 32) tp[q] = buf[HALO + q];
+      if (op.store_mode == 0) for (int q = lane; q < n_out; q += 32) tp[q] = buf[HALO + q];
+      else for (int q = lane; q < n_out; q += 32) tp[q] += buf[HALO + q];
       __syncwarp();
     }
   }
@@ -398,6 +416,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, in
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int c0, int c1, int c2, const void *src) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1),
                "r"(c2), "r"(smem_u32(src))
+               : "memory");
+}
+// tensor-map reduce: destination tile += shared tile (SASS UTMAREDG.ADD; f64 from the tensor map)
+__device__ __forceinline__ void tma_red_add_3d(const CUtensorMap *tm, int c0, int c1, int c2, const void *src) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_u32(src))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -585,15 +609,19 @@ __global__ void __launch_bounds__(LX * 32, MINB)
     else __syncthreads();  // every window has been read before the tile is overwritten
     if (live) {
       double *tl = buf + lane;
+      const double sg = op.store_mode == 2 ? -1.0 : 1.0;
       X3D_UNROLL
       for (int m = 0; m < L; ++m)
-        if (q0 + m < n_out) tl[(q0 + m) * LX] = x[m];
+        if (q0 + m < n_out) tl[(q0 + m) * LX] = sg * x[m];
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       const int bx = static_cast<int>(tile % g.nbx), by = static_cast<int>(tile / g.nbx);
-      for (int b = 0; b < g.nbox_out; ++b) tma_store_3d(&tm_out, bx * LX, b * g.br_out, by, buf + b * g.br_out * LX);
+      for (int b = 0; b < g.nbox_out; ++b) {
+        if (op.store_mode == 0) tma_store_3d(&tm_out, bx * LX, b * g.br_out, by, buf + b * g.br_out * LX);
+        else tma_red_add_3d(&tm_out, bx * LX, b * g.br_out, by, buf + b * g.br_out * LX);
+      }
       bulk_commit();
     }
   }
@@ -680,7 +708,10 @@ __global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
       const long long tile = first + k * step;
       const int bx = static_cast<int>(tile % g.nbx), by = static_cast<int>(tile / g.nbx);
       const unsigned char *src = smem_raw + slot * slot_bytes;
-      for (int b = 0; b < g.nbox_out; ++b) tma_store_3d(&tm_out, bx * 16, b * g.br_out, by, src + (8 + b * g.br_out) * 128);
+      for (int b = 0; b < g.nbox_out; ++b) {
+        if (op.store_mode == 0) tma_store_3d(&tm_out, bx * 16, b * g.br_out, by, src + (8 + b * g.br_out) * 128);
+        else tma_red_add_3d(&tm_out, bx * 16, b * g.br_out, by, src + (8 + b * g.br_out) * 128);
+      }
       bulk_commit();
       if (k >= 1 && k - 1 + NB < mine) {  // refill the slot of the previous store once it has left shared memory
         bulk_wait_read<1>();
@@ -800,9 +831,10 @@ __global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
     }
     __syncwarp();  // every lane has read its window (and the closure rows)
     if (live) {
+      const double sg = op.store_mode == 2 ? -1.0 : 1.0;
       X3D_UNROLL
       for (int m = 0; m < L; ++m)
-        if (q0 + m < n_out) buf[off[(m + HALO) & 7] + 8 * (m + HALO)] = x[m];
+        if (q0 + m < n_out) buf[off[(m + HALO) & 7] + 8 * (m + HALO)] = sg * x[m];
     }
     fence_proxy_async();
     __syncwarp();

@@ -138,7 +138,10 @@ struct SolverImpl : SolverState {
   DevBuf d_pp;                // device: pp2y[ny] | pp4y[ny] | ppy[ny]
   DevBuf dpd;                 // wall pressure gradients kept between gradp and pre_correc (navier.f90:439-496):
                               // x faces 4 x (ny,nzl) | y faces 4 x (nx,nzl) | z faces 4 x (nx,ny)
-  PreOp d1s[2];               // dery with the ppy multiply (istret /= 0), npaire 0 / 1
+  // operators whose store is an accumulation (DevOp::store_mode): t += op(u) for the sums of divergence
+  // (navier.f90:325,339) and t -= op(u) for cor_vel folded into the last pressure-gradient operators (:242-244,426-430)
+  PreOp ivp_y_add, dvp_z_add, dpv_x_sub, ipv_x_sub;
+  bool fuse_sums = true;      // X3D_FUSE_SUMS=0 restores the separate elementwise passes
   // fused momentum kernels (periodic directions): compressed tables of D1 / D2 per axis
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
@@ -284,6 +287,11 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
       S->fused[a] = build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]);
     }
   }
+  S->ivp_y_add = S->ivp[1]; S->ivp_y_add.op.store_mode = 1;
+  S->dvp_z_add = S->dvp[2]; S->dvp_z_add.op.store_mode = 1;
+  S->dpv_x_sub = S->dpv[0]; S->dpv_x_sub.op.store_mode = 2;
+  S->ipv_x_sub = S->ipv[0]; S->ipv_x_sub.op.store_mode = 2;
+  if (const char *e = getenv("X3D_FUSE_SUMS")) S->fuse_sums = atoi(e) != 0;
   x3d_poisson_params pp{};
   pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
   pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
@@ -633,10 +641,14 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   run(ctx, S.dvp[0], B(S.ux), pp1);    // :297
   run(ctx, S.ivp[0], B(S.uy), pgy1);   // :313
   run(ctx, S.ivp[0], B(S.uz), pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
-  run(ctx, S.ivp[1], pp1, upi2);       // :321
   run(ctx, S.dvp[1], pgy1, duy);       // :322
-  const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.nzl;
-  map(ctx, n2, [=] __device__(long long q) { duy[q] = duy[q] + upi2[q]; });  // :325
+  if (S.fuse_sums) {
+    run(ctx, S.ivp_y_add, pp1, duy);   // :321 + :325: duy += interyvp(pp1), accumulated by the operator's store
+  } else {
+    run(ctx, S.ivp[1], pp1, upi2);     // :321
+    const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.nzl;
+    map(ctx, n2, [=] __device__(long long q) { duy[q] = duy[q] + upi2[q]; });  // :325
+  }
   run(ctx, S.ivp[1], pgz1, upi2);      // :327
   const double *duy3 = duy, *uzp3 = upi2;
   if (S.nranks > 1) {  // :329-330, both fields between one pair of barriers
@@ -646,8 +658,12 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
     duy3 = t1; uzp3 = t2;
   }
   run(ctx, S.ivp[2], duy3, out);       // :333
-  run(ctx, S.dvp[2], uzp3, po3);       // :335
   const long long n3 = static_cast<long long>(S.n3);
+  if (nlock != 2 && S.fuse_sums) {
+    run(ctx, S.dvp_z_add, uzp3, out);  // :335 + :339: out += derzvp(uzp3)
+    return;
+  }
+  run(ctx, S.dvp[2], uzp3, po3);       // :335
   if (nlock == 2) {                    // :339-347 (each rank subtracts its own corner value)
     const long long ref = static_cast<long long>(S.nxm) * S.nyml * (S.nzm - 1);
     double *tmp = B(S.red_out) + 8;
@@ -658,6 +674,12 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   } else {
     map(ctx, n3, [=] __device__(long long q) { out[q] = out[q] + po3[q]; });
   }
+}
+
+// the wall-gradient capture of gradp needs px, py, pz: cor_vel is folded into the operators only without Dirichlet faces
+static bool fused_cor_vel(const SolverImpl &S) {
+  const auto &p = S.p;
+  return S.fuse_sums && p.nclx1 != 2 && p.nclxn != 2 && p.ncly1 != 2 && p.nclyn != 2 && p.nclz1 != 2 && p.nclzn != 2;
 }
 
 // navier.f90:386-431
@@ -676,6 +698,12 @@ static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
   run(ctx, S.ipv[1], pp2, ppi2);   // :413
   run(ctx, S.dpv[1], pp2, pgy2);   // :415
   run(ctx, S.ipv[1], pgz2, pgzi2); // :417  (transpose_y_to_x :422-424 is local)
+  if (fused_cor_vel(S)) {  // cor_vel (:242-244) folded in: u -= derxpv(ppi2), v -= interxpv(pgy2), w -= interxpv(pgzi2)
+    run(ctx, S.dpv_x_sub, ppi2, B(S.ux));
+    run(ctx, S.ipv_x_sub, pgy2, B(S.uy));
+    run(ctx, S.ipv_x_sub, pgzi2, B(S.uz));
+    return;
+  }
   run(ctx, S.dpv[0], ppi2, B(S.px));   // :426
   run(ctx, S.ipv[0], pgy2, B(S.py));   // :428
   run(ctx, S.ipv[0], pgzi2, B(S.pz));  // :430
@@ -728,9 +756,11 @@ void solver_step(Ctx &ctx, int nsteps) {
       divergence(ctx, S, B(S.pp3), 1);
       poisson_solve_device(ctx, B(S.pp3));
       gradp(ctx, S, B(S.pp3), itr);
-      double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
-      const double *px = B(S.px), *py = B(S.py), *pz = B(S.pz);
-      map(ctx, n, [=] __device__(long long q) { u[q] = u[q] - px[q]; v[q] = v[q] - py[q]; w[q] = w[q] - pz[q]; });  // cor_vel
+      if (!fused_cor_vel(S)) {
+        double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+        const double *px = B(S.px), *py = B(S.py), *pz = B(S.pz);
+        map(ctx, n, [=] __device__(long long q) { u[q] = u[q] - px[q]; v[q] = v[q] - py[q]; w[q] = w[q] - pz[q]; });  // cor_vel
+      }
     }
   }
 }
