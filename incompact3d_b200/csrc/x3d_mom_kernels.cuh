@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
       unsigned char *bufC = smem_raw + slot * slot_bytes;
       if (q < 2) { mbar_wait(full + slot, par); ghosts(bufC); }
       dd2 r[L];
-      {  // xnu * D2(c)
+      {  // xnu * D2(c) and - 1/2 a D1(c): both right-hand sides from one read of the window of c
         dd2 x[L];
         {
           dd2 win[NWIN];
@@ -264,31 +264,18 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
           for (int j = 0; j < NWIN; ++j) win[j] = acc.ld(bufC, j);
           X3D_UNROLL
           for (int m = 0; m < L; ++m) {
-            const dd2 v = rhs_interior<D2, NT2, NWIN, dd2>(op2, win, m);
+            const dd2 v2 = rhs_interior<D2, NT2, NWIN, dd2>(op2, win, m);
+            const dd2 v1 = rhs_interior<D1, 2, NWIN, dd2>(op1, win, m);
             const bool ok = live && q0 + m < n;
-            x[m].x = ok ? v.x : 0.0;
-            x[m].y = ok ? v.y : 0.0;
+            r[m].x = ok ? v2.x : 0.0;
+            r[m].y = ok ? v2.y : 0.0;
+            x[m].x = ok ? v1.x : 0.0;
+            x[m].y = ok ? v1.y : 0.0;
           }
         }
-        pair_solve_periodic<L>(x, s2, w2, b2, scan2, lane, nc, live, op2.alpha, q0, n);
+        pair_solve_periodic<L>(r, s2, w2, b2, scan2, lane, nc, live, op2.alpha, q0, n);
         X3D_UNROLL
-        for (int m = 0; m < L; ++m) r[m] = xnu * x[m];
-      }
-      __syncwarp();  // also keeps the compiler from hoisting the next section's shared-memory loads (register pressure)
-      {  // - 1/2 a D1(c)
-        dd2 x[L];
-        {
-          dd2 win[NWIN];
-          X3D_UNROLL
-          for (int j = 0; j < NWIN; ++j) win[j] = acc.ld(bufC, j);
-          X3D_UNROLL
-          for (int m = 0; m < L; ++m) {
-            const dd2 v = rhs_interior<D1, 2, NWIN, dd2>(op1, win, m);
-            const bool ok = live && q0 + m < n;
-            x[m].x = ok ? v.x : 0.0;
-            x[m].y = ok ? v.y : 0.0;
-          }
-        }
+        for (int m = 0; m < L; ++m) r[m] = xnu * r[m];
         pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, q0, n);
         X3D_UNROLL
         for (int m = 0; m < L; ++m) {
