@@ -236,6 +236,13 @@ int x3do_solver_capture_wall_gradients(void *sv, int itr, const double *gdt3, co
     return 0;
   } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+// lagpolx / lagpoly / lagpolz (src/ibm.f90:83-343) on caller data; coords may be NULL for uniform directions
+void x3do_lagpol(double *u, int nx, int ny, int nz, int axis, int nobjmax, int npif, int izap, const int *nobj, const double *xi,
+                 const double *xf, const int *nipif, const int *nfpif, const double *coords, double d, double len) {
+  IbmGeom g;
+  g.nobjmax = nobjmax; g.npif = npif; g.izap = izap; g.nobj = nobj; g.xi = xi; g.xf = xf; g.nipif = nipif; g.nfpif = nfpif;
+  lagpol(u, nx, ny, nz, axis, g, coords, d, len);
+}
 void x3do_channel_cfr(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant) {
   channel_cfr_apply(u, nx, ny, nz, ppy, dy, yly, constant);
 }

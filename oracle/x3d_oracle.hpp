@@ -157,6 +157,15 @@ struct Solver {
   double *W(int i, size_t n);
 };
 
+// ---- ibm.f90: Lagrange reconstruction inside the bodies (iibm = 2) ---------------------------------------
+struct IbmGeom {           // module complex_geometry for one direction (src/module_param.f90:546-556)
+  int nobjmax = 0, npif = 2, izap = 1;
+  const int *nobj = nullptr;     // (na, nb)
+  const double *xi = nullptr, *xf = nullptr;   // (nobjmax, na, nb)
+  const int *nipif = nullptr, *nfpif = nullptr;  // (0:nobjmax, na, nb)
+};
+void lagpol(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len);
+
 void channel_cfr_apply(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant);
 
 }  // namespace x3do

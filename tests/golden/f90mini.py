@@ -233,9 +233,14 @@ class Transpiler:
         arrays = set(extra_arrays) | self.arrays_hint
         body = []
         local_arrays = []
+        int_scalars = set()
         for ln in lines[1:]:
             if re.match(r"(integer|real|complex|logical|character|type)\b", ln) and "::" in ln:
                 decl, names = ln.split("::", 1)
+                if decl.strip().startswith("integer") and "dimension" not in decl and "parameter" not in decl:
+                    for item in _split_args(names):
+                        if "(" not in item and "=" not in item:
+                            int_scalars.add(item.strip())
                 dim = re.search(r"dimension\s*\(", decl)
                 dimspec = None
                 if dim:
@@ -297,6 +302,12 @@ class Transpiler:
                     nm = item[:k0].strip()
                     dims = [self.expr(d, arrays, True) for d in _split_args(item[k0 + 1:_match_paren(item, k0)])]
                     emit(f"{nm} = farr(({', '.join(dims)},))")
+                return
+            m = re.match(r"do\s+while\s*\((.*)\)$", ln)
+            if m:
+                emit(f"while {self.expr(m.group(1), arrays)}:")
+                ind += 1
+                emit("pass")
                 return
             m = re.match(r"do\s+(\w+)\s*=\s*(.*)$", ln)
             if m:
@@ -362,6 +373,8 @@ class Transpiler:
                 emit(f"{lhs}.a[...] = {rhs}.a")
             elif lhs in arrays:
                 emit(f"{lhs}[...] = {r}")
+            elif lhs in int_scalars and ("/" in rhs or "." in rhs):
+                emit(f"{lhs} = _fint({r})")   # real -> integer assignment truncates (Fortran)
             else:
                 emit(f"{self.expr(lhs, arrays)} = {r}")
 
@@ -390,6 +403,10 @@ def _frange(lo, hi, st):
     return range(lo, hi + (1 if st > 0 else -1), st)
 
 
+def _fint(x):
+    return x.astype(int) if isinstance(x, np.ndarray) else int(x)
+
+
 def _real(x, *a):
     if isinstance(x, complex) or (isinstance(x, np.ndarray) and np.iscomplexobj(x)):
         return x.real
@@ -397,7 +414,7 @@ def _real(x, *a):
 
 
 def base_namespace():
-    ns = {"ALL": ALL, "np": np, "farr": farr, "FArr": FArr, "_frange": _frange, "_real": _real,
+    ns = {"ALL": ALL, "np": np, "farr": farr, "FArr": FArr, "_frange": _frange, "_real": _real, "_fint": _fint,
           "sin": np.sin, "cos": np.cos, "tan": np.tan, "exp": np.exp, "sqrt": np.sqrt,
           "abs": np.abs, "atan": np.arctan, "acos": np.arccos, "asin": np.arcsin,
           "log": np.log, "sinh": np.sinh, "cosh": np.cosh, "tanh": np.tanh,
