@@ -91,6 +91,21 @@ int x3d_set_stretching(x3d_ctx *ctx, int ny, const double *yp, const double *ypi
                        const double *ppy, const double *pp2y, const double *pp4y,
                        const double *ppyi, const double *pp2yi, const double *pp4yi);
 
+/* ---- immersed-boundary pre-pass (iibm = 2) ------------------------------
+ * When iibm = 2 every derx/dery/derz and derxx/deryy/derzz first rebuilds its INPUT inside the solid bodies by
+ * Lagrange interpolation (lagpolx/y/z + polint, src/ibm.f90:83-389; call sites src/derive.f90:23,84,157,...).
+ * The geometry is module complex_geometry (src/module_param.f90:546-556), filled by genepsi3d on the host:
+ *   nobj(na,nb), xi/xf(nobjmax,na,nb), nipif/nfpif(0:nobjmax,na,nb) with (na,nb) = (ny,nz) for x lines,
+ *   (nx,nz) for y lines, (nx,ny) for z lines -- local pencil extents; npif, izap from module param;
+ *   d = mesh step, len = domain length; coords = yp(ncoords = ny) for axis 1 (NULL, 0 on the uniform axes).    */
+int x3d_set_ibm_geometry(x3d_ctx *ctx, int axis, int nobjmax, int npif, int izap, int na, int nb, const int *nobj,
+                         const double *xi, const double *xf, const int *nipif, const int *nfpif, const double *coords,
+                         int ncoords, double d, double len);
+/* lagpolx(u) / lagpoly(u) / lagpolz(u), src/ibm.f90:83,168,260: u (host or device) is modified in place */
+int x3d_lagpolx(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz);
+int x3d_lagpoly(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz);
+int x3d_lagpolz(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz);
+
 /* ---- compact operators ------------------------------------------------
  * abstract interfaces DERIVATIVE_X/Y/Z, src/module_param.f90:136-167 and
  * FILTER_X/Y/Z :203-226.  t is output; u input; r,s caller scratch (ignored:

@@ -275,6 +275,43 @@ def _solver_init_tgv(self):
     self._check(fn(self._h))
 
 
+def _set_ibm_geometry(self, axis, nobjmax, npif, izap, nobj, xi, xf, nipif, nfpif, d, length, coords=None):
+    """module complex_geometry of one direction (src/module_param.f90:546-556): nobj(na,nb), xi/xf(nobjmax,na,nb),
+    nipif/nfpif(0:nobjmax,na,nb), Fortran order; coords = yp for axis 1"""
+    keep = []
+
+    def iarr(a):
+        a = np.asfortranarray(a, dtype=np.int32)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int))
+
+    def darr(a):
+        a = np.asfortranarray(a, dtype=np.float64)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+    nobj = np.asarray(nobj)
+    na, nb = nobj.shape
+    fn = self._L.x3d_set_ibm_geometry
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    fn.argtypes = [C.c_void_p] + [C.c_int] * 6 + [ip, dp, dp, ip, ip, dp, C.c_int, C.c_double, C.c_double]
+    cptr = darr(coords) if coords is not None else None
+    self._check(fn(self._h, int(axis), int(nobjmax), int(npif), int(izap), int(na), int(nb), iarr(nobj), darr(xi), darr(xf),
+                   iarr(nipif), iarr(nfpif), cptr, 0 if coords is None else len(coords), float(d), float(length)))
+
+
+def _make_lagpol(ax):
+    def f(self, u, nx=None, ny=None, nz=None):
+        keep = []
+        shape = list(u.shape) if isinstance(u, np.ndarray) else list(reversed(u.shape))
+        n = [C.c_int(int(v)) for v in (shape if nx is None else (nx, ny, nz))]
+        fn = getattr(self._L, "x3d_lagpol" + ax)
+        fn.argtypes = [C.c_void_p, C.c_void_p] + [C.POINTER(C.c_int)] * 3
+        self._check(fn(self._h, _addr(u, keep), *[C.byref(v) for v in n]))
+    f.__name__ = "lagpol" + ax
+    f.__doc__ = f"reference procedure `lagpol{ax}(u)` (src/ibm.f90): u is rebuilt inside the bodies, in place"
+    return f
+
+
 def _solver_init_channel(self):
     fn = self._L.x3d_solver_init_channel
     fn.argtypes = [C.c_void_p]
@@ -348,6 +385,9 @@ for _n in ("transpose_x_to_y", "transpose_y_to_z", "transpose_z_to_y", "transpos
 X3D.solver_init = _solver_init
 X3D.solver_init_tgv = _solver_init_tgv
 X3D.solver_init_channel = _solver_init_channel
+X3D.set_ibm_geometry = _set_ibm_geometry
+for _ax in "xyz":
+    setattr(X3D, "lagpol" + _ax, _make_lagpol(_ax))
 X3D.solver_step = _solver_step
 X3D.solver_diagnostics_tgv = _solver_diag
 X3D.solver_divergence = _solver_divergence

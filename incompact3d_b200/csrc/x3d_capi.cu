@@ -12,6 +12,9 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p);
 void poisson_solve_device(Ctx &ctx, double *d_rhs);
 void poisson_dims(Ctx &ctx, int d[3]);
 void solver_init(Ctx &ctx, const x3d_solver_params &p);
+void set_ibm_geometry(Ctx &ctx, int axis, int nobjmax, int npif, int izap, int na, int nb, const int *nobj, const double *xi,
+                      const double *xf, const int *nipif, const int *nfpif, const double *coords, int ncoords, double d, double len);
+void lagpol(Ctx &ctx, int axis, double *u, int nx, int ny, int nz);
 void solver_init_tgv(Ctx &ctx);
 void solver_init_channel(Ctx &ctx);
 void solver_step(Ctx &ctx, int nsteps);
@@ -120,10 +123,17 @@ int x3d_set_stretching(x3d_ctx *ctx, int ny, const double *yp, const double *ypi
     c.st_ppyi.assign(ppyi, ppyi + ny); c.st_pp2yi.assign(pp2yi, pp2yi + ny); c.st_pp4yi.assign(pp4yi, pp4yi + ny);
   });
 }
+int x3d_set_ibm_geometry(x3d_ctx *ctx, int axis, int nobjmax, int npif, int izap, int na, int nb, const int *nobj, const double *xi,
+                         const double *xf, const int *nipif, const int *nfpif, const double *coords, int ncoords, double d, double len) {
+  return guard([&] { set_ibm_geometry(ctx->c, axis, nobjmax, npif, izap, na, nb, nobj, xi, xf, nipif, nfpif, coords, ncoords, d, len); });
+}
+int x3d_lagpolx(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz) { return guard([&] { lagpol(ctx->c, 0, u, *nx, *ny, *nz); }); }
+int x3d_lagpoly(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz) { return guard([&] { lagpol(ctx->c, 1, u, *nx, *ny, *nz); }); }
+int x3d_lagpolz(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz) { return guard([&] { lagpol(ctx->c, 2, u, *nx, *ny, *nz); }); }
 int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit, int nclx, int ncly, int nclz) {
   return guard([&] {
-    if (iibm == 2 || iibm == 3)
-      throw Error("iibm=2/3 (lagpol/cubspl pre-pass inside the operators, src/derive.f90:23-24) is not implemented");
+    if (iibm == 3)
+      throw Error("iibm=3 (cubic-spline pre-pass cubsplx/y/z inside the operators, src/derive.f90:24) is not implemented");
     ctx->c.iibm = iibm; ctx->c.istret = istret; ctx->c.iimplicit = iimplicit;
     ctx->c.ncl[0] = nclx != 0; ctx->c.ncl[1] = ncly != 0; ctx->c.ncl[2] = nclz != 0;
   });

@@ -56,6 +56,14 @@ struct Ctx {
   bool ncl[3] = {true, true, true};
   // stretched-mesh metrics of the host's stretching() (x3d_set_stretching); empty when istret == 0
   std::vector<double> st_yp, st_ypi, st_ppy, st_pp2y, st_pp4y, st_ppyi, st_pp2yi, st_pp4yi;
+  // immersed-boundary geometry per direction (x3d_set_ibm_geometry); device copies
+  struct IbmAxis {
+    bool set = false;
+    int nobjmax = 0, npif = 2, izap = 1, na = 0, nb = 0, ncoords = 0;
+    double d = 0.0, len = 0.0;
+    DevBuf nobj, xi, xf, nipif, nfpif, coords;
+  };
+  IbmAxis ibm[3];
   // optional per-launch CUDA-event timing (x3d_profile_begin / x3d_profile_end)
   bool profiling = false;
   std::vector<ProfRec> prof;
@@ -101,5 +109,7 @@ const TriTable &get_tri(Ctx &ctx, const double *f, const double *s, const double
 void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double *d_u, double *d_t);
 // full operator call with host-or-device pointers
 void run_op(Ctx &ctx, OpCall &call, const double *u, double *t);
+// lagpolx/y/z on a device array (nx,ny,nz), in place
+void lagpol_device(Ctx &ctx, int axis, double *d_u, int nx, int ny, int nz);
 
 }  // namespace x3d

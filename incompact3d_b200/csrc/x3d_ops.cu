@@ -165,6 +165,12 @@ void run_op(Ctx &ctx, OpCall &call, const double *u, double *t) {
       done = true;
     }
   }
+  // iibm = 2: the collocated derivatives first rebuild their input inside the bodies, in place (derive.f90:23)
+  bool u_modified = false;
+  if (!done && ctx.iibm == 2 && (call.kind == D1 || call.kind == D2)) {
+    lagpol_device(ctx, call.axis, const_cast<double *>(d_u), call.dims_in[0], call.dims_in[1], call.dims_in[2]);
+    u_modified = true;
+  }
   if (!done) {
     DevOp op;
     build_devop(ctx, call, op);
@@ -194,6 +200,8 @@ void run_op(Ctx &ctx, OpCall &call, const double *u, double *t) {
   } else {
     t_needs_upload = true;
   }
+  if (u_modified && !u_dev)  // the reference modifies the caller's array: hand the rebuilt input back
+    X3D_CUDA(cudaMemcpyAsync(const_cast<double *>(u), d_u, cnt_in * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   if (!t_dev && t_needs_upload) {
     X3D_CUDA(cudaMemcpyAsync(t, d_t, cnt_out * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
     X3D_CUDA(cudaStreamSynchronize(ctx.stream));
