@@ -274,7 +274,7 @@ typedef struct x3d_solver_params {
   int nclx1, nclxn, ncly1, nclyn, nclz1, nclzn;
   double xlx, yly, zlz;
   double re, dt;
-  int ifirstder, isecondder, ipinter, itimescheme; /* 5 = RK3 */
+  int ifirstder, isecondder, ipinter, itimescheme; /* 1 Euler, 2 AB2, 3 AB3, 5 RK3 (src/variables.f90:1340-1399) */
   int istret; double beta;
   double nu0nu, cnu;
   int p_row, p_col;

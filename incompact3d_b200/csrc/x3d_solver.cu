@@ -115,7 +115,7 @@ struct SolverImpl : SolverState {
   x3d_solver_params p{};
   AxisCoeffs A[3];
   int nxm = 0, nym = 0, nzm = 0;
-  double xnu = 0, adt[3]{}, bdt[3]{}, gdt[3]{};
+  double xnu = 0, adt[3]{}, bdt[3]{}, cdt[3]{}, gdt[3]{};
   int iadvance = 1, ntime = 1;
   long long itime = 0;
   size_t n = 0, n3 = 0;       // local x-pencil points, local pressure z-pencil points
@@ -126,7 +126,7 @@ struct SolverImpl : SolverState {
   int nyl = 0, y0 = 0;        // local y extent / offset of the velocity z-pencil
   int nyml = 0;               // local y extent of the pressure z-pencils
   // fields
-  DevBuf ux, uy, uz, px, py, pz, pp3, dux[2], duy[2], duz[2];
+  DevBuf ux, uy, uz, px, py, pz, pp3, dux[3], duy[3], duz[3];
   DevBuf w[16];
   DevBuf red_partial, red_out;
   double *h_red = nullptr;  // pinned
@@ -218,8 +218,14 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
     S->adt[2] = (3.0 / 4.0) * dt; S->bdt[2] = (-5.0 / 12.0) * dt; S->gdt[2] = S->adt[2] + S->bdt[2];
   } else if (p.itimescheme == 1) {
     S->iadvance = 1; S->ntime = 1; S->adt[0] = dt; S->gdt[0] = dt;
+  } else if (p.itimescheme == 2) {  // AB2, variables.f90:1355-1363
+    S->iadvance = 1; S->ntime = 2; S->adt[0] = 1.5 * dt; S->bdt[0] = -0.5 * dt; S->gdt[0] = S->adt[0] + S->bdt[0];
+  } else if (p.itimescheme == 3) {  // AB3, :1364-1374
+    S->iadvance = 1; S->ntime = 3;
+    S->adt[0] = (23.0 / 12.0) * dt; S->bdt[0] = -(16.0 / 12.0) * dt; S->cdt[0] = (5.0 / 12.0) * dt;
+    S->gdt[0] = S->adt[0] + S->bdt[0] + S->cdt[0];
   } else {
-    throw Error("x3d_solver_init: itimescheme 1 (Euler) and 5 (RK3) are implemented");
+    throw Error("x3d_solver_init: itimescheme 1 (Euler), 2 (AB2), 3 (AB3) and 5 (RK3) are implemented");
   }
   // local extents (xcompact3d.f90:191-201: main decomposition, ph3 = (nxm,nym,nz), ph1 = (nxm,nym,nzm))
   S->id_v = 0;
@@ -512,6 +518,30 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *rhs[3][3]) {
   }
 }
 
+// Adams-Bashforth 2 / 3 (time_integrators.f90:75-100) for the three components; rhs(q, c) is the current right-hand
+// side of component c.  First step Euler, second step of AB3 is AB2; the stored right-hand sides shift afterwards.
+template <class F>
+static void adams_bashforth(Ctx &ctx, SolverImpl &S, F rhs) {
+  const long long n = static_cast<long long>(S.n);
+  double *fld[3] = {B(S.ux), B(S.uy), B(S.uz)};
+  double *h2[3] = {B(S.dux[1]), B(S.duy[1]), B(S.duz[1])};
+  double *h3[3] = {S.ntime > 2 ? B(S.dux[2]) : nullptr, S.ntime > 2 ? B(S.duy[2]) : nullptr, S.ntime > 2 ? B(S.duz[2]) : nullptr};
+  const double dt = S.p.dt, a = S.adt[0], b = S.bdt[0], c3 = S.cdt[0], g = S.gdt[0];
+  const bool ab3 = S.p.itimescheme == 3;
+  const int mode = S.itime == 1 ? 0 : ((ab3 && S.itime == 2) ? 1 : (ab3 ? 3 : 2));   // 0 Euler, 1 AB2 start of AB3, 2 AB2, 3 AB3
+  for (int c = 0; c < 3; ++c) {
+    double *u = fld[c], *d2 = h2[c], *d3 = h3[c];
+    map(ctx, n, [=] __device__(long long q) {
+      const double x = rhs(q, c);
+      if (mode == 0) u[q] = (ab3 ? dt : g) * x + u[q];
+      else if (mode == 1) { u[q] = 1.5 * dt * x - 0.5 * dt * d2[q] + u[q]; d3[q] = d2[q]; }
+      else if (mode == 2) u[q] = a * x + b * d2[q] + u[q];
+      else { u[q] = a * x + b * d2[q] + c3 * d3[q] + u[q]; d3[q] = d2[q]; }
+      d2[q] = x;
+    });
+  }
+}
+
 // intt for the fused form: dux1 = r_x + r_y + r_z formed on the fly
 static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *rhs[3][3]) {
   const long long n = static_cast<long long>(S.n);
@@ -526,6 +556,12 @@ static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *rhs[3][3]) {
     return;
   }
   double *a2 = B(S.dux[1]), *b2 = B(S.duy[1]), *c2 = B(S.duz[1]);
+  if (S.p.itimescheme == 2 || S.p.itimescheme == 3) {
+    adams_bashforth(ctx, S, [=] __device__(long long q, int c) {
+      return c == 0 ? (z0[q] + y0[q]) + x0[q] : (c == 1 ? (z1[q] + y1[q]) + x1[q] : (z2[q] + y2[q]) + x2[q]);
+    });
+    return;
+  }
   if (itr == 1) {
     const double g = S.gdt[0];
     map(ctx, n, [=] __device__(long long q) {
@@ -562,6 +598,10 @@ static void intt3(Ctx &ctx, SolverImpl &S, int itr) {
     return;
   }
   double *a2 = B(S.dux[1]), *b2 = B(S.duy[1]), *c2 = B(S.duz[1]);
+  if (S.p.itimescheme == 2 || S.p.itimescheme == 3) {
+    adams_bashforth(ctx, S, [=] __device__(long long q, int c) { return c == 0 ? a1[q] : (c == 1 ? b1[q] : c1[q]); });
+    return;
+  }
   if (itr == 1) {
     const double g = S.gdt[0];
     map(ctx, n, [=] __device__(long long q) {

@@ -227,6 +227,25 @@ int x3do_solver_pre_correc(void *sv, int itr, const double *gdt3) {
     return 0;
   } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+// one call of intt (src/time_integrators.f90:20-190) on caller data: var[n], dvar[n * ntime] (Fortran dvar1(:,:,:,q) blocks)
+int x3do_solver_intt(void *sv, long long itime, int itr, long long n, double *var, double *dvar) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    s->itime = itime; s->itr = itr;
+    std::vector<double> v(var, var + n), d[3];
+    for (int q = 0; q < s->ntime; ++q) d[q].assign(dvar + q * n, dvar + (q + 1) * n);
+    s->intt(v, d);
+    std::memcpy(var, v.data(), n * 8);
+    for (int q = 0; q < s->ntime; ++q) std::memcpy(dvar + q * n, d[q].data(), n * 8);
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// adt, bdt, cdt, gdt (3 each), then ntime and iadvance_time (src/variables.f90:1340-1423)
+void x3do_solver_time_coefficients(void *sv, double *out14) {
+  auto *s = static_cast<Solver *>(sv);
+  for (int q = 0; q < 3; ++q) { out14[q] = s->adt[q]; out14[3 + q] = s->bdt[q]; out14[6 + q] = s->cdt[q]; out14[9 + q] = s->gdt[q]; }
+  out14[12] = s->ntime; out14[13] = s->iadvance_time;
+}
 int x3do_solver_capture_wall_gradients(void *sv, int itr, const double *gdt3, const double *px, const double *py, const double *pz) {
   try {
     auto *s = static_cast<Solver *>(sv);

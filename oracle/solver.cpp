@@ -54,8 +54,14 @@ void Solver::init() {
     ntime = 2;
   } else if (p.itimescheme == 1) {  // Euler, variables.f90:1343-1349
     iadvance_time = 1; adt[0] = dt; bdt[0] = 0.0; gdt[0] = adt[0] + bdt[0]; ntime = 1;
+  } else if (p.itimescheme == 2) {  // AB2, :1355-1363
+    iadvance_time = 1; adt[0] = 1.5 * dt; bdt[0] = -0.5 * dt; gdt[0] = adt[0] + bdt[0]; ntime = 2;
+  } else if (p.itimescheme == 3) {  // AB3, :1364-1374
+    iadvance_time = 1;
+    adt[0] = (23.0 / 12.0) * dt; bdt[0] = -(16.0 / 12.0) * dt; cdt[0] = (5.0 / 12.0) * dt;
+    gdt[0] = adt[0] + bdt[0] + cdt[0]; ntime = 3;
   } else {
-    throw std::runtime_error("oracle solver: itimescheme 1 (Euler) and 5 (RK3) are restated");
+    throw std::runtime_error("oracle solver: itimescheme 1 (Euler), 2 (AB2), 3 (AB3) and 5 (RK3) are restated");
   }
   po.init(X, Y, Z, p.istret ? &st : nullptr);
   const size_t n = static_cast<size_t>(p.nx) * p.ny * p.nz;
@@ -211,6 +217,35 @@ void Solver::intt(std::vector<double> &var, std::vector<double> *dvar) {
     const double g = gdt[itr - 1];
 #pragma omp parallel for schedule(static)
     for (size_t q = 0; q < n; ++q) v[q] = g * d1[q] + v[q];
+    return;
+  }
+  if (p.itimescheme == 2) {  // time_integrators.f90:75-84
+    double *d2 = dvar[1].data();
+    const double g = gdt[itr - 1], a = adt[itr - 1], b = bdt[itr - 1];
+    if (itime == 1) {
+#pragma omp parallel for schedule(static)
+      for (size_t q = 0; q < n; ++q) v[q] = g * d1[q] + v[q];
+    } else {
+#pragma omp parallel for schedule(static)
+      for (size_t q = 0; q < n; ++q) v[q] = a * d1[q] + b * d2[q] + v[q];
+    }
+    for (size_t q = 0; q < n; ++q) d2[q] = d1[q];
+    return;
+  }
+  if (p.itimescheme == 3) {  // :85-100
+    double *d2 = dvar[1].data(), *d3 = dvar[2].data();
+    const double dt = p.dt, a = adt[itr - 1], b = bdt[itr - 1], c = cdt[itr - 1];
+    if (itime == 1) {
+#pragma omp parallel for schedule(static)
+      for (size_t q = 0; q < n; ++q) v[q] = dt * d1[q] + v[q];
+    } else if (itime == 2) {
+#pragma omp parallel for schedule(static)
+      for (size_t q = 0; q < n; ++q) { v[q] = 1.5 * dt * d1[q] - 0.5 * dt * d2[q] + v[q]; d3[q] = d2[q]; }
+    } else {
+#pragma omp parallel for schedule(static)
+      for (size_t q = 0; q < n; ++q) { v[q] = a * d1[q] + b * d2[q] + c * d3[q] + v[q]; d3[q] = d2[q]; }
+    }
+    for (size_t q = 0; q < n; ++q) d2[q] = d1[q];
     return;
   }
   double *d2 = dvar[1].data();

@@ -132,7 +132,7 @@ struct Solver {
   Poisson po;
   int nxm, nym, nzm;
   double xnu;
-  double adt[5]{}, bdt[5]{}, gdt[5]{};
+  double adt[5]{}, bdt[5]{}, cdt[5]{}, gdt[5]{};
   int iadvance_time = 1, ntime = 1;
   int itime = 0, itr = 1;
   std::vector<double> ux, uy, uz, px, py, pz, pp3;

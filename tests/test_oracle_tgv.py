@@ -46,3 +46,20 @@ def test_tgv_65_matches_reference_golden(golden_dir):
         assert abs(tmax.value) < 1e-11 and tmoy.value < 1e-12  # DIV U max / mean at machine level
     print("worst relative deviation from the reference golden file:", worst)
     L.x3do_solver_destroy(s)
+
+
+def test_adams_bashforth_consistent_with_rk3():
+    """AB2 / AB3 (time_integrators.f90:75-100) are restated without golden data: check them against the pinned RK3
+    path - same flow, small time step, the kinetic-energy histories agree to the schemes' truncation error."""
+    out = {}
+    for scheme in (2, 3, 5):
+        L, s = make_solver(n=33, dt=0.001, itimescheme=scheme)
+        L.x3do_solver_init_tgv(s)
+        assert L.x3do_solver_step(s, 12) == 0
+        d = (C.c_double * 4)()
+        L.x3do_solver_postprocess_tgv(s, d)
+        out[scheme] = np.array(d[:])
+        L.x3do_solver_destroy(s)
+    assert np.abs(out[3] / out[5] - 1).max() < 2e-6, out
+    assert np.abs(out[2] / out[5] - 1).max() < 2e-5, out
+    assert not np.array_equal(out[2], out[3])

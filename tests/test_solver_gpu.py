@@ -41,13 +41,25 @@ def test_tgv_65_free_slip_matches_reference_golden(golden_dir):
                                     # line lengths for which the fused momentum kernels run (y: L=9, z: L=17; ragged lane blocks)
                                     ((40, 168, 304), (0,) * 6), ((24, 304, 176), (0,) * 6), ((170, 176, 168), (0,) * 6)])
 def test_solver_matches_oracle(nn, ncl):
+    _solver_vs_oracle(nn, ncl, 5, 3)
+
+
+# Euler / AB2 / AB3 (time_integrators.f90:71-100, variables.f90:1343-1374): four steps so that AB3 passes through
+# its Euler and AB2 start-up steps; unfused and fused momentum paths
+@pytest.mark.parametrize("scheme", [1, 2, 3])
+@pytest.mark.parametrize("nn,ncl", [((48, 40, 56), (0,) * 6), ((33, 33, 40), (1, 1, 1, 1, 0, 0)), ((24, 304, 176), (0,) * 6)])
+def test_adams_bashforth_matches_oracle(nn, ncl, scheme):
+    _solver_vs_oracle(nn, ncl, scheme, 4)
+
+
+def _solver_vs_oracle(nn, ncl, scheme, nsteps):
     from incompact3d_b200 import X3D
     length = 2 * np.pi
     L = ol.lib()
-    Ls, s = make_solver(n=nn, ncl=ncl, length=length, re=1600.0, dt=0.002)
+    Ls, s = make_solver(n=nn, ncl=ncl, length=length, re=1600.0, dt=0.002, itimescheme=scheme)
     Ls.x3do_solver_init_tgv(s)
     x = X3D(0)
-    x.solver_init(*nn, ncl=ncl, xlx=length, yly=length, zlz=length, re=1600.0, dt=0.002)
+    x.solver_init(*nn, ncl=ncl, xlx=length, yly=length, zlz=length, re=1600.0, dt=0.002, itimescheme=scheme)
     x.solver_init_tgv()
     n = nn[0] * nn[1] * nn[2]
     # perturb the TGV field so that all velocity components and all operators are exercised
@@ -59,7 +71,7 @@ def test_solver_matches_oracle(nn, ncl):
     x.solver_set_velocity(ux, uy, uz)
     dp = C.POINTER(C.c_double)
     Ls.x3do_solver_set_velocity(s, ux.ctypes.data_as(dp), uy.ctypes.data_as(dp), uz.ctypes.data_as(dp))
-    for it in range(3):
+    for it in range(nsteps):
         x.solver_step(1)
         assert Ls.x3do_solver_step(s, 1) == 0
         gu, gv, gw = x.solver_get_velocity()
