@@ -34,6 +34,11 @@ bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M) {
   for (int c = H; c <= nc - H - 2; ++c)
     for (int m = 0; m < L; ++m)
       if (std::fabs(R(c * L + m, T_RS)) > 1e-18 * rsmax) return false;
+  // constant super-diagonal: fw(i) = ff w(i) for every row but the last
+  const double ff = R(1, T_FW) / R(1, T_W);
+  for (int i = 0; i < T.n - 1; ++i)
+    if (std::fabs(R(i, T_FW) - ff * R(i, T_W)) > 4e-16 * std::fabs(R(i, T_FW))) return false;
+  M.ff = ff;
   std::vector<double> h(static_cast<size_t>(3) * MOM_TABS * L * 2, 0.0);
   for (int t = 0; t < MOM_TABS; ++t) {
     const int c = t < H ? t : (t == H ? H : nc - H - 1 + (t - H - 1));
@@ -106,7 +111,7 @@ bool mom_pair_eligible(int n, int L) {
 // out[0..2] = xnu D2(c) - 1/2 (D1(c a) + a D1(c)) along this axis, a = f[axis]
 void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
                      const double *const f[3], double *const out[3], long long n1, int nline, long long nouter, long long sline,
-                     long long souter) {
+                     long long souter, bool add) {
   MomGeom g{};
   size_t smem = 0;
   if (!M1.ok || !M2.ok || M1.L != M2.L || !mom_pair_plan(nline, M1.L, g, smem)) throw Error("fused momentum kernel: ineligible call");
@@ -114,13 +119,14 @@ void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, con
   g.npos = static_cast<long long>(g.nbx) * nouter;
   g.ia = axis; g.ic1 = (axis + 1) % 3; g.ic2 = (axis + 2) % 3;
   g.xnu = xnu;
+  g.add = add ? 1 : 0;
   MomMaps maps;
   for (int q = 0; q < 3; ++q) {
     maps.in[q] = make_line_map(f[q], n1, nline, nouter, sline, souter, 16, g.br, true);
     maps.halo[q] = make_line_map(f[q], n1, nline, nouter, sline, souter, 16, 8, true);
     maps.out[q] = make_line_map(out[q], n1, nline, nouter, sline, souter, 16, g.br, true);
   }
-  MomTabs tb{reinterpret_cast<const double2 *>(M1.d_c), reinterpret_cast<const double2 *>(M2.d_c), M1.d_scan, M2.d_scan};
+  MomTabs tb{reinterpret_cast<const double2 *>(M1.d_c), reinterpret_cast<const double2 *>(M2.d_c), M1.d_scan, M2.d_scan, M1.ff, M2.ff};
   const bool nt4 = op2.c[2] != 0.0 || op2.c[3] != 0.0;
   auto launch = [&](auto kern) {
     X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -137,7 +143,7 @@ void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, con
 
 // x lines: fields are (n, nlines) arrays with contiguous lines
 void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
-                  const double *const f[3], double *const out[3], int n, long long nlines) {
+                  const double *const f[3], double *const out[3], int n, long long nlines, bool add) {
   MomGeom g{};
   size_t smem = 0;
   if (!M1.ok || !M2.ok || M1.L != M2.L || !mom_x_plan(n, M1.L, g, smem)) throw Error("fused x momentum kernel: ineligible call");
@@ -150,8 +156,9 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
   g.nbx = 1;
   g.ia = 0; g.ic1 = 1; g.ic2 = 2;
   g.xnu = xnu;
+  g.add = add ? 1 : 0;
   MomMaps maps{};
-  MomTabs tb{reinterpret_cast<const double2 *>(M1.d_c), reinterpret_cast<const double2 *>(M2.d_c), M1.d_scan, M2.d_scan};
+  MomTabs tb{reinterpret_cast<const double2 *>(M1.d_c), reinterpret_cast<const double2 *>(M2.d_c), M1.d_scan, M2.d_scan, M1.ff, M2.ff};
   const bool nt4 = op2.c[2] != 0.0 || op2.c[3] != 0.0;
   auto launch = [&](auto kern) {
     X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -8,18 +8,19 @@ struct MomTable {        // compressed coefficient table of one periodic operato
   double *d_c = nullptr;     // [3][MOM_TABS][L] double2
   double *d_scan = nullptr;  // [10][32]
   int L = 0, nc = 0;
+  double ff = 0.0;           // constant super-diagonal of the periodic operator
   bool ok = false;
   ~MomTable();
 };
 bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M);
-// y / z lines: out[c] = xnu D2(f[c]) - 1/2 (D1(f[c] f[axis]) + f[axis] D1(f[c]))
+// y / z lines: out[c] (+)= xnu D2(f[c]) - 1/2 (D1(f[c] f[axis]) + f[axis] D1(f[c]))
 void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
                      const double *const f[3], double *const out[3], long long n1, int nline, long long nouter, long long sline,
-                     long long souter);
+                     long long souter, bool add = false);
 bool mom_pair_eligible(int n, int L);
 // x lines (contiguous): f / out are (n, nlines) arrays
 void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
-                  const double *const f[3], double *const out[3], int n, long long nlines);
+                  const double *const f[3], double *const out[3], int n, long long nlines, bool add = false);
 bool mom_x_eligible(int n, int L);
 
 }  // namespace x3d

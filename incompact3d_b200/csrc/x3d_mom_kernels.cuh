@@ -38,10 +38,12 @@ struct MomGeom {
   int nc;               // chunks per line
   int ia, ic1, ic2;     // field index of the advecting velocity and of the two other components
   double xnu;
+  int add;              // 0: out = r, 1: out += r (TMA reduce-add stores)
 };
 struct MomTabs {        // device: [3][mom_tabs(L) L] double2 each ((s,Pf) (w,fw) (Pb,rs)), and [10][32] scan multipliers
   const double2 *c1, *c2;
   const double *scan1, *scan2;
+  double ff1, ff2;     // the operators' constant super-diagonal (ffx = alfaix ... of src/schemes.f90)
 };
 // chunk tables: H head chunks, 1 generic, H+1 tail chunks (the last chunk may hold a single row); H covers >= 45 rows (the Sherman-Morrison vector of the
 // 6th-order schemes decays by 0.382 per row: 0.382^45 = 1.5e-19)
@@ -56,7 +58,7 @@ constexpr int MOM_THREADS = 32 * (PAIR_WARPS + 4);
 template <int L>
 __device__ __forceinline__ void pair_solve_periodic(dd2 (&x)[L], const double2 *__restrict__ cSP, const double2 *__restrict__ cWF,
                                                     const double2 *__restrict__ cBR, const double *__restrict__ scan, int lane, int nc,
-                                                    bool live, double alpha, int q0, int n) {
+                                                    bool live, double alpha, double ff, int q0, int n) {
   X3D_UNROLL
   for (int m = 1; m < L; ++m) x[m] = fma2(-cSP[m].x, x[m - 1], x[m]);
   dd2 v = x[L - 1];
@@ -71,9 +73,9 @@ __device__ __forceinline__ void pair_solve_periodic(dd2 (&x)[L], const double2 *
     dd2 xn = {0.0, 0.0};
     X3D_UNROLL
     for (int m = L - 1; m >= 0; --m) {
-      const double2 wf = cWF[m];
+      // (t(i) - ff t(i+1)) fw(i) as in src/derive.f90:47-50; ff is one number for a periodic operator
       const dd2 tt = fma2(cSP[m].y, cin, x[m]);
-      xn = fma2(-wf.y, xn, wf.x * tt);
+      xn = cWF[m].x * fma2(-ff, xn, tt);
       x[m] = xn;
     }
   }
@@ -114,8 +116,14 @@ struct TileAcc<false> {  // y / z: [row][16 lanes], 128B swizzle, rows 8 .. 8+n-
     X3D_UNROLL
     for (int p = 0; p < 8; ++p) off[p] = base * 8 + (jw ^ ((base + p) & 7));
   }
-  __device__ __forceinline__ dd2 ld(const unsigned char *slot, int j) const { return reinterpret_cast<const dd2 *>(slot)[off[j & 7] + 8 * j]; }
-  __device__ __forceinline__ void st(unsigned char *slot, int j, dd2 v) const { reinterpret_cast<dd2 *>(slot)[off[j & 7] + 8 * j] = v; }
+  // one 16-byte access per lane pair (dd2 itself is only 8-byte aligned, which would split it in two)
+  __device__ __forceinline__ dd2 ld(const unsigned char *slot, int j) const {
+    const double2 t = reinterpret_cast<const double2 *>(slot)[off[j & 7] + 8 * j];
+    return {t.x, t.y};
+  }
+  __device__ __forceinline__ void st(unsigned char *slot, int j, dd2 v) const {
+    reinterpret_cast<double2 *>(slot)[off[j & 7] + 8 * j] = make_double2(v.x, v.y);
+  }
 };
 template <>
 struct TileAcc<true> {  // x: 16 contiguous lines of pitch n+8 doubles (4 ghosts each side); the pair is two lines
@@ -198,14 +206,22 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
           const long long line0 = pos * 16;
           const int nl = static_cast<int>(g.nlines - line0 < 16 ? g.nlines - line0 : 16);
           double *dst = g.fout[fld[q]] + line0 * n;
-          for (int l = 0; l < nl; ++l)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * n),
-                         "r"(smem_u32(src + (l * g.pitch + HALO) * 8)), "r"(static_cast<unsigned>(n) * 8u)
-                         : "memory");
+          if (g.add == 0) {
+            for (int l = 0; l < nl; ++l)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * n),
+                           "r"(smem_u32(src + (l * g.pitch + HALO) * 8)), "r"(static_cast<unsigned>(n) * 8u)
+                           : "memory");
+          } else {
+            for (int l = 0; l < nl; ++l)
+              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * n),
+                           "r"(smem_u32(src + (l * g.pitch + HALO) * 8)), "r"(static_cast<unsigned>(n) * 8u)
+                           : "memory");
+          }
         } else {
           const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
           const CUtensorMap *tm = &maps.out[fld[q]];
-          for (int b = 0; b < g.nbox; ++b) tma_store_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
+          if (g.add == 0) for (int b = 0; b < g.nbox; ++b) tma_store_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
+          else for (int b = 0; b < g.nbox; ++b) tma_red_add_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
         }
         bulk_commit();
         if (p + 1 < mine) {
@@ -273,10 +289,10 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
             x[m].y = ok ? v1.y : 0.0;
           }
         }
-        pair_solve_periodic<L>(r, s2, w2, b2, scan2, lane, nc, live, op2.alpha, q0, n);
+        pair_solve_periodic<L>(r, s2, w2, b2, scan2, lane, nc, live, op2.alpha, tb.ff2, q0, n);
         X3D_UNROLL
         for (int m = 0; m < L; ++m) r[m] = xnu * r[m];
-        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, q0, n);
+        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, tb.ff1, q0, n);
         X3D_UNROLL
         for (int m = 0; m < L; ++m) {
           const dd2 a = acc.ld(bufA, m + HALO);
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
             x[m].y = ok ? v.y : 0.0;
           }
         }
-        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, q0, n);
+        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, tb.ff1, q0, n);
         X3D_UNROLL
         for (int m = 0; m < L; ++m) {
           r[m].x = fma(-0.5, x[m].x, r[m].x);

@@ -469,52 +469,47 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
   });
 }
 
-// Fused form of momentum_rhs for periodic y and z: per direction one kernel writes
-// r_c = xnu D2(c) - 1/2 (D1(c a) + a D1(c)); the x direction uses the operator kernels.  The three partial
-// right-hand sides are summed inside intt3 (same terms as transeq.f90:312-314,323-325,460-470, summed in a
-// different order).  rhs[d][c]: direction d, component c.
-static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *rhs[3][3]) {
+// Fused form of momentum_rhs for periodic y and z: per direction one kernel forms
+// r_c = xnu D2(c) - 1/2 (D1(c a) + a D1(c)).  The z kernel stores its r_c into sum[c], the y and x kernels add theirs
+// with TMA reduce-add stores, so that intt reads one array per component: sum = (r_z + r_y) + r_x (same terms as
+// transeq.f90:312-314,323-325,460-470, summed in a different order).
+static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3]) {
   const long long n = static_cast<long long>(S.n);
   const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   const double xnu = S.xnu, half = 0.5;
   const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
+  const double *f[3] = {u, v, w};
+  // ---- z, transeq.f90:236-314 (z pencils)
+  {
+    double *t0 = B(S.w[9]), *t1 = B(S.w[10]), *t2 = B(S.w[11]), *o0 = B(S.w[12]), *o1 = B(S.w[13]), *o2 = B(S.w[14]);
+    const bool alias = S.nranks == 1;
+    const double *fz[3] = {u, v, w};
+    if (!alias) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
+      double *dst[3] = {t0, t1, t2};
+      transpose_device_multi(ctx, 1, 3, f, dst, S.id_v, 1);
+      fz[0] = t0; fz[1] = t1; fz[2] = t2;
+    }
+    double *o[3] = {alias ? sum[0] : o0, alias ? sum[1] : o1, alias ? sum[2] : o2};
+    const long long lanes = static_cast<long long>(nx) * S.nyl;
+    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, fz, o, lanes, nz, 1, lanes, lanes * nz, false);
+    if (!alias) transpose_device_multi(ctx, 2, 3, o, sum, S.id_v, 1);  // transeq.f90:318-320
+  }
+  // ---- y, transeq.f90:188-219,336-338
+  launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, true);
   // ---- x, transeq.f90:114-146,442-444
   if (S.fused[0]) {
-    const double *f[3] = {u, v, w};
-    double *o[3] = {rhs[0][0], rhs[0][1], rhs[0][2]};
-    launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, o, nx, static_cast<long long>(ny) * S.nzl);
+    launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true);
   } else {  // operator kernels + three elementwise passes
     double *ta = B(S.w[9]), *tb = B(S.w[10]), *tc = B(S.w[11]), *td = B(S.w[12]), *te = B(S.w[13]), *tf = B(S.w[14]);
-    double *rx = rhs[0][0], *ry = rhs[0][1], *rz = rhs[0][2];
+    double *rx = sum[0], *ry = sum[1], *rz = sum[2];
     map(ctx, n, [=] __device__(long long q) { const double a = u[q]; ta[q] = a * a; tb[q] = a * v[q]; tc[q] = a * w[q]; });
     run(ctx, S.d1[0][1], ta, td); run(ctx, S.d1[0][0], tb, te); run(ctx, S.d1[0][0], tc, tf);
     run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);
     map(ctx, n, [=] __device__(long long q) { const double a = u[q]; td[q] = td[q] + a * ta[q]; te[q] = te[q] + a * tb[q]; tf[q] = tf[q] + a * tc[q]; });
     run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);
     map(ctx, n, [=] __device__(long long q) {
-      rx[q] = xnu * ta[q] - half * td[q]; ry[q] = xnu * tb[q] - half * te[q]; rz[q] = xnu * tc[q] - half * tf[q];
+      rx[q] = rx[q] + (xnu * ta[q] - half * td[q]); ry[q] = ry[q] + (xnu * tb[q] - half * te[q]); rz[q] = rz[q] + (xnu * tc[q] - half * tf[q]);
     });
-  }
-  // ---- y, transeq.f90:188-219,336-338
-  {
-    const double *f[3] = {u, v, w};
-    double *o[3] = {rhs[1][0], rhs[1][1], rhs[1][2]};
-    launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, o, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny);
-  }
-  // ---- z, transeq.f90:236-314 (z pencils)
-  {
-    double *t0 = B(S.w[9]), *t1 = B(S.w[10]), *t2 = B(S.w[11]), *o0 = B(S.w[12]), *o1 = B(S.w[13]), *o2 = B(S.w[14]);
-    const bool alias = S.nranks == 1;
-    const double *f[3] = {u, v, w};
-    if (!alias) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
-      double *dst[3] = {t0, t1, t2};
-      transpose_device_multi(ctx, 1, 3, f, dst, S.id_v, 1);
-      f[0] = t0; f[1] = t1; f[2] = t2;
-    }
-    double *o[3] = {alias ? rhs[2][0] : o0, alias ? rhs[2][1] : o1, alias ? rhs[2][2] : o2};
-    const long long lanes = static_cast<long long>(nx) * S.nyl;
-    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, f, o, lanes, nz, 1, lanes, lanes * nz);
-    if (!alias) transpose_device_multi(ctx, 2, 3, o, rhs[2], S.id_v, 1);  // transeq.f90:318-320
   }
 }
 
@@ -542,37 +537,32 @@ static void adams_bashforth(Ctx &ctx, SolverImpl &S, F rhs) {
   }
 }
 
-// intt for the fused form: dux1 = r_x + r_y + r_z formed on the fly
-static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *rhs[3][3]) {
+// intt for the fused form: sum[c] holds the right-hand side (dux1 of the reference)
+static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *sum[3]) {
   const long long n = static_cast<long long>(S.n);
   double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
-  const double *x0 = rhs[0][0], *x1 = rhs[0][1], *x2 = rhs[0][2], *y0 = rhs[1][0], *y1 = rhs[1][1], *y2 = rhs[1][2];
-  const double *z0 = rhs[2][0], *z1 = rhs[2][1], *z2 = rhs[2][2];
+  const double *r0 = sum[0], *r1 = sum[1], *r2 = sum[2];
   if (S.p.itimescheme == 1) {
     const double g = S.gdt[0];
-    map(ctx, n, [=] __device__(long long q) {
-      u[q] = g * ((z0[q] + y0[q]) + x0[q]) + u[q]; v[q] = g * ((z1[q] + y1[q]) + x1[q]) + v[q]; w[q] = g * ((z2[q] + y2[q]) + x2[q]) + w[q];
-    });
+    map(ctx, n, [=] __device__(long long q) { u[q] = g * r0[q] + u[q]; v[q] = g * r1[q] + v[q]; w[q] = g * r2[q] + w[q]; });
     return;
   }
   double *a2 = B(S.dux[1]), *b2 = B(S.duy[1]), *c2 = B(S.duz[1]);
   if (S.p.itimescheme == 2 || S.p.itimescheme == 3) {
-    adams_bashforth(ctx, S, [=] __device__(long long q, int c) {
-      return c == 0 ? (z0[q] + y0[q]) + x0[q] : (c == 1 ? (z1[q] + y1[q]) + x1[q] : (z2[q] + y2[q]) + x2[q]);
-    });
+    adams_bashforth(ctx, S, [=] __device__(long long q, int c) { return c == 0 ? r0[q] : (c == 1 ? r1[q] : r2[q]); });
     return;
   }
   if (itr == 1) {
     const double g = S.gdt[0];
     map(ctx, n, [=] __device__(long long q) {
-      const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
+      const double x = r0[q], y = r1[q], z = r2[q];
       u[q] = g * x + u[q]; v[q] = g * y + v[q]; w[q] = g * z + w[q];
       a2[q] = x; b2[q] = y; c2[q] = z;
     });
   } else if (itr < S.iadvance) {
     const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
     map(ctx, n, [=] __device__(long long q) {
-      const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
+      const double x = r0[q], y = r1[q], z = r2[q];
       u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
       a2[q] = x; b2[q] = y; c2[q] = z;
     });
@@ -581,8 +571,7 @@ static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *rhs[3][3]) {
     // right-hand side (time_integrators.f90:151-154), so it is not written
     const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
     map(ctx, n, [=] __device__(long long q) {
-      const double x = (z0[q] + y0[q]) + x0[q], y = (z1[q] + y1[q]) + x1[q], z = (z2[q] + y2[q]) + x2[q];
-      u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
+      u[q] = a * r0[q] + b * a2[q] + u[q]; v[q] = a * r1[q] + b * b2[q] + v[q]; w[q] = a * r2[q] + b * c2[q] + w[q];
     });
   }
 }
@@ -785,7 +774,7 @@ void solver_step(Ctx &ctx, int nsteps) {
     for (int itr = 1; itr <= S.iadvance; ++itr) {  // xcompact3d.f90:46-88
       boundary_conditions(ctx, S);
       if (S.fused[1] && S.fused[2]) {
-        double *rhs[3][3] = {{B(S.w[0]), B(S.w[1]), B(S.w[2])}, {B(S.w[3]), B(S.w[4]), B(S.w[5])}, {B(S.w[6]), B(S.w[7]), B(S.w[8])}};
+        double *rhs[3] = {B(S.w[0]), B(S.w[1]), B(S.w[2])};
         momentum_rhs_fused(ctx, S, rhs);
         intt3_fused(ctx, S, itr, rhs);
       } else {
