@@ -55,7 +55,9 @@ def main():
     # ---- slab-decomposed solver vs the single-rank oracle -----------------------------------------
     import oracle_lib as ol
     from test_oracle_tgv import make_solver
-    for nn, ncl in (((32, 24, 40), (0,) * 6), ((33, 25, 33), (1,) * 6)):
+    # the last case has line lengths for which the fused momentum kernels (and their reduce-add accumulation across
+    # the z -> y transposes) run
+    for nn, ncl in (((32, 24, 40), (0,) * 6), ((33, 25, 33), (1,) * 6), ((24, 176, 168), (0,) * 6)):
         length = 2 * np.pi
         x = X3D(local)
         x.decomp_init(*nn, 1, world, rank, world, fresh_id())
@@ -80,6 +82,9 @@ def main():
         got = np.array([d["eek"], d["eps"], d["eps2"], d["enst"]])
         assert np.abs(got / np.array(out[:]) - 1).max() < 1e-10, (got, out[:])
         assert abs(d["divmax"]) < 1e-11
+        if nn[1] >= 168 and os.environ.get("X3D_FUSED", "1") != "0":
+            names = {r["name"] for r in x.profile_step(1)}
+            assert "momentum_fused_y(k_mom_pair)" in names and "momentum_fused_z(k_mom_pair)" in names, names
         x.close()
         dist.barrier()
     if rank == 0:
