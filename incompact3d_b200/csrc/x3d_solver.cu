@@ -145,7 +145,18 @@ struct SolverImpl : SolverState {
   // fused momentum kernels (periodic directions): compressed tables of D1 / D2 per axis
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
-  ~SolverImpl() override { if (h_red) cudaFreeHost(h_red); }
+  // several ranks, X3D_OVERLAP=1: the y -> z transposes of the velocity run on `aux` while the x and y momentum
+  // kernels compute.  Off by default: on 2 B200 it gave 42.4 ms per 512^3 step against 42.3 ms on one stream (the
+  // hidden copies are paid back by slower kernels beside them and by the extra array intt then reads).
+  bool overlap = false;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~SolverImpl() override {
+    if (h_red) cudaFreeHost(h_red);
+    if (aux) cudaStreamDestroy(aux);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
 };
 
 namespace {
@@ -298,6 +309,7 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   S->dpv_x_sub = S->dpv[0]; S->dpv_x_sub.op.store_mode = 2;
   S->ipv_x_sub = S->ipv[0]; S->ipv_x_sub.op.store_mode = 2;
   if (const char *e = getenv("X3D_FUSE_SUMS")) S->fuse_sums = atoi(e) != 0;
+  if (const char *e = getenv("X3D_OVERLAP")) S->overlap = atoi(e) != 0;
   x3d_poisson_params pp{};
   pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
   pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
@@ -470,37 +482,68 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
 }
 
 // Fused form of momentum_rhs for periodic y and z: per direction one kernel forms
-// r_c = xnu D2(c) - 1/2 (D1(c a) + a D1(c)).  The z kernel stores its r_c into sum[c], the y and x kernels add theirs
-// with TMA reduce-add stores, so that intt reads one array per component: sum = (r_z + r_y) + r_x (same terms as
-// transeq.f90:312-314,323-325,460-470, summed in a different order).
-static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3]) {
+// r_c = xnu D2(c) - 1/2 (D1(c a) + a D1(c)).
+//  * one rank: the z kernel stores its r_c into sum[c], the y and x kernels add theirs with TMA reduce-add stores, so
+//    that intt reads one array per component: sum = (r_z + r_y) + r_x;
+//  * several ranks: the y -> z transposes of u, v, w run on a second stream (copy engines / peer stores) while the
+//    y kernel stores and the x kernel adds into sum[c]; the z kernel follows and its result comes back through the
+//    z -> y transposes into extra[c], which intt adds: extra + (r_y + r_x).
+// Same terms as transeq.f90:312-314,323-325,460-470, summed in a different order.
+static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *extra[3]) {
   const long long n = static_cast<long long>(S.n);
   const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   const double xnu = S.xnu, half = 0.5;
   const int nx = S.p.nx, ny = S.p.ny, nz = S.p.nz;
   const double *f[3] = {u, v, w};
-  // ---- z, transeq.f90:236-314 (z pencils)
-  {
-    double *t0 = B(S.w[9]), *t1 = B(S.w[10]), *t2 = B(S.w[11]), *o0 = B(S.w[12]), *o1 = B(S.w[13]), *o2 = B(S.w[14]);
-    const bool alias = S.nranks == 1;
-    const double *fz[3] = {u, v, w};
-    if (!alias) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
-      double *dst[3] = {t0, t1, t2};
-      transpose_device_multi(ctx, 1, 3, f, dst, S.id_v, 1);
-      fz[0] = t0; fz[1] = t1; fz[2] = t2;
+  const bool alias = S.nranks == 1;
+  double *t[3] = {B(S.w[9]), B(S.w[10]), B(S.w[11])}, *o[3] = {B(S.w[12]), B(S.w[13]), B(S.w[14])};
+  const long long lanes = static_cast<long long>(nx) * S.nyl;
+  extra[0] = extra[1] = extra[2] = nullptr;
+  bool z_first = true;
+  if (!alias) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
+    if (S.overlap) {
+      if (!S.aux) {
+        int lo = 0, hi = 0;
+        X3D_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        X3D_CUDA(cudaStreamCreateWithPriority(&S.aux, cudaStreamNonBlocking, hi));
+        X3D_CUDA(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+        X3D_CUDA(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
+      }
+      cudaStream_t main_stream = ctx.stream;
+      X3D_CUDA(cudaEventRecord(S.ev_fork, main_stream));
+      X3D_CUDA(cudaStreamWaitEvent(S.aux, S.ev_fork, 0));
+      ctx.stream = S.aux;
+      try {
+        transpose_device_multi(ctx, 1, 3, f, t, S.id_v, 1);
+      } catch (...) { ctx.stream = main_stream; throw; }
+      ctx.stream = main_stream;
+      X3D_CUDA(cudaEventRecord(S.ev_join, S.aux));
+      z_first = false;
+    } else {
+      transpose_device_multi(ctx, 1, 3, f, t, S.id_v, 1);
     }
-    double *o[3] = {alias ? sum[0] : o0, alias ? sum[1] : o1, alias ? sum[2] : o2};
-    const long long lanes = static_cast<long long>(nx) * S.nyl;
-    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, fz, o, lanes, nz, 1, lanes, lanes * nz, false);
-    if (!alias) transpose_device_multi(ctx, 2, 3, o, sum, S.id_v, 1);  // transeq.f90:318-320
   }
+  auto z_dir = [&](bool into_sum) {  // transeq.f90:236-314 (z pencils)
+    const double *fz[3] = {alias ? u : t[0], alias ? v : t[1], alias ? w : t[2]};
+    double *oz[3] = {alias ? sum[0] : o[0], alias ? sum[1] : o[1], alias ? sum[2] : o[2]};
+    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, fz, oz, lanes, nz, 1, lanes, lanes * nz, false);
+    if (!alias) {  // transeq.f90:318-320
+      if (into_sum) {
+        transpose_device_multi(ctx, 2, 3, o, sum, S.id_v, 1);
+      } else {
+        transpose_device_multi(ctx, 2, 3, o, t, S.id_v, 1);
+        extra[0] = t[0]; extra[1] = t[1]; extra[2] = t[2];
+      }
+    }
+  };
+  if (z_first) z_dir(true);
   // ---- y, transeq.f90:188-219,336-338
-  launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, true);
+  launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, z_first);
   // ---- x, transeq.f90:114-146,442-444
   if (S.fused[0]) {
     launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true);
   } else {  // operator kernels + three elementwise passes
-    double *ta = B(S.w[9]), *tb = B(S.w[10]), *tc = B(S.w[11]), *td = B(S.w[12]), *te = B(S.w[13]), *tf = B(S.w[14]);
+    double *ta = B(S.w[3]), *tb = B(S.w[4]), *tc = B(S.w[5]), *td = B(S.w[6]), *te = B(S.w[7]), *tf = B(S.w[8]);
     double *rx = sum[0], *ry = sum[1], *rz = sum[2];
     map(ctx, n, [=] __device__(long long q) { const double a = u[q]; ta[q] = a * a; tb[q] = a * v[q]; tc[q] = a * w[q]; });
     run(ctx, S.d1[0][1], ta, td); run(ctx, S.d1[0][0], tb, te); run(ctx, S.d1[0][0], tc, tf);
@@ -510,6 +553,10 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3]) {
     map(ctx, n, [=] __device__(long long q) {
       rx[q] = rx[q] + (xnu * ta[q] - half * td[q]); ry[q] = ry[q] + (xnu * tb[q] - half * te[q]); rz[q] = rz[q] + (xnu * tc[q] - half * tf[q]);
     });
+  }
+  if (!z_first) {
+    X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));
+    z_dir(false);
   }
 }
 
@@ -537,32 +584,39 @@ static void adams_bashforth(Ctx &ctx, SolverImpl &S, F rhs) {
   }
 }
 
-// intt for the fused form: sum[c] holds the right-hand side (dux1 of the reference)
-static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *sum[3]) {
+// right-hand side of component c at point q in the fused form: sum[c], plus extra[c] when the z part came back
+// through a transpose (several ranks)
+struct FusedRhs {
+  const double *r[3], *e[3];
+  __device__ __forceinline__ double operator()(long long q, int c) const { return e[0] ? e[c][q] + r[c][q] : r[c][q]; }
+};
+
+// intt for the fused form (dux1 of the reference is formed on the fly)
+static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *sum[3], double *extra[3]) {
   const long long n = static_cast<long long>(S.n);
   double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
-  const double *r0 = sum[0], *r1 = sum[1], *r2 = sum[2];
+  const FusedRhs R{{sum[0], sum[1], sum[2]}, {extra[0], extra[1], extra[2]}};
   if (S.p.itimescheme == 1) {
     const double g = S.gdt[0];
-    map(ctx, n, [=] __device__(long long q) { u[q] = g * r0[q] + u[q]; v[q] = g * r1[q] + v[q]; w[q] = g * r2[q] + w[q]; });
+    map(ctx, n, [=] __device__(long long q) { u[q] = g * R(q, 0) + u[q]; v[q] = g * R(q, 1) + v[q]; w[q] = g * R(q, 2) + w[q]; });
     return;
   }
   double *a2 = B(S.dux[1]), *b2 = B(S.duy[1]), *c2 = B(S.duz[1]);
   if (S.p.itimescheme == 2 || S.p.itimescheme == 3) {
-    adams_bashforth(ctx, S, [=] __device__(long long q, int c) { return c == 0 ? r0[q] : (c == 1 ? r1[q] : r2[q]); });
+    adams_bashforth(ctx, S, [=] __device__(long long q, int c) { return R(q, c); });
     return;
   }
   if (itr == 1) {
     const double g = S.gdt[0];
     map(ctx, n, [=] __device__(long long q) {
-      const double x = r0[q], y = r1[q], z = r2[q];
+      const double x = R(q, 0), y = R(q, 1), z = R(q, 2);
       u[q] = g * x + u[q]; v[q] = g * y + v[q]; w[q] = g * z + w[q];
       a2[q] = x; b2[q] = y; c2[q] = z;
     });
   } else if (itr < S.iadvance) {
     const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
     map(ctx, n, [=] __device__(long long q) {
-      const double x = r0[q], y = r1[q], z = r2[q];
+      const double x = R(q, 0), y = R(q, 1), z = R(q, 2);
       u[q] = a * x + b * a2[q] + u[q]; v[q] = a * y + b * b2[q] + v[q]; w[q] = a * z + b * c2[q] + w[q];
       a2[q] = x; b2[q] = y; c2[q] = z;
     });
@@ -571,7 +625,7 @@ static void intt3_fused(Ctx &ctx, SolverImpl &S, int itr, double *sum[3]) {
     // right-hand side (time_integrators.f90:151-154), so it is not written
     const double a = S.adt[itr - 1], b = S.bdt[itr - 1];
     map(ctx, n, [=] __device__(long long q) {
-      u[q] = a * r0[q] + b * a2[q] + u[q]; v[q] = a * r1[q] + b * b2[q] + v[q]; w[q] = a * r2[q] + b * c2[q] + w[q];
+      u[q] = a * R(q, 0) + b * a2[q] + u[q]; v[q] = a * R(q, 1) + b * b2[q] + v[q]; w[q] = a * R(q, 2) + b * c2[q] + w[q];
     });
   }
 }
@@ -774,9 +828,9 @@ void solver_step(Ctx &ctx, int nsteps) {
     for (int itr = 1; itr <= S.iadvance; ++itr) {  // xcompact3d.f90:46-88
       boundary_conditions(ctx, S);
       if (S.fused[1] && S.fused[2]) {
-        double *rhs[3] = {B(S.w[0]), B(S.w[1]), B(S.w[2])};
-        momentum_rhs_fused(ctx, S, rhs);
-        intt3_fused(ctx, S, itr, rhs);
+        double *rhs[3] = {B(S.w[0]), B(S.w[1]), B(S.w[2])}, *extra[3];
+        momentum_rhs_fused(ctx, S, rhs, extra);
+        intt3_fused(ctx, S, itr, rhs, extra);
       } else {
         momentum_rhs(ctx, S, B(S.dux[0]), B(S.duy[0]), B(S.duz[0]));
         intt3(ctx, S, itr);
