@@ -91,9 +91,11 @@ int x3d_set_stretching(x3d_ctx *ctx, int ny, const double *yp, const double *ypi
                        const double *ppy, const double *pp2y, const double *pp4y,
                        const double *ppyi, const double *pp2yi, const double *pp4yi);
 
-/* ---- immersed-boundary pre-pass (iibm = 2) ------------------------------
- * When iibm = 2 every derx/dery/derz and derxx/deryy/derzz first rebuilds its INPUT inside the solid bodies by
- * Lagrange interpolation (lagpolx/y/z + polint, src/ibm.f90:83-389; call sites src/derive.f90:23,84,157,...).
+/* ---- immersed-boundary pre-pass (iibm = 2, 3) ---------------------------
+ * When iibm = 2 every derx/dery/derz, derxx/deryy/derzz and filx/fily/filz first rebuilds its INPUT inside the solid
+ * bodies by Lagrange interpolation (lagpolx/y/z + polint, src/ibm.f90:83-389; call sites src/derive.f90:23,84,157,...,
+ * src/filters.f90:235,...); when iibm = 3 by clamped cubic splines with the operator's `lind` as wall value
+ * (cubsplx/y/z + cubic_spline, src/ibm.f90:399-968; call sites src/derive.f90:24,..., src/filters.f90:236,...).
  * The geometry is module complex_geometry (src/module_param.f90:546-556), filled by genepsi3d on the host:
  *   nobj(na,nb), xi/xf(nobjmax,na,nb), nipif/nfpif(0:nobjmax,na,nb) with (na,nb) = (ny,nz) for x lines,
  *   (nx,nz) for y lines, (nx,ny) for z lines -- local pencil extents; npif, izap from module param;
@@ -105,6 +107,16 @@ int x3d_set_ibm_geometry(x3d_ctx *ctx, int axis, int nobjmax, int npif, int izap
 int x3d_lagpolx(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz);
 int x3d_lagpoly(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz);
 int x3d_lagpolz(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz);
+/* iibm = 3 with ianal /= 0: the wall positions analitic_x / analitic_y return for xi / xf (src/ibm.f90:412-417,
+ * 1034-1070), computed by the host for its case; same shape as xi / xf.  NULL, NULL = ianal 0 (the default).        */
+int x3d_set_ibm_analytic(x3d_ctx *ctx, int axis, const double *ana_i, const double *ana_f);
+/* cubsplx(u,lind) / cubsply(u,lind) / cubsplz(u,lind), src/ibm.f90:399,559,724: u (host or device) is modified in
+ * place.  Where the reference leaves a value undefined (a node that lies in no spline interval gets what the previous
+ * spline call returned, possibly on another line) the library stores the previous value of the same line, starting
+ * from lind; a body with xi == xf (the reference aborts) is left untouched.                                          */
+int x3d_cubsplx(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz, const double *lind);
+int x3d_cubsply(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz, const double *lind);
+int x3d_cubsplz(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz, const double *lind);
 
 /* ---- compact operators ------------------------------------------------
  * abstract interfaces DERIVATIVE_X/Y/Z, src/module_param.f90:136-167 and

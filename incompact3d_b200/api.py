@@ -312,6 +312,33 @@ def _make_lagpol(ax):
     return f
 
 
+def _set_ibm_analytic(self, axis, ana_i=None, ana_f=None):
+    """analytic wall positions for iibm = 3 with ianal /= 0 (what analitic_x / analitic_y return for xi / xf,
+    src/ibm.f90:412-417); None, None switches back to ianal = 0"""
+    fn = self._L.x3d_set_ibm_analytic
+    dp = C.POINTER(C.c_double)
+    fn.argtypes = [C.c_void_p, C.c_int, dp, dp]
+    if ana_i is None or ana_f is None:
+        self._check(fn(self._h, int(axis), None, None))
+        return
+    ai, af = np.asfortranarray(ana_i, dtype=np.float64), np.asfortranarray(ana_f, dtype=np.float64)
+    self._check(fn(self._h, int(axis), ai.ctypes.data_as(dp), af.ctypes.data_as(dp)))
+
+
+def _make_cubspl(ax):
+    def f(self, u, lind, nx=None, ny=None, nz=None):
+        keep = []
+        shape = list(u.shape) if isinstance(u, np.ndarray) else list(reversed(u.shape))
+        n = [C.c_int(int(v)) for v in (shape if nx is None else (nx, ny, nz))]
+        ld = C.c_double(float(lind))
+        fn = getattr(self._L, "x3d_cubspl" + ax)
+        fn.argtypes = [C.c_void_p, C.c_void_p] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_double)]
+        self._check(fn(self._h, _addr(u, keep), *[C.byref(v) for v in n], C.byref(ld)))
+    f.__name__ = "cubspl" + ax
+    f.__doc__ = f"reference procedure `cubspl{ax}(u,lind)` (src/ibm.f90): u is rebuilt inside the bodies by cubic splines, in place"
+    return f
+
+
 def _solver_init_channel(self):
     fn = self._L.x3d_solver_init_channel
     fn.argtypes = [C.c_void_p]
@@ -386,8 +413,10 @@ X3D.solver_init = _solver_init
 X3D.solver_init_tgv = _solver_init_tgv
 X3D.solver_init_channel = _solver_init_channel
 X3D.set_ibm_geometry = _set_ibm_geometry
+X3D.set_ibm_analytic = _set_ibm_analytic
 for _ax in "xyz":
     setattr(X3D, "lagpol" + _ax, _make_lagpol(_ax))
+    setattr(X3D, "cubspl" + _ax, _make_cubspl(_ax))
 X3D.solver_step = _solver_step
 X3D.solver_diagnostics_tgv = _solver_diag
 X3D.solver_divergence = _solver_divergence

@@ -15,6 +15,8 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p);
 void set_ibm_geometry(Ctx &ctx, int axis, int nobjmax, int npif, int izap, int na, int nb, const int *nobj, const double *xi,
                       const double *xf, const int *nipif, const int *nfpif, const double *coords, int ncoords, double d, double len);
 void lagpol(Ctx &ctx, int axis, double *u, int nx, int ny, int nz);
+void cubspl(Ctx &ctx, int axis, double *u, int nx, int ny, int nz, double lind);
+void set_ibm_analytic(Ctx &ctx, int axis, const double *ana_i, const double *ana_f);
 void solver_init_tgv(Ctx &ctx);
 void solver_init_channel(Ctx &ctx);
 void solver_step(Ctx &ctx, int nsteps);
@@ -130,10 +132,14 @@ int x3d_set_ibm_geometry(x3d_ctx *ctx, int axis, int nobjmax, int npif, int izap
 int x3d_lagpolx(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz) { return guard([&] { lagpol(ctx->c, 0, u, *nx, *ny, *nz); }); }
 int x3d_lagpoly(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz) { return guard([&] { lagpol(ctx->c, 1, u, *nx, *ny, *nz); }); }
 int x3d_lagpolz(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz) { return guard([&] { lagpol(ctx->c, 2, u, *nx, *ny, *nz); }); }
+int x3d_set_ibm_analytic(x3d_ctx *ctx, int axis, const double *ana_i, const double *ana_f) {
+  return guard([&] { set_ibm_analytic(ctx->c, axis, ana_i, ana_f); });
+}
+int x3d_cubsplx(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz, const double *lind) { return guard([&] { cubspl(ctx->c, 0, u, *nx, *ny, *nz, *lind); }); }
+int x3d_cubsply(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz, const double *lind) { return guard([&] { cubspl(ctx->c, 1, u, *nx, *ny, *nz, *lind); }); }
+int x3d_cubsplz(x3d_ctx *ctx, double *u, const int *nx, const int *ny, const int *nz, const double *lind) { return guard([&] { cubspl(ctx->c, 2, u, *nx, *ny, *nz, *lind); }); }
 int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit, int nclx, int ncly, int nclz) {
   return guard([&] {
-    if (iibm == 3)
-      throw Error("iibm=3 (cubic-spline pre-pass cubsplx/y/z inside the operators, src/derive.f90:24) is not implemented");
     ctx->c.iibm = iibm; ctx->c.istret = istret; ctx->c.iimplicit = iimplicit;
     ctx->c.ncl[0] = nclx != 0; ctx->c.ncl[1] = ncly != 0; ctx->c.ncl[2] = nclz != 0;
   });
@@ -141,10 +147,11 @@ int x3d_set_flags(x3d_ctx *ctx, int iibm, int istret, int iimplicit, int nclx, i
 
 // ---- collocated operators --------------------------------------------------------
 static int colloc(x3d_ctx *ctx, Kind kind, int axis, int ncl1, int ncln, double *t, const double *u, const double *f,
-                  const double *s, const double *w, const double *pp, int nx, int ny, int nz, int npaire) {
+                  const double *s, const double *w, const double *pp, int nx, int ny, int nz, int npaire, const double *lind) {
   return guard([&] {
     if (!ctx) throw Error("null context");
     OpCall call{};
+    call.lind = lind ? *lind : 0.0;
     call.kind = kind; call.axis = axis; call.ncl1 = ncl1; call.ncln = ncln;
     call.periodic = (ncl1 == 0 && ncln == 0);
     call.npaire = npaire;
@@ -163,15 +170,15 @@ static int colloc(x3d_ctx *ctx, Kind kind, int axis, int ncl1, int ncln, double 
   int x3d_##name(x3d_ctx *ctx, double *tx, const double *ux, double *rx, double *sx, const double *ffx,       \
                  const double *fsx, const double *fwx, const int *nx, const int *ny, const int *nz,           \
                  const int *npaire, const double *lind) {                                                     \
-    (void)rx; (void)sx; (void)lind;                                                                           \
-    return colloc(ctx, kind, axis, a, b, tx, ux, ffx, fsx, fwx, nullptr, *nx, *ny, *nz, *npaire);             \
+    (void)rx; (void)sx;                                                                                       \
+    return colloc(ctx, kind, axis, a, b, tx, ux, ffx, fsx, fwx, nullptr, *nx, *ny, *nz, *npaire, lind);       \
   }
 #define X3D_DEF_Y(name, kind, axis, a, b)                                                                     \
   int x3d_##name(x3d_ctx *ctx, double *ty, const double *uy, double *ry, double *sy, const double *ffy,       \
                  const double *fsy, const double *fwy, const double *ppy, const int *nx, const int *ny,       \
                  const int *nz, const int *npaire, const double *lind) {                                      \
-    (void)ry; (void)sy; (void)lind;                                                                           \
-    return colloc(ctx, kind, axis, a, b, ty, uy, ffy, fsy, fwy, ppy, *nx, *ny, *nz, *npaire);                 \
+    (void)ry; (void)sy;                                                                                       \
+    return colloc(ctx, kind, axis, a, b, ty, uy, ffy, fsy, fwy, ppy, *nx, *ny, *nz, *npaire, lind);           \
   }
 #define X3D_FIVE(M, stem, kind, axis) \
   M(stem##_00, kind, axis, 0, 0) M(stem##_11, kind, axis, 1, 1) M(stem##_12, kind, axis, 1, 2) \

@@ -83,6 +83,7 @@ struct OpCall {
   const double *f, *s, *w;   // host LU arrays (caller-owned)
   const double *post;        // host ppy/ppyi or nullptr
   bool rhs_only;
+  double lind;               // the operators' last argument: wall value of the iibm = 3 pre-pass
 };
 
 void build_devop(const Ctx &ctx, const OpCall &call, DevOp &op);

@@ -62,6 +62,8 @@ struct Ctx {
     int nobjmax = 0, npif = 2, izap = 1, na = 0, nb = 0, ncoords = 0;
     double d = 0.0, len = 0.0;
     DevBuf nobj, xi, xf, nipif, nfpif, coords;
+    bool analytic = false;        // iibm = 3 with ianal /= 0: analytic wall positions
+    DevBuf ana_i, ana_f;
   };
   IbmAxis ibm[3];
   // optional per-launch CUDA-event timing (x3d_profile_begin / x3d_profile_end)
@@ -111,5 +113,7 @@ void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double 
 void run_op(Ctx &ctx, OpCall &call, const double *u, double *t);
 // lagpolx/y/z on a device array (nx,ny,nz), in place
 void lagpol_device(Ctx &ctx, int axis, double *d_u, int nx, int ny, int nz);
+// cubsplx/y/z on a device array (nx,ny,nz), in place; lind = the value imposed on the walls
+void cubspl_device(Ctx &ctx, int axis, double *d_u, int nx, int ny, int nz, double lind);
 
 }  // namespace x3d

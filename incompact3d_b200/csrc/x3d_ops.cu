@@ -165,10 +165,12 @@ void run_op(Ctx &ctx, OpCall &call, const double *u, double *t) {
       done = true;
     }
   }
-  // iibm = 2: the collocated derivatives first rebuild their input inside the bodies, in place (derive.f90:23)
+  // iibm = 2 / 3: the collocated derivatives and the filters first rebuild their input inside the bodies, in place
+  // (derive.f90:23-24, filters.f90:235-236)
   bool u_modified = false;
-  if (!done && ctx.iibm == 2 && (call.kind == D1 || call.kind == D2)) {
-    lagpol_device(ctx, call.axis, const_cast<double *>(d_u), call.dims_in[0], call.dims_in[1], call.dims_in[2]);
+  if (!done && (ctx.iibm == 2 || ctx.iibm == 3) && (call.kind == D1 || call.kind == D2 || call.kind == FIL)) {
+    if (ctx.iibm == 2) lagpol_device(ctx, call.axis, const_cast<double *>(d_u), call.dims_in[0], call.dims_in[1], call.dims_in[2]);
+    else cubspl_device(ctx, call.axis, const_cast<double *>(d_u), call.dims_in[0], call.dims_in[1], call.dims_in[2], call.lind);
     u_modified = true;
   }
   if (!done) {

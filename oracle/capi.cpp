@@ -262,6 +262,17 @@ void x3do_lagpol(double *u, int nx, int ny, int nz, int axis, int nobjmax, int n
   g.nobjmax = nobjmax; g.npif = npif; g.izap = izap; g.nobj = nobj; g.xi = xi; g.xf = xf; g.nipif = nipif; g.nfpif = nfpif;
   lagpol(u, nx, ny, nz, axis, g, coords, d, len);
 }
+// cubsplx / cubsply / cubsplz (src/ibm.f90:399-874); ana_i / ana_f may be NULL (ianal = 0)
+int x3do_cubspl(double *u, int nx, int ny, int nz, int axis, int nobjmax, int npif, int izap, const int *nobj, const double *xi,
+                const double *xf, const int *nipif, const int *nfpif, const double *coords, double d, double len, double lind,
+                const double *ana_i, const double *ana_f) {
+  try {
+    IbmGeom g;
+    g.nobjmax = nobjmax; g.npif = npif; g.izap = izap; g.nobj = nobj; g.xi = xi; g.xf = xf; g.nipif = nipif; g.nfpif = nfpif;
+    cubspl(u, nx, ny, nz, axis, g, coords, d, len, lind, ana_i, ana_f);
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
 void x3do_channel_cfr(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant) {
   channel_cfr_apply(u, nx, ny, nz, ppy, dy, yly, constant);
 }

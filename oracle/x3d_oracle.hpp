@@ -165,6 +165,8 @@ struct IbmGeom {           // module complex_geometry for one direction (src/mod
   const int *nipif = nullptr, *nfpif = nullptr;  // (0:nobjmax, na, nb)
 };
 void lagpol(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len);
+void cubspl(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len, double lind,
+            const double *ana_i, const double *ana_f);
 
 void channel_cfr_apply(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant);
 

@@ -60,7 +60,7 @@ def configure(x3d, A, axis, istret=0, iimplicit=0):
     x3d.set_flags(iibm=0, istret=istret, iimplicit=iimplicit, nclx=ncl[0], ncly=ncl[1], nclz=ncl[2])
 
 
-def product_op(x3d, name, u, A, npaire, post=None, t=None):
+def product_op(x3d, name, u, A, npaire, post=None, t=None, lind=0.0):
     """call x3d.<name> with the reference argument list; u,t numpy (host) or torch (device)"""
     fam, ax, bc = parse(name)
     axis = "xyz".index(ax)
@@ -83,9 +83,9 @@ def product_op(x3d, name, u, A, npaire, post=None, t=None):
     if fam in ("d1", "d2", "fil"):
         if fam == "d1" and ax == "y":
             pp = post if post is not None else np.ones(ny)
-            fn(t, u, None, None, *lu, pp, nx, ny, nz, npaire, 0.0)
+            fn(t, u, None, None, *lu, pp, nx, ny, nz, npaire, lind)
         else:
-            fn(t, u, None, None, *lu, nx, ny, nz, npaire, 0.0)
+            fn(t, u, None, None, *lu, nx, ny, nz, npaire, lind)
     else:
         vel = [nx, ny, nz]
         if fam in ("dpv", "ipv"):
