@@ -9,6 +9,7 @@ buffers, so nothing is served from cache between iterations.
 import argparse
 import json
 import os
+import re
 import sys
 
 import numpy as np
@@ -16,7 +17,49 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse(name):
+    """-> (family, axis letter, bc) ; family in d1, d2, dvp, ivp, dpv, ipv"""
+    m = re.match(r"^der([xyz])(\1?)_(\d\d)$", name)
+    if m:
+        return ("d2" if m.group(2) else "d1"), m.group(1), m.group(3)
+    m = re.match(r"^(der|inter)([xyz])(vp|pv)$", name)
+    return ("d" if m.group(1) == "der" else "i") + m.group(3), m.group(2), "00"
+
+
+def call_op(x3d, A, name, fam, ax, u, t, dims, npaire):
+    """the reference argument lists (src/module_param.f90:136-167, src/derive.f90:3796-5615)"""
+    nx, ny, nz = dims
+    axis = "xyz".index(ax)
+    n, nm = A.n, A.nm
+    p = "p" if npaire == 1 else ""
+    fn = getattr(x3d, name)
+    if fam in ("d1", "d2"):
+        f, s, w = A.lu(fam + p)
+        if fam == "d1" and ax == "y":
+            fn(t, u, None, None, f, s, w, np.ones(ny), nx, ny, nz, npaire, 0.0)
+        else:
+            fn(t, u, None, None, f, s, w, nx, ny, nz, npaire, 0.0)
+        return
+    if fam == "dvp":
+        lu = list(A.lu("vp"))
+    elif fam == "ivp":
+        lu = list(A.lu("ivpp"))
+    elif fam == "dpv":
+        lu = list(A.lu("pvp")) + list(A.lu("vp"))
+    else:
+        lu = list(A.lu("ipvp")) + list(A.lu("ivp"))
+    vel = [nx, ny, nz]
+    to_p = fam in ("dvp", "ivp")
+    if ax == "x":
+        ints = [vel[0], nm, vel[1], vel[2]] if to_p else [nm, vel[0], vel[1], vel[2]]
+    elif ax == "y":
+        ints = [vel[0], vel[1], nm, vel[2]] if to_p else [vel[0], nm, vel[1], vel[2]]
+    else:
+        ints = [vel[0], vel[1], vel[2], nm] if to_p else [vel[0], vel[1], nm, vel[2]]
+    extra = [np.ones(nm if name == "deryvp" else n)] if name in ("deryvp", "derypv") else []
+    fn(t, u, None, None, *lu, *extra, *ints, npaire)
 
 
 def main():
@@ -28,9 +71,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    from incompact3d_b200 import X3D
-    import helpers as H
-    import oracle_lib as ol  # coefficients only (plays the Fortran host's schemes()); not timed
+    from incompact3d_b200 import X3D, AxisSchemes   # AxisSchemes: the library's host-side schemes() (plays the Fortran host)
 
     nx, ny, nz = args.n
     x3d = X3D(0)
@@ -39,7 +80,6 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = json.load(open(pk)).get("hbm_gbs")
-    rng = np.random.default_rng(20261017)
     res = []
     with torch.cuda.stream(stream):
         xs = torch.arange(nx, dtype=torch.float64, device="cuda") * (2 * np.pi / nx)
@@ -48,25 +88,25 @@ def main():
         u += 0.1 * (torch.rand_like(u) * 2 - 1)
         t = torch.empty_like(u)
         for name in args.ops.split(","):
-            fam, ax, bc = H.parse(name)
+            fam, ax, bc = parse(name)
             axis = "xyz".index(ax)
             n = (nx, ny, nz)[axis]
-            if bc is None:
-                bc = "00"
-            A = ol.Axis(n, int(bc[0]), int(bc[1]), 2 * np.pi, af=0.45)
-            H.configure(x3d, A, axis)
-            uin = u
+            A = AxisSchemes(n, int(bc[0]), int(bc[1]), 2 * np.pi)
+            x3d.set_deriv_coeffs(axis, A.c)
+            ncl = [True, True, True]
+            ncl[axis] = A.periodic
+            x3d.set_flags(iibm=0, istret=0, iimplicit=0, nclx=ncl[0], ncly=ncl[1], nclz=ncl[2])
             if fam in ("dpv", "ipv") and not A.periodic:
                 continue
             npaire = 1 if fam != "dvp" else 0
             for _ in range(args.warmup):
-                H.product_op(x3d, name, uin, A, npaire, t=t)
+                call_op(x3d, A, name, fam, ax, u, t, (nx, ny, nz), npaire)
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             stream.synchronize()
             e0.record(stream)
             for _ in range(args.iters):
-                H.product_op(x3d, name, uin, A, npaire, t=t)
+                call_op(x3d, A, name, fam, ax, u, t, (nx, ny, nz), npaire)
             e1.record(stream)
             e1.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
