@@ -81,6 +81,7 @@ int x3d_create(x3d_ctx **out, int device) {
     X3D_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
     if (const char *e = getenv("X3D_STRIDED_VARIANT")) h->c.strided_variant = atoi(e);
     if (const char *e = getenv("X3D_CONTIG_VARIANT")) h->c.contig_variant = atoi(e);
+    if (const char *e = getenv("X3D_CONTIG_COMPRESS")) h->c.contig_compress = atoi(e) != 0;
     *out = h;
   });
 }

@@ -66,8 +66,18 @@ struct TriTable {
   double *d_scan = nullptr;   // [10][32] Kogge-Stone multipliers (x kernels), [2][nc] chunk products
   double *d_chunk = nullptr;  // [2][nc]: Af(c) forward chunk product, Ab(c) backward chunk product
   std::vector<double> h_rows, h_scan;  // host copies (compressed tables of the fused kernels are derived from them)
+  // compressed rows for long lines (built on first use, x3d_tables.cu: compress_tri): the LU rows reach their
+  // floating-point fixed point a few dozen rows from the boundaries, so chunks c_head .. nc-c_head-2 share one table.
+  // c_head = 0: not built yet, -1: the table does not compress
+  // d_rows_c is the shared-memory image of k_contig: 7 columns of (2 c_head + 2) L entries (c_head head chunks, one
+  // generic chunk, c_head + 1 tail chunks), then the Sherman-Morrison column once more with its own head count c_head_rs
+  // (it decays more slowly than the LU rows converge: 0.82 per row for the alpha = 0.49 interpolators)
+  mutable double *d_rows_c = nullptr;
+  mutable int c_head = 0, c_head_rs = 0;
   ~TriTable();
 };
+// builds T.d_rows_c; returns the number of head chunks, or -1
+int compress_tri(const TriTable &T);
 
 struct Ctx;
 

@@ -48,6 +48,7 @@ struct Ctx {
   long long launches = 0;
   // kernel variants (tuning knobs; X3D_STRIDED_VARIANT / X3D_CONTIG_VARIANT override)
   int strided_variant = 6, contig_variant = 1;
+  bool contig_compress = true;   // X3D_CONTIG_COMPRESS=0: long x lines keep the full coefficient table in shared memory
   // module state made explicit (x3d_set_deriv_coeffs / x3d_set_filter_coeffs / x3d_set_flags)
   x3d_deriv_coeffs dc[3]{};
   x3d_filter_coeffs fc[3]{};

@@ -199,11 +199,13 @@ static void launch_strided(Ctx &ctx, const DevOp &op, const LineGeom &g, const T
 }
 
 template <int KIND, int NT, int L, int WPB, int NB, int MINB, bool TMA>
-static void launch_contig_one(Ctx &ctx, const DevOp &op, const LineGeom &g, const TriTable &T, const double *u, double *t) {
-  const int NP = T.nc * L;
-  int NBUF = (NP > op.n_in ? NP : op.n_in) + 2 * HALO;
+static void launch_contig_one(Ctx &ctx, const DevOp &op, const LineGeom &g, const TriTable &T, const double *u, double *t,
+                              int chead = 0) {
+  const int NPL = T.nc * L;                                    // padded line length
+  const int NP = chead > 0 ? (2 * chead + 2) * L : NPL;        // coefficient rows held in shared memory
+  int NBUF = (NPL > op.n_in ? NPL : op.n_in) + 2 * HALO;
   NBUF = (NBUF + 1) & ~1;
-  const int COEF = (7 * NP + 1) & ~1;
+  const int COEF = (7 * NP + (chead > 0 ? (2 * T.c_head_rs + 2) * L : 0) + 1) & ~1;
   const size_t smem = static_cast<size_t>(COEF + WPB * (NB * NBUF + 8) + WPB * NB) * sizeof(double);
   auto kern = k_contig<KIND, NT, L, WPB, NB, MINB, TMA>;
   static size_t configured = 0;
@@ -214,9 +216,21 @@ static void launch_contig_one(Ctx &ctx, const DevOp &op, const LineGeom &g, cons
   long long blocks = (g.nlines + WPB - 1) / WPB;
   const long long cap = static_cast<long long>(ctx.sm_count) * MINB;
   if (blocks > cap) blocks = cap;
-  kern<<<static_cast<unsigned>(blocks), 32 * WPB, smem, ctx.stream>>>(op, u, t, T.d_rows, T.d_scan, T.nc, g.nlines, NP, NBUF, COEF);
+  kern<<<static_cast<unsigned>(blocks), 32 * WPB, smem, ctx.stream>>>(op, u, t, chead > 0 ? T.d_rows_c : T.d_rows, T.d_scan, T.nc, g.nlines, NP, NBUF,
+                                                                         COEF, chead, chead > 0 ? T.c_head_rs : 0);
   X3D_CUDA(cudaGetLastError());
   ctx.launches++;
+}
+
+// dynamic shared memory of k_contig<.., L, WPB, NB, ..> for this operator (same formula as launch_contig_one)
+template <int L>
+static size_t contig_smem(const DevOp &op, const TriTable &T, int wpb, int nb, int chead = 0) {
+  const int NPL = T.nc * L;
+  const int NP = chead > 0 ? (2 * chead + 2) * L : NPL;
+  int NBUF = (NPL > op.n_in ? NPL : op.n_in) + 2 * HALO;
+  NBUF = (NBUF + 1) & ~1;
+  const int COEF = (7 * NP + (chead > 0 ? (2 * T.c_head_rs + 2) * L : 0) + 1) & ~1;
+  return static_cast<size_t>(COEF + wpb * (nb * NBUF + 8) + wpb * nb) * sizeof(double);
 }
 
 template <int KIND, int NT, int L>
@@ -224,6 +238,22 @@ static void launch_contig_L(Ctx &ctx, const DevOp &op, const LineGeom &g, const 
   const bool even = (op.n_in % 2 == 0) && (op.n_out % 2 == 0);
   const bool aligned = (reinterpret_cast<uintptr_t>(u) % 16 == 0) && (reinterpret_cast<uintptr_t>(t) % 16 == 0);
   const int v = (even && aligned) ? ctx.contig_variant : 0;
+  if constexpr (L >= 25) {
+    // long lines (n > 544): the same two-slot TMA ring as the short ones, so that the load of the next line and the
+    // store of the previous one run under the arithmetic; 8 warps when their line buffers fit beside the coefficient
+    // table, else 4.  Without it (X3D_CONTIG_VARIANT=0, odd n) a warp loads, solves and stores one after the other.
+    constexpr size_t SMEM_MAX = 227 * 1024;
+    if (v != 0) {
+      if (contig_smem<L>(op, T, 8, 2) <= SMEM_MAX) return launch_contig_one<KIND, NT, L, 8, 2, 1, true>(ctx, op, g, T, u, t);
+      // the full coefficient table (7 columns x line length) leaves room for 4 warps only: use the compressed one
+      const int chead = ctx.contig_compress ? compress_tri(T) : -1;
+      if (chead > 0 && contig_smem<L>(op, T, 8, 2, chead) <= SMEM_MAX)
+        return launch_contig_one<KIND, NT, L, 8, 2, 1, true>(ctx, op, g, T, u, t, chead);
+      if (chead > 0 && contig_smem<L>(op, T, 4, 2, chead) <= SMEM_MAX)
+        return launch_contig_one<KIND, NT, L, 4, 2, 1, true>(ctx, op, g, T, u, t, chead);
+      if (contig_smem<L>(op, T, 4, 2) <= SMEM_MAX) return launch_contig_one<KIND, NT, L, 4, 2, 1, true>(ctx, op, g, T, u, t);
+    }
+  }
   if constexpr (L == 9 || L == 17) {
     if (v == 1) return launch_contig_one<KIND, NT, L, 8, 2, 2, true>(ctx, op, g, T, u, t);
     if (v == 2) return launch_contig_one<KIND, NT, L, 8, 3, 1, true>(ctx, op, g, T, u, t);

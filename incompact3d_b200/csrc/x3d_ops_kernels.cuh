@@ -235,7 +235,10 @@ template <int KIND, int NT, int L, int WPB, int NB, int MINB, bool TMA>
 __global__ void __launch_bounds__(32 * WPB, MINB)
     k_contig(const __grid_constant__ DevOp op, const double *__restrict__ u, double *__restrict__ t,
              const double *__restrict__ rows, const double *__restrict__ scan, int nc, long long nlines, int NP,
-             int NBUF, int COEF) {
+             int NBUF, int COEF, int CHEAD, int CHEAD_RS) {
+  // NP = rows of the coefficient table: nc * L, or (2 CHEAD + 2) * L when it is compressed (CHEAD > 0: head chunks,
+  // one generic chunk, CHEAD + 1 tail chunks; `rows` is then the ready shared-memory image with the Sherman-Morrison
+  // column appended under its own head count CHEAD_RS, see compress_tri)
   constexpr int NWIN = L + 2 * HALO;
   extern __shared__ __align__(16) double smem[];
   double *coef = smem;  // [7][NP], COEF doubles reserved (even)
@@ -245,9 +248,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB)
   double *sb = wbase + NB * NBUF;  // [8] explicit boundary rows of the current line
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + COEF + WPB * WSTRIDE) + warp * NB;
   const int n_in = op.n_in, n_out = op.n_out;
-  for (int idx = threadIdx.x; idx < NP * TRI_W; idx += blockDim.x) {
-    const int r = idx / TRI_W, col = idx % TRI_W;
-    if (col < 7) coef[col * NP + r] = __ldg(rows + idx);
+  if (CHEAD > 0) {
+    const int nimg = 7 * NP + (2 * CHEAD_RS + 2) * L;
+    for (int idx = threadIdx.x; idx < nimg; idx += blockDim.x) coef[idx] = __ldg(rows + idx);
+  } else {
+    for (int idx = threadIdx.x; idx < NP * TRI_W; idx += blockDim.x) {
+      const int r = idx / TRI_W, col = idx % TRI_W;
+      if (col < 7) coef[col * NP + r] = __ldg(rows + idx);
+    }
   }
   for (int q = lane; q < WSTRIDE; q += 32) wbase[q] = 0.0;
   if (TMA && lane == 0) {
@@ -261,9 +269,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB)
   const int cl = c < nc ? c : nc - 1;  // idle lanes shadow the last chunk (results discarded)
   const int q0 = cl * L;
   const bool live = c < nc;
-  const double *cS = coef + T_S * NP + q0, *cPF = coef + T_PF * NP + q0, *cW = coef + T_W * NP + q0,
-               *cFW = coef + T_FW * NP + q0, *cPB = coef + T_PB * NP + q0, *cRS = coef + T_RS * NP + q0,
-               *cPO = coef + T_POST * NP + q0;
+  const int tab = CHEAD <= 0 ? cl : (cl < CHEAD ? cl : (cl >= nc - CHEAD - 1 ? CHEAD + 1 + cl - (nc - CHEAD - 1) : CHEAD));
+  const int qc = tab * L;
+  const int tab_rs = cl < CHEAD_RS ? cl : (cl >= nc - CHEAD_RS - 1 ? CHEAD_RS + 1 + cl - (nc - CHEAD_RS - 1) : CHEAD_RS);
+  const double *cS = coef + T_S * NP + qc, *cPF = coef + T_PF * NP + qc, *cW = coef + T_W * NP + qc,
+               *cFW = coef + T_FW * NP + qc, *cPB = coef + T_PB * NP + qc,
+               *cRS = CHEAD > 0 ? coef + 7 * NP + tab_rs * L : coef + T_RS * NP + qc, *cPO = coef + T_POST * NP + qc;
   const long long first = static_cast<long long>(blockIdx.x) * WPB + warp;
   const long long step = static_cast<long long>(gridDim.x) * WPB;
   const unsigned in_bytes = static_cast<unsigned>(n_in) * 8u, out_bytes = static_cast<unsigned>(n_out) * 8u;

@@ -99,6 +99,8 @@ CASES = [  # (dims, axis letter) -- line lengths of the BASELINE configs, ragged
     ((34, 16, 3), "y"), ((8, 2, 10), "z"),
     # long lines (BASELINE config #5: 1536^3 over 8 GPUs) and beyond
     ((1536, 3, 2), "x"), ((8, 1536, 2), "y"), ((6, 2, 1537), "z"), ((1100, 2, 2), "x"), ((5, 2, 2048), "z"), ((2050, 2, 1), "x"),
+    # enough long x lines for every warp's TMA ring to wrap (more lines than 148 CTAs x 4 warps)
+    ((1536, 40, 16), "x"),
 ]
 
 
