@@ -124,6 +124,31 @@ def check_cubics_exact(backend, x3d=None, tol=1e-13):
     assert worst < tol, worst
 
 
+def check_filter_transfer_function(backend, x3d=None, tol=2e-13):
+    """periodic filter (Gaitonde & Visbal 6th-order tridiagonal filter, src/filters.f90:87-93): a Fourier mode is scaled by
+    T(k) = [a + b cos(kh) + c cos(2kh) + d cos(3kh)] / (1 + 2 af cos(kh)),
+    a = (11 + 10 af)/16, b = (15 + 34 af)/32, c = (-3 + 6 af)/16, d = (1 - 2 af)/32; T(0) = 1, T(pi/h) = 0"""
+    h = LEN / N
+    xs = np.arange(N) * h
+    worst = 0.0
+    for af in (0.45, 0.3, -0.2):
+        a, b, c, d = (11 + 10 * af) / 16, (15 + 34 * af) / 32, (-3 + 6 * af) / 16, (1 - 2 * af) / 32
+        for axis, ax in enumerate("xyz"):
+            A = ol.Axis(N, 0, 0, LEN, af=af)
+            for m in PERIODIC_MODES + [0, N // 2]:
+                k = 2 * np.pi * m / LEN
+                T = (a + b * np.cos(k * h) + c * np.cos(2 * k * h) + d * np.cos(3 * k * h)) / (1 + 2 * af * np.cos(k * h))
+                u, lanes = _field(np.cos(k * xs), axis)
+                f = _apply(backend, x3d, f"fil{ax}_00", u, A, 1, axis)
+                worst = max(worst, np.abs(f - T * u).max() / lanes.max())
+            assert abs((a + b + c + d) / (1 + 2 * af) - 1) < 1e-15 and abs(a - b + c - d) < 1e-15
+    assert worst < tol, worst
+
+
+def test_oracle_filter_transfer_function():
+    check_filter_transfer_function("oracle")
+
+
 def test_oracle_periodic_modified_wavenumbers():
     check_periodic_modified_wavenumbers("oracle")
 
@@ -157,3 +182,8 @@ def test_product_symmetric_modes(x3d):
 @pytest.mark.gpu
 def test_product_cubics_exact(x3d):
     check_cubics_exact("product", x3d, tol=1e-12)
+
+
+@pytest.mark.gpu
+def test_product_filter_transfer_function(x3d):
+    check_filter_transfer_function("product", x3d, tol=2e-12)
