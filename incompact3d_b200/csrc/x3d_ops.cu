@@ -113,10 +113,13 @@ void launch_line_op(Ctx &ctx, const DevOp &op, const OpCall &call, const double 
   if (L < 0) throw Error("x-direction line too long for the warp-per-line kernel (n <= 2080)");
   const TriTable &T = get_tri(ctx, call.f, call.s, call.w, n_out, L, op.periodic != 0, op.alpha, call.post);
   // operators that accumulate into their destination move 24 B per point, not 16: they get their own class
-  static const char *names[2][3] = {{"compact_x(k_contig)", "compact_y(k_strided)", "compact_z(k_strided)"},
-                                    {"accumulate_x(k_contig, TMA reduce-add)", "accumulate_y(k_strided, TMA reduce-add)",
-                                     "accumulate_z(k_strided, TMA reduce-add)"}};
-  ProfScope ps(ctx, names[op.store_mode != 0][call.axis]);
+  // the class names carry the kernel that runs: k_pair for y / z lines that qualify, the k_tile / k_strided fallbacks else
+  static const char *names[2][2][3] = {
+      {{"compact_x(k_contig)", "compact_y(k_strided)", "compact_z(k_strided)"},
+       {"accumulate_x(k_contig, TMA reduce-add)", "accumulate_y(k_strided)", "accumulate_z(k_strided)"}},
+      {{"compact_x(k_contig)", "compact_y(k_pair)", "compact_z(k_pair)"},
+       {"accumulate_x(k_contig, TMA reduce-add)", "accumulate_y(k_pair, TMA reduce-add)", "accumulate_z(k_pair, TMA reduce-add)"}}};
+  ProfScope ps(ctx, names[g.pair ? 1 : 0][op.store_mode != 0][call.axis]);
   switch (op.kind) {
     case D1: launch_kind_D1(ctx, op, g, T, d_u, d_t); break;
     case D2: launch_kind_D2(ctx, op, g, T, d_u, d_t); break;
