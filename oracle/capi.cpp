@@ -218,6 +218,28 @@ static std::vector<double> *dpd_array(Solver *s, int q) {
 }
 void x3do_solver_set_wall_gradient(void *sv, int q, const double *in) { auto *v = dpd_array(static_cast<Solver *>(sv), q); std::memcpy(v->data(), in, v->size() * 8); }
 void x3do_solver_get_wall_gradient(void *sv, int q, double *out) { auto *v = dpd_array(static_cast<Solver *>(sv), q); std::memcpy(out, v->data(), v->size() * 8); }
+// wall velocity plane q in the order bxx1 bxy1 bxz1 bxxn bxyn bxzn | byx1 .. byzn | bzx1 .. bzzn
+void x3do_solver_set_wall_velocity(void *sv, int q, const double *in) { auto &v = static_cast<Solver *>(sv)->bw[q]; std::memcpy(v.data(), in, v.size() * 8); }
+void x3do_solver_get_wall_velocity(void *sv, int q, double *out) { auto &v = static_cast<Solver *>(sv)->bw[q]; std::memcpy(out, v.data(), v.size() * 8); }
+// inflow / outflow of the cylinder case on the solver's velocity; noise planes bxo, byo, bzo may be NULL (zero)
+int x3do_solver_inflow_outflow(void *sv, int itr, const double *gdt3, double u1, double u2, double inflow_noise, const double *bxo,
+                               const double *byo, const double *bzo) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    for (int q = 0; q < 3; ++q) s->gdt[q] = gdt3[q];
+    s->itr = itr; s->p.u1 = u1; s->p.u2 = u2; s->p.inflow_noise = inflow_noise;
+    if (bxo) std::memcpy(s->bxo.data(), bxo, s->bxo.size() * 8);
+    if (byo) std::memcpy(s->byo.data(), byo, s->byo.size() * 8);
+    if (bzo) std::memcpy(s->bzo.data(), bzo, s->bzo.size() * 8);
+    s->inflow();
+    s->outflow();
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void x3do_ibm_body(double *ux, double *uy, double *uz, const double *ep, long long n) { ibm_body(ux, uy, uz, ep, static_cast<size_t>(n)); }
+void x3do_ibm_corgp(double *ux, double *uy, double *uz, const double *px, const double *py, const double *pz, long long n, int nlock) {
+  ibm_corgp(ux, uy, uz, px, py, pz, static_cast<size_t>(n), nlock);
+}
 int x3do_solver_pre_correc(void *sv, int itr, const double *gdt3) {
   try {
     auto *s = static_cast<Solver *>(sv);

@@ -71,8 +71,12 @@ void Solver::init() {
   for (int q = 0; q < ntime; ++q) { dux[q].assign(n, 0.0); duy[q].assign(n, 0.0); duz[q].assign(n, 0.0); }
   const size_t nyz = static_cast<size_t>(p.ny) * p.nz, nxz = static_cast<size_t>(p.nx) * p.nz, nxy = static_cast<size_t>(p.nx) * p.ny;
   for (auto *v : {&dpdyx1, &dpdzx1, &dpdyxn, &dpdzxn}) v->assign(nyz, 0.0);
+  for (int q = 0; q < 6; ++q) bw[q].assign(nyz, 0.0);
+  for (auto *v : {&bxo, &byo, &bzo}) v->assign(nyz, 0.0);
   for (auto *v : {&dpdxy1, &dpdzy1, &dpdxyn, &dpdzyn}) v->assign(nxz, 0.0);
   for (auto *v : {&dpdxz1, &dpdyz1, &dpdxzn, &dpdyzn}) v->assign(nxy, 0.0);
+  for (int q = 6; q < 12; ++q) bw[q].assign(nxz, 0.0);
+  for (int q = 12; q < 18; ++q) bw[q].assign(nxy, 0.0);
   itime = 0;
 }
 
@@ -112,6 +116,7 @@ void Solver::channel_cfr(std::vector<double> &u, double constant) {
 
 // boundary_conditions_channel, Case-Channel.f90:150-170 (cpg = F, idir_stream = 1)
 void Solver::boundary_conditions() {
+  if (p.itype == 5) { inflow(); outflow(); }   // boundary_conditions_cyl, Case-Cylinder-wake.f90:84-98
   if (p.itype == 3) channel_cfr(ux, 2.0 / 3.0);
 }
 
@@ -266,17 +271,29 @@ void Solver::pre_correc() {
   const int nx = p.nx, ny = p.ny, nz = p.nz;
   auto id = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
   const double g = gdt[itr - 1];
-  if (p.ncl[0][0] == 2)  // :560-574
+  std::vector<double> &bxx1 = bw[0], &bxy1 = bw[1], &bxz1 = bw[2], &bxxn = bw[3], &bxyn = bw[4], &bxzn = bw[5];
+  std::vector<double> &byx1 = bw[6], &byy1 = bw[7], &byz1 = bw[8], &byxn = bw[9], &byyn = bw[10], &byzn = bw[11];
+  std::vector<double> &bzx1 = bw[12], &bzy1 = bw[13], &bzz1 = bw[14], &bzxn = bw[15], &bzyn = bw[16], &bzzn = bw[17];
+  // inflow / outflow flow-rate balance, :534-560 (itype channel, uniform, abl with nclx = 2 on both sides)
+  if ((p.itype == 3 || p.itype == 11 || p.itype == 10) && p.ncl[0][0] == 2 && p.ncl[0][1] == 2) {
+    double ut1 = 0.0, ut = 0.0;
+    for (size_t q = 0; q < bxx1.size(); ++q) ut1 = ut1 + bxx1[q];
+    ut1 = ut1 / static_cast<double>(ny * nz);
+    for (size_t q = 0; q < bxxn.size(); ++q) ut = ut + bxxn[q];
+    ut = ut / static_cast<double>(ny * nz);
+    for (size_t q = 0; q < bxxn.size(); ++q) bxxn[q] = bxxn[q] - ut + ut1;
+  }
+  if (p.ncl[0][0] == 2)  // :564-579
     for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
       const size_t q = j + static_cast<size_t>(ny) * k;
       dpdyx1[q] *= g; dpdzx1[q] *= g;
-      ux[id(0, j, k)] = 0.0; uy[id(0, j, k)] = 0.0 + dpdyx1[q]; uz[id(0, j, k)] = 0.0 + dpdzx1[q];
+      ux[id(0, j, k)] = bxx1[q]; uy[id(0, j, k)] = bxy1[q] + dpdyx1[q]; uz[id(0, j, k)] = bxz1[q] + dpdzx1[q];
     }
-  if (p.ncl[0][1] == 2)  // :575-589
+  if (p.ncl[0][1] == 2)  // :580-595
     for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
       const size_t q = j + static_cast<size_t>(ny) * k;
       dpdyxn[q] *= g; dpdzxn[q] *= g;
-      ux[id(nx - 1, j, k)] = 0.0; uy[id(nx - 1, j, k)] = 0.0 + dpdyxn[q]; uz[id(nx - 1, j, k)] = 0.0 + dpdzxn[q];
+      ux[id(nx - 1, j, k)] = bxxn[q]; uy[id(nx - 1, j, k)] = bxyn[q] + dpdyxn[q]; uz[id(nx - 1, j, k)] = bxzn[q] + dpdzxn[q];
     }
   if (p.ncl[0][0] == 1) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) ux[id(0, j, k)] = 0.0;        // :600-606
   if (p.ncl[0][1] == 1) for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) ux[id(nx - 1, j, k)] = 0.0;   // :607-613
@@ -284,13 +301,13 @@ void Solver::pre_correc() {
     for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * k;
       dpdxy1[q] *= g; dpdzy1[q] *= g;
-      ux[id(i, 0, k)] = 0.0 + dpdxy1[q]; uy[id(i, 0, k)] = 0.0; uz[id(i, 0, k)] = 0.0 + dpdzy1[q];
+      ux[id(i, 0, k)] = byx1[q] + dpdxy1[q]; uy[id(i, 0, k)] = byy1[q]; uz[id(i, 0, k)] = byz1[q] + dpdzy1[q];
     }
   if (p.ncl[1][1] == 2)  // :644-689
     for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * k;
       dpdxyn[q] *= g; dpdzyn[q] *= g;
-      ux[id(i, ny - 1, k)] = 0.0 + dpdxyn[q]; uy[id(i, ny - 1, k)] = 0.0; uz[id(i, ny - 1, k)] = 0.0 + dpdzyn[q];
+      ux[id(i, ny - 1, k)] = byxn[q] + dpdxyn[q]; uy[id(i, ny - 1, k)] = byyn[q]; uz[id(i, ny - 1, k)] = byzn[q] + dpdzyn[q];
     }
   if (p.ncl[1][0] == 1) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) uy[id(i, 0, k)] = 0.0;        // :693-701
   if (p.ncl[1][1] == 1) for (int k = 0; k < nz; ++k) for (int i = 0; i < nx; ++i) uy[id(i, ny - 1, k)] = 0.0;   // :703-711
@@ -298,16 +315,59 @@ void Solver::pre_correc() {
     for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * j;
       dpdxz1[q] *= g; dpdyz1[q] *= g;
-      ux[id(i, j, 0)] = 0.0 + dpdxz1[q]; uy[id(i, j, 0)] = 0.0 + dpdyz1[q]; uz[id(i, j, 0)] = 0.0;
+      ux[id(i, j, 0)] = bzx1[q] + dpdxz1[q]; uy[id(i, j, 0)] = bzy1[q] + dpdyz1[q]; uz[id(i, j, 0)] = bzz1[q];
     }
   if (p.ncl[2][1] == 2)  // :729-745
     for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * j;
       dpdxzn[q] *= g; dpdyzn[q] *= g;
-      ux[id(i, j, nz - 1)] = 0.0 + dpdxzn[q]; uy[id(i, j, nz - 1)] = 0.0 + dpdyzn[q]; uz[id(i, j, nz - 1)] = 0.0;
+      ux[id(i, j, nz - 1)] = bzxn[q] + dpdxzn[q]; uy[id(i, j, nz - 1)] = bzyn[q] + dpdyzn[q]; uz[id(i, j, nz - 1)] = bzzn[q];
     }
   if (p.ncl[2][0] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, 0)] = 0.0;        // :751-759
   if (p.ncl[2][1] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, nz - 1)] = 0.0;   // :761-769
+}
+
+// Case-Cylinder-wake.f90:100-133: inflow plane; bxo, byo, bzo are the reference's random_number planes
+void Solver::inflow() {
+  for (size_t q = 0; q < bw[0].size(); ++q) {
+    bw[0][q] = p.u1 + bxo[q] * p.inflow_noise;
+    bw[1][q] = 0.0 + byo[q] * p.inflow_noise;
+    bw[2][q] = 0.0 + bzo[q] * p.inflow_noise;
+  }
+}
+
+// Case-Cylinder-wake.f90:135-203: convective outflow, celerity from the plane nx - 1 or from u1 / u2
+void Solver::outflow() {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  auto id = [&](int i, int j, int k) { return i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
+  const double dx = X.d, udx = 1.0 / dx;
+  double uxmax = -1609.0, uxmin = 1609.0;
+  for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
+    const double v = ux[id(nx - 2, j, k)];
+    if (v > uxmax) uxmax = v;
+    if (v < uxmin) uxmin = v;
+  }
+  const double g = gdt[itr - 1];
+  double cx;
+  if (p.u1 == 0.0) cx = (0.5 * (uxmax + uxmin)) * g * udx;
+  else if (p.u1 == 1.0) cx = uxmax * g * udx;
+  else if (p.u1 == 2.0) cx = p.u2 * g * udx;
+  else cx = (0.5 * (p.u1 + p.u2)) * g * udx;
+  for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
+    const size_t q = j + static_cast<size_t>(ny) * k;
+    bw[3][q] = ux[id(nx - 1, j, k)] - cx * (ux[id(nx - 1, j, k)] - ux[id(nx - 2, j, k)]);
+    bw[4][q] = uy[id(nx - 1, j, k)] - cx * (uy[id(nx - 1, j, k)] - uy[id(nx - 2, j, k)]);
+    bw[5][q] = uz[id(nx - 1, j, k)] - cx * (uz[id(nx - 1, j, k)] - uz[id(nx - 2, j, k)]);
+  }
+}
+
+// src/ibm.f90:52-80 and :14-49
+void ibm_body(double *ux, double *uy, double *uz, const double *ep, size_t n) {
+  for (size_t q = 0; q < n; ++q) { ux[q] = (1.0 - ep[q]) * ux[q]; uy[q] = (1.0 - ep[q]) * uy[q]; uz[q] = (1.0 - ep[q]) * uz[q]; }
+}
+void ibm_corgp(double *ux, double *uy, double *uz, const double *px, const double *py, const double *pz, size_t n, int nlock) {
+  if (nlock == 1) for (size_t q = 0; q < n; ++q) { ux[q] = -px[q] + ux[q]; uy[q] = -py[q] + uy[q]; uz[q] = -pz[q] + uz[q]; }
+  if (nlock == 2) for (size_t q = 0; q < n; ++q) { ux[q] = px[q] + ux[q]; uy[q] = py[q] + uy[q]; uz[q] = pz[q] + uz[q]; }
 }
 
 // navier.f90:257-372

@@ -123,7 +123,9 @@ struct SolverParams {
   SchemeOptions opt;
   int istret = 0;
   double beta = 0.259065151;
-  int itype = 0;  // 0: TGV-type box; 3: channel (itype_channel): constant flow rate channel_cfr, Case-Channel.f90:150-170
+  int itype = 0;  // 0: TGV-type box; 3: channel (itype_channel): constant flow rate channel_cfr, Case-Channel.f90:150-170;
+                  // 5: cylinder wake (itype_cyl): inflow / convective outflow planes, Case-Cylinder-wake.f90:84-203
+  double u1 = 1.0, u2 = 1.0, inflow_noise = 0.0;   // module param (inflow / outflow of the cylinder case)
 };
 struct Solver {
   SolverParams p;
@@ -140,6 +142,12 @@ struct Solver {
   std::vector<std::vector<double>> work;
   // wall pressure-gradient terms captured by gradp and used by pre_correc (navier.f90:439-496, 560-746)
   std::vector<double> dpdyx1, dpdzx1, dpdyxn, dpdzxn, dpdxy1, dpdzy1, dpdxyn, dpdzyn, dpdxz1, dpdyz1, dpdxzn, dpdyzn;
+  // wall velocities (src/module_param.f90:242-244), zero unless a case sets them, in the order
+  // bxx1 bxy1 bxz1 bxxn bxyn bxzn | byx1 byy1 byz1 byxn byyn byzn | bzx1 bzy1 bzz1 bzxn bzyn bzzn
+  std::vector<double> bw[18];
+  std::vector<double> bxo, byo, bzo;   // inflow noise planes (random_number in the reference; inputs here)
+  void inflow();                       // Case-Cylinder-wake.f90:100-133
+  void outflow();                      // Case-Cylinder-wake.f90:135-203
   void init();
   void init_tgv();
   void init_channel();        // Case-Channel.f90:25-107, iin = 0 (laminar profile + deterministic perturbation)
@@ -169,5 +177,8 @@ void cubspl(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const
             const double *ana_i, const double *ana_f);
 
 void channel_cfr_apply(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant);
+// src/ibm.f90:14-80: the "old school" solid body (iibm = 1): velocity zeroed inside the body, bracketed by corgp_IBM
+void ibm_body(double *ux, double *uy, double *uz, const double *ep, size_t n);
+void ibm_corgp(double *ux, double *uy, double *uz, const double *px, const double *py, const double *pz, size_t n, int nlock);
 
 }  // namespace x3do
