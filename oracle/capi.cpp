@@ -236,6 +236,37 @@ int x3do_solver_inflow_outflow(void *sv, int itr, const double *gdt3, double u1,
     return 0;
   } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+// immersed boundary of the solver: iibm, ep1 (nx,ny,nz), wall velocity; geometry of one direction (copied)
+int x3do_solver_set_ibm(void *sv, int iibm, const double *ep1, const double *ubc3) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    s->iibm = iibm;
+    s->ep1.assign(ep1, ep1 + s->ux.size());
+    for (int q = 0; q < 3; ++q) s->ubc[q] = ubc3 ? ubc3[q] : 0.0;
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int x3do_solver_set_ibm_geometry(void *sv, int axis, int nobjmax, int npif, int izap, const int *nobj, const double *xi, const double *xf,
+                                 const int *nipif, const int *nfpif) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    const int n[3] = {s->p.nx, s->p.ny, s->p.nz};
+    const size_t nl = static_cast<size_t>(n[axis == 0 ? 1 : 0]) * n[axis == 2 ? 1 : 2];
+    auto &I = s->ibm[axis];
+    I.nobj.assign(nobj, nobj + nl);
+    I.xi.assign(xi, xi + nl * nobjmax); I.xf.assign(xf, xf + nl * nobjmax);
+    I.nipif.assign(nipif, nipif + nl * (nobjmax + 1)); I.nfpif.assign(nfpif, nfpif + nl * (nobjmax + 1));
+    I.g.nobjmax = nobjmax; I.g.npif = npif; I.g.izap = izap;
+    I.g.nobj = I.nobj.data(); I.g.xi = I.xi.data(); I.g.xf = I.xf.data(); I.g.nipif = I.nipif.data(); I.g.nfpif = I.nfpif.data();
+    I.set = true;
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void x3do_solver_init_cyl(void *sv, double u1, double u2) {
+  auto *s = static_cast<Solver *>(sv);
+  s->p.u1 = u1; s->p.u2 = u2;
+  s->init_cyl();
+}
 void x3do_ibm_body(double *ux, double *uy, double *uz, const double *ep, long long n) { ibm_body(ux, uy, uz, ep, static_cast<size_t>(n)); }
 void x3do_ibm_corgp(double *ux, double *uy, double *uz, const double *px, const double *py, const double *pz, long long n, int nlock) {
   ibm_corgp(ux, uy, uz, px, py, pz, static_cast<size_t>(n), nlock);

@@ -146,31 +146,42 @@ void Solver::momentum_rhs_eq(double *dux1, double *duy1, double *duz1) {
   double *tg1 = W(6, n), *th1 = W(7, n), *ti1 = W(8, n);
   double *tg2 = W(9, n), *th2 = W(10, n), *ti2 = W(11, n);
   double *tg3 = W(12, n), *th3 = W(13, n), *ti3 = W(14, n), *tj = W(15, n);
-  const double *u = ux.data(), *v = uy.data(), *w = uz.data();
+  double *u = ux.data(), *v = uy.data(), *w = uz.data();
   const double *ppy = p.istret ? st.ppy.data() : nullptr;
   const double half = 0.5;
+  const double bx = ubc[0], by = ubc[1], bz = ubc[2];
+  // with iibm = 2 / 3 every collocated derivative first rebuilds its input inside the bodies, in place -- the
+  // velocity arrays included (src/derive.f90:23-24); lind = product of the wall velocities (src/transeq.f90:120-146)
+  auto der1 = [&](const AxisScheme &A, int axis, const int dd[3], double *in, double *out, int npaire, const double *post, double lind = 0.0) {
+    ibm_prepass(axis, in, lind);
+    x3do::der1(A, axis, dd, in, out, npaire, post);
+  };
+  auto der2 = [&](const AxisScheme &A, int axis, const int dd[3], double *in, double *out, int npaire, double lind = 0.0) {
+    ibm_prepass(axis, in, lind);
+    x3do::der2(A, axis, dd, in, out, npaire);
+  };
   // ---- x pencils, :114-146
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { ta[q] = u[q] * u[q]; tb[q] = u[q] * v[q]; tc[q] = u[q] * w[q]; }
-  der1(X, 0, d, ta, td, 1, nullptr); der1(X, 0, d, tb, te, 0, nullptr); der1(X, 0, d, tc, tf, 0, nullptr);
-  der1(X, 0, d, u, ta, 0, nullptr); der1(X, 0, d, v, tb, 1, nullptr); der1(X, 0, d, w, tc, 1, nullptr);
+  der1(X, 0, d, ta, td, 1, nullptr, bx * bx); der1(X, 0, d, tb, te, 0, nullptr, bx * by); der1(X, 0, d, tc, tf, 0, nullptr, bx * bz);
+  der1(X, 0, d, u, ta, 0, nullptr, bx); der1(X, 0, d, v, tb, 1, nullptr, by); der1(X, 0, d, w, tc, 1, nullptr, bz);
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { tg1[q] = td[q] + u[q] * ta[q]; th1[q] = te[q] + u[q] * tb[q]; ti1[q] = tf[q] + u[q] * tc[q]; }
   // ---- y pencils, :188-219
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { td[q] = u[q] * v[q]; te[q] = v[q] * v[q]; tf[q] = w[q] * v[q]; }
-  der1(Y, 1, d, td, tg2, 0, ppy); der1(Y, 1, d, te, th2, 1, ppy); der1(Y, 1, d, tf, ti2, 0, ppy);
-  der1(Y, 1, d, u, td, 1, ppy); der1(Y, 1, d, v, te, 0, ppy); der1(Y, 1, d, w, tf, 1, ppy);
+  der1(Y, 1, d, td, tg2, 0, ppy, bx * by); der1(Y, 1, d, te, th2, 1, ppy, by * by); der1(Y, 1, d, tf, ti2, 0, ppy, bz * by);
+  der1(Y, 1, d, u, td, 1, ppy, bx); der1(Y, 1, d, v, te, 0, ppy, by); der1(Y, 1, d, w, tf, 1, ppy, bz);
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { tg2[q] = tg2[q] + v[q] * td[q]; th2[q] = th2[q] + v[q] * te[q]; ti2[q] = ti2[q] + v[q] * tf[q]; }
   // ---- z pencils, :249-314
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { td[q] = u[q] * w[q]; te[q] = v[q] * w[q]; tf[q] = w[q] * w[q]; }
-  der1(Z, 2, d, td, tg3, 0, nullptr); der1(Z, 2, d, te, th3, 0, nullptr); der1(Z, 2, d, tf, ti3, 1, nullptr);
-  der1(Z, 2, d, u, td, 1, nullptr); der1(Z, 2, d, v, te, 1, nullptr); der1(Z, 2, d, w, tf, 0, nullptr);
+  der1(Z, 2, d, td, tg3, 0, nullptr, bx * bz); der1(Z, 2, d, te, th3, 0, nullptr, by * bz); der1(Z, 2, d, tf, ti3, 1, nullptr, bz * bz);
+  der1(Z, 2, d, u, td, 1, nullptr, bx); der1(Z, 2, d, v, te, 1, nullptr, by); der1(Z, 2, d, w, tf, 0, nullptr, bz);
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { td[q] = tg3[q] + w[q] * td[q]; te[q] = th3[q] + w[q] * te[q]; tf[q] = ti3[q] + w[q] * tf[q]; }
-  der2(Z, 2, d, u, ta, 1); der2(Z, 2, d, v, tb, 1); der2(Z, 2, d, w, tc, 0);
+  der2(Z, 2, d, u, ta, 1, bx); der2(Z, 2, d, v, tb, 1, by); der2(Z, 2, d, w, tc, 0, bz);
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) {
     td[q] = xnu * ta[q] - half * td[q]; te[q] = xnu * tb[q] - half * te[q]; tf[q] = xnu * tc[q] - half * tf[q];
@@ -178,22 +189,22 @@ void Solver::momentum_rhs_eq(double *dux1, double *duy1, double *duz1) {
     tg2[q] = td[q] - half * tg2[q]; th2[q] = te[q] - half * th2[q]; ti2[q] = tf[q] - half * ti2[q];
   }
   // ---- diffusive terms in y, :336-372
-  der2(Y, 1, d, u, td, 1); der2(Y, 1, d, v, te, 0); der2(Y, 1, d, w, tf, 1);
+  der2(Y, 1, d, u, td, 1, bx); der2(Y, 1, d, v, te, 0, by); der2(Y, 1, d, w, tf, 1, bz);
   if (p.istret != 0) {
     const int nx = p.nx, ny = p.ny, nz = p.nz;
-    der1(Y, 1, d, u, tj, 1, ppy);
+    der1(Y, 1, d, u, tj, 1, ppy, bx);
 #pragma omp parallel for collapse(2) schedule(static)
     for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
       td[q] = td[q] * st.pp2y[j] - st.pp4y[j] * tj[q];
     }
-    der1(Y, 1, d, v, tj, 0, ppy);
+    der1(Y, 1, d, v, tj, 0, ppy, by);
 #pragma omp parallel for collapse(2) schedule(static)
     for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
       te[q] = te[q] * st.pp2y[j] - st.pp4y[j] * tj[q];
     }
-    der1(Y, 1, d, w, tj, 1, ppy);
+    der1(Y, 1, d, w, tj, 1, ppy, bz);
 #pragma omp parallel for collapse(2) schedule(static)
     for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
       const size_t q = i + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k);
@@ -203,7 +214,7 @@ void Solver::momentum_rhs_eq(double *dux1, double *duy1, double *duz1) {
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) { ta[q] = xnu * td[q] + tg2[q]; tb[q] = xnu * te[q] + th2[q]; tc[q] = xnu * tf[q] + ti2[q]; }  // :431-433
   // ---- diffusive terms in x and final sum, :442-470
-  der2(X, 0, d, u, td, 0); der2(X, 0, d, v, te, 1); der2(X, 0, d, w, tf, 1);
+  der2(X, 0, d, u, td, 0, bx); der2(X, 0, d, v, te, 1, by); der2(X, 0, d, w, tf, 1, bz);
 #pragma omp parallel for schedule(static)
   for (size_t q = 0; q < n; ++q) {
     td[q] = xnu * td[q]; te[q] = xnu * te[q]; tf[q] = xnu * tf[q];
@@ -325,6 +336,33 @@ void Solver::pre_correc() {
     }
   if (p.ncl[2][0] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, 0)] = 0.0;        // :751-759
   if (p.ncl[2][1] == 1) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) uz[id(i, j, nz - 1)] = 0.0;   // :761-769
+  if (iibm == 1) {  // :782-786, solid body old school
+    const size_t n = ux.size();
+    ibm_corgp(ux.data(), uy.data(), uz.data(), px.data(), py.data(), pz.data(), n, 1);
+    ibm_body(ux.data(), uy.data(), uz.data(), ep1.data(), n);
+    ibm_corgp(ux.data(), uy.data(), uz.data(), px.data(), py.data(), pz.data(), n, 2);
+  }
+}
+
+void Solver::ibm_prepass(int axis, double *arr, double lind) {
+  if (iibm != 2 && iibm != 3) return;
+  if (!ibm[axis].set) throw std::runtime_error("oracle solver: iibm = 2 / 3 without geometry for this direction");
+  const AxisScheme &A = axis == 0 ? X : (axis == 1 ? Y : Z);
+  const double len = axis == 0 ? p.xlx : (axis == 1 ? p.yly : p.zlz);
+  std::vector<double> yp_uniform;
+  const double *coords = nullptr;
+  if (axis == 1) {
+    if (p.istret != 0) coords = st.yp.data();
+    else { yp_uniform.resize(p.ny); for (int j = 0; j < p.ny; ++j) yp_uniform[j] = j * A.d; coords = yp_uniform.data(); }
+  }
+  if (iibm == 2) lagpol(arr, p.nx, p.ny, p.nz, axis, ibm[axis].g, coords, A.d, len);
+  else cubspl(arr, p.nx, p.ny, p.nz, axis, ibm[axis].g, coords, A.d, len, lind, nullptr, nullptr);
+}
+
+// Case-Cylinder-wake.f90:205-279 with iin = 0 (no initial noise): uniform stream u1
+void Solver::init_cyl() {
+  for (size_t q = 0; q < ux.size(); ++q) { ux[q] = 0.0 + p.u1; uy[q] = 0.0; uz[q] = 0.0; }
+  itime = 0;
 }
 
 // Case-Cylinder-wake.f90:100-133: inflow plane; bxo, byo, bzo are the reference's random_number planes
@@ -378,9 +416,20 @@ void Solver::divergence(double *pp3out, int nlock, double *tmax_out, double *tmo
   double *pp1 = W(20, n1), *pgy1 = W(21, n1), *pgz1 = W(22, n1);
   double *upi2 = W(23, n2), *duydypi2 = W(24, n2), *po3 = W(25, n3);
   const int dx1[3] = {nx, ny, nz};
-  apply_op(mk(DVP, X, 0, X.cfx6, X.csx6, X.cwx6), 0, dx1, ux.data(), pp1);        // :297
-  apply_op(mk(IVP, X, 1, X.cifxp6, X.cisxp6, X.ciwxp6), 0, dx1, uy.data(), pgy1);  // :313
-  apply_op(mk(IVP, X, 1, X.cifxp6, X.cisxp6, X.ciwxp6), 0, dx1, uz.data(), pgz1);  // :314
+  const double *ta1 = ux.data(), *tb1 = uy.data(), *tc1 = uz.data();
+  if (iibm != 0) {  // :285-293
+    const size_t n = static_cast<size_t>(nx) * ny * nz;
+    double *a = W(26, n), *b = W(27, n), *c = W(28, n);
+    for (size_t q = 0; q < n; ++q) {
+      a[q] = (1.0 - ep1[q]) * ux[q] + ep1[q] * ubc[0];
+      b[q] = (1.0 - ep1[q]) * uy[q] + ep1[q] * ubc[1];
+      c[q] = (1.0 - ep1[q]) * uz[q] + ep1[q] * ubc[2];
+    }
+    ta1 = a; tb1 = b; tc1 = c;
+  }
+  apply_op(mk(DVP, X, 0, X.cfx6, X.csx6, X.cwx6), 0, dx1, ta1, pp1);        // :297
+  apply_op(mk(IVP, X, 1, X.cifxp6, X.cisxp6, X.ciwxp6), 0, dx1, tb1, pgy1);  // :313
+  apply_op(mk(IVP, X, 1, X.cifxp6, X.cisxp6, X.ciwxp6), 0, dx1, tc1, pgz1);  // :314
   const int dy2[3] = {nxm, ny, nz};
   const double *ppyi = p.istret ? st.ppyi.data() : nullptr;
   apply_op(mk(IVP, Y, 1, Y.cifxp6, Y.cisxp6, Y.ciwxp6), 1, dy2, pp1, upi2);           // :321

@@ -113,6 +113,17 @@ struct Poisson {
 void inversion5_v1(const std::vector<cplx> &aaa_in, cplx *eee, int nx, int nyh, int nz);
 void inversion5_v2(std::vector<cplx> &aaa, cplx *eee, int nx, int nym, int nz);
 
+// ---- ibm.f90: Lagrange reconstruction inside the bodies (iibm = 2) ---------------------------------------
+struct IbmGeom {           // module complex_geometry for one direction (src/module_param.f90:546-556)
+  int nobjmax = 0, npif = 2, izap = 1;
+  const int *nobj = nullptr;     // (na, nb)
+  const double *xi = nullptr, *xf = nullptr;   // (nobjmax, na, nb)
+  const int *nipif = nullptr, *nfpif = nullptr;  // (0:nobjmax, na, nb)
+};
+void lagpol(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len);
+void cubspl(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len, double lind,
+            const double *ana_i, const double *ana_f);
+
 // ---- solver (transeq.f90, time_integrators.f90, navier.f90, Case-TGV.f90) ------
 struct SolverParams {
   int nx = 65, ny = 65, nz = 65;
@@ -146,6 +157,19 @@ struct Solver {
   // bxx1 bxy1 bxz1 bxxn bxyn bxzn | byx1 byy1 byz1 byxn byyn byzn | bzx1 bzy1 bzz1 bzxn bzyn bzzn
   std::vector<double> bw[18];
   std::vector<double> bxo, byo, bzo;   // inflow noise planes (random_number in the reference; inputs here)
+  // immersed boundary (iibm = 1: body() around the projection; 2 / 3: reconstruction inside the derivative operators,
+  // src/derive.f90:23-24, and the masked velocity in divergence, src/navier.f90:285-293); geometry is an input
+  int iibm = 0;
+  std::vector<double> ep1;
+  double ubc[3] = {0.0, 0.0, 0.0};
+  struct IbmStore {
+    IbmGeom g;
+    std::vector<int> nobj, nipif, nfpif;
+    std::vector<double> xi, xf;
+    bool set = false;
+  } ibm[3];
+  void ibm_prepass(int axis, double *arr, double lind);
+  void init_cyl();                     // Case-Cylinder-wake.f90:205-279 with iin = 0
   void inflow();                       // Case-Cylinder-wake.f90:100-133
   void outflow();                      // Case-Cylinder-wake.f90:135-203
   void init();
@@ -164,17 +188,6 @@ struct Solver {
   void postprocess_tgv(double out[4]);  // eek, eps, eps2, enst
   double *W(int i, size_t n);
 };
-
-// ---- ibm.f90: Lagrange reconstruction inside the bodies (iibm = 2) ---------------------------------------
-struct IbmGeom {           // module complex_geometry for one direction (src/module_param.f90:546-556)
-  int nobjmax = 0, npif = 2, izap = 1;
-  const int *nobj = nullptr;     // (na, nb)
-  const double *xi = nullptr, *xf = nullptr;   // (nobjmax, na, nb)
-  const int *nipif = nullptr, *nfpif = nullptr;  // (0:nobjmax, na, nb)
-};
-void lagpol(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len);
-void cubspl(double *u, int nx, int ny, int nz, int axis, const IbmGeom &g, const double *coords, double d, double len, double lind,
-            const double *ana_i, const double *ana_f);
 
 void channel_cfr_apply(double *u, int nx, int ny, int nz, const double *ppy, double dy, double yly, double constant);
 // src/ibm.f90:14-80: the "old school" solid body (iibm = 1): velocity zeroed inside the body, bracketed by corgp_IBM
