@@ -267,6 +267,17 @@ void x3do_solver_init_cyl(void *sv, double u1, double u2) {
   s->p.u1 = u1; s->p.u2 = u2;
   s->init_cyl();
 }
+// momentum_forcing (case.f90:538 -> Case-Channel.f90:396-420) on caller arrays, with the solver's velocity
+int x3do_solver_momentum_forcing(void *sv, long long itime, int cpg, double fcpg, double wrotation, int spinup_time, int iin, double *dux,
+                                 double *duy, double *duz) {
+  try {
+    auto *s = static_cast<Solver *>(sv);
+    s->itime = static_cast<int>(itime);
+    s->p.cpg = cpg != 0; s->fcpg = fcpg; s->p.wrotation = wrotation; s->p.spinup_time = spinup_time; s->p.iin = iin;
+    s->momentum_forcing(dux, duy, duz);
+    return 0;
+  } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
 void x3do_ibm_body(double *ux, double *uy, double *uz, const double *ep, long long n) { ibm_body(ux, uy, uz, ep, static_cast<size_t>(n)); }
 void x3do_ibm_corgp(double *ux, double *uy, double *uz, const double *px, const double *py, const double *pz, long long n, int nlock) {
   ibm_corgp(ux, uy, uz, px, py, pz, static_cast<size_t>(n), nlock);

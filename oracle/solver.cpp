@@ -40,6 +40,11 @@ void Solver::init() {
   Z = make_axis(p.nz, p.ncl[2][0], p.ncl[2][1], p.zlz, p.opt);
   nxm = X.nm; nym = Y.nm; nzm = Z.nm;
   xnu = 1.0 / p.re;  // parameters.f90:302
+  if (p.cpg) {       // :305-311: re is Re_tau; viscosity from the estimated centre-line Reynolds number
+    const double re_cent = std::pow(p.re / 0.116, 1.0 / 0.88);
+    xnu = 1.0 / re_cent;
+    fcpg = 2.0 / p.yly * ((p.re / re_cent) * (p.re / re_cent));
+  }
   st.istret = p.istret;
   if (p.istret != 0) {
     st.beta = p.beta; st.yly = p.yly;
@@ -117,7 +122,7 @@ void Solver::channel_cfr(std::vector<double> &u, double constant) {
 // boundary_conditions_channel, Case-Channel.f90:150-170 (cpg = F, idir_stream = 1)
 void Solver::boundary_conditions() {
   if (p.itype == 5) { inflow(); outflow(); }   // boundary_conditions_cyl, Case-Cylinder-wake.f90:84-98
-  if (p.itype == 3) channel_cfr(ux, 2.0 / 3.0);
+  if (p.itype == 3 && !p.cpg) channel_cfr(ux, 2.0 / 3.0);
 }
 
 // Case-TGV.f90:58-100 (iin=1, no noise)
@@ -365,6 +370,18 @@ void Solver::init_cyl() {
   itime = 0;
 }
 
+// momentum_forcing_channel, Case-Channel.f90:396-420 (idir_stream = 1)
+void Solver::momentum_forcing(double *dux1, double *duy1, double *) {
+  if (p.itype != 3) return;
+  const size_t n = ux.size();
+  if (p.cpg)
+    for (size_t q = 0; q < n; ++q) dux1[q] = dux1[q] + fcpg;
+  if (itime < p.spinup_time && p.iin <= 2) {
+    const double w = p.wrotation;
+    for (size_t q = 0; q < n; ++q) { dux1[q] = dux1[q] - w * uy[q]; duy1[q] = duy1[q] + w * ux[q]; }
+  }
+}
+
 // Case-Cylinder-wake.f90:100-133: inflow plane; bxo, byo, bzo are the reference's random_number planes
 void Solver::inflow() {
   for (size_t q = 0; q < bw[0].size(); ++q) {
@@ -504,6 +521,7 @@ void Solver::step() {
   for (itr = 1; itr <= iadvance_time; ++itr) {
     boundary_conditions();                         // xcompact3d.f90:52
     momentum_rhs_eq(dux[0].data(), duy[0].data(), duz[0].data());
+    momentum_forcing(dux[0].data(), duy[0].data(), duz[0].data());   // the end of momentum_rhs_eq, transeq.f90:539
     intt(ux, dux); intt(uy, duy); intt(uz, duz);
     pre_correc();
     divergence(pp3.data(), 1, nullptr, nullptr);  // solve_poisson, navier.f90:76

@@ -137,6 +137,11 @@ struct SolverParams {
   int itype = 0;  // 0: TGV-type box; 3: channel (itype_channel): constant flow rate channel_cfr, Case-Channel.f90:150-170;
                   // 5: cylinder wake (itype_cyl): inflow / convective outflow planes, Case-Cylinder-wake.f90:84-203
   double u1 = 1.0, u2 = 1.0, inflow_noise = 0.0;   // module param (inflow / outflow of the cylinder case)
+  // channel forcing (Case-Channel.f90:396-420, parameters.f90:303-311): constant pressure gradient instead of the
+  // constant flow rate, and the spin-up rotation
+  bool cpg = false;
+  double wrotation = 0.0;
+  int spinup_time = 0, iin = 0;
 };
 struct Solver {
   SolverParams p;
@@ -175,6 +180,8 @@ struct Solver {
   void init();
   void init_tgv();
   void init_channel();        // Case-Channel.f90:25-107, iin = 0 (laminar profile + deterministic perturbation)
+  double fcpg = 0.0;          // parameters.f90:310
+  void momentum_forcing(double *dux1, double *duy1, double *duz1);   // case.f90:538-567 -> momentum_forcing_channel
   void boundary_conditions(); // case.f90 boundary_conditions -> boundary_conditions_channel
   void channel_cfr(std::vector<double> &u, double constant);
   void capture_wall_gradients(const double *px1, const double *py1, const double *pz1);

@@ -8,6 +8,7 @@ Executes the reference's own statements (via f90mini.py) of
   * src/ibm.f90                 body, corgp_IBM
   * src/navier.f90              pre_correc with non-zero wall velocities (inflow / outflow planes of the cylinder case)
                                 and with the inflow / outflow flow-rate correction of itype = channel, nclx = 2
+  * src/Case-Channel.f90        momentum_forcing_channel (constant pressure gradient, spin-up rotation)
 on small seeded random fields and writes tests/golden/cyl.npz.
 """
 import os
@@ -127,6 +128,22 @@ def main():
             out[f"pre_correc/{tag}/out/{nm}"] = fu[q].a.copy()
         for nm in ("bxxn",):
             out[f"pre_correc/{tag}/out/{nm}"] = ns[nm].a.copy()
+    # ---- momentum_forcing_channel: constant pressure gradient and spin-up rotation (Case-Channel.f90:396-420)
+    chan = load("Case-Channel")
+    d = [np.asfortranarray(rng.uniform(-1, 1, (NX, NY, NZ, 2))) for _ in range(3)]
+    for q, nm in enumerate(("dux", "duy", "duz")):
+        out[f"forcing/in/{nm}"] = d[q][..., 0].copy()
+    for tag, cpg, itime, spin in (("cpg", True, 5, 0), ("rot", False, 5, 10), ("rot_over", False, 12, 10), ("both", True, 3, 10)):
+        ns = base()
+        ns.update(dict(cpg=cpg, fcpg=0.0123, idir_stream=1, itime=itime, spinup_time=spin, iin=1, wrotation=0.37, ntime=2))
+        _, code = tr.subroutine(sub_text(chan, "momentum_forcing_channel"))
+        exec(code, ns)
+        fd = [fm.FArr(a.copy(order="F")) for a in d]
+        ns["momentum_forcing_channel"](fd[0], fd[1], fd[2], *[fm.FArr(a.copy(order="F")) for a in u])
+        for q, nm in enumerate(("dux", "duy", "duz")):
+            out[f"forcing/{tag}/{nm}"] = fd[q].a[..., 0].copy()
+            assert np.array_equal(fd[q].a[..., 1], d[q][..., 1])
+        out[f"forcing/{tag}/par"] = np.array([float(cpg), 0.0123, float(itime), float(spin), 0.37])
     np.savez_compressed(os.path.join(HERE, "cyl.npz"), **out)
     print("cyl.npz:", len(out), "entries")
 

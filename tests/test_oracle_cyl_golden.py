@@ -109,3 +109,20 @@ def test_pre_correc_with_wall_velocities(gold, tag, itype):
     changed = not np.array_equal(buf, gold[f"pre_correc/{tag}/in/bxxn"])
     assert changed == (tag == "channel")     # the flow-rate correction is not applied to the cylinder case
     L.x3do_solver_destroy(s)
+
+
+@pytest.mark.parametrize("tag", ["cpg", "rot", "rot_over", "both"])
+def test_channel_momentum_forcing(gold, tag):
+    """momentum_forcing_channel (src/Case-Channel.f90:396-420): constant pressure gradient, spin-up rotation"""
+    L = ol.lib()
+    u = [np.asfortranarray(gold[f"outflow/in/{n}"]).copy(order="F") for n in ("ux", "uy", "uz")]
+    nn = u[0].shape
+    s = _solver(L, nn, (0, 0, 2, 2, 0, 0), 3, 2.0)
+    L.x3do_solver_set_velocity(s, *[_p(a) for a in u])
+    L.x3do_solver_momentum_forcing.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]
+    cpg, fcpg, itime, spin, wrot = (float(v) for v in gold[f"forcing/{tag}/par"])
+    d = [np.asfortranarray(gold[f"forcing/in/{n}"]).copy(order="F") for n in ("dux", "duy", "duz")]
+    assert L.x3do_solver_momentum_forcing(s, int(itime), int(cpg), fcpg, wrot, int(spin), 1, *[_p(a) for a in d]) == 0
+    for a, nm in zip(d, ("dux", "duy", "duz")):
+        assert np.array_equal(a, gold[f"forcing/{tag}/{nm}"]), (tag, nm)
+    L.x3do_solver_destroy(s)
