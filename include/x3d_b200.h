@@ -317,6 +317,11 @@ int x3d_schemes_axis(int n, int ncl1, int ncln, double len, int ifirstder, int i
                      double nu0nu, double cnu, x3d_deriv_coeffs *coeffs, int which, double *f, double *s,
                      double *w);
 
+/* set_filter_coefficients (src/filters.f90:62-219) likewise: the parfiX/Y/Z scalars for filter parameter af and one
+ * prepared LU triple (which: 0 fiffx,fifsx,fifwx | 1 fiffxp,fifsxp,fifwxp), n entries each                       */
+int x3d_filter_axis(int n, int ncl1, int ncln, double af, x3d_filter_coeffs *coeffs, int which, double *f, double *s,
+                    double *w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,6 +197,19 @@ class AxisSchemes:
             self._cache[name] = (f, s, w)
         return self._cache[name]
 
+    def filter(self, af, p=False):
+        """`set_filter_coefficients` (src/filters.f90:62-219) for this direction: returns (FilterCoeffs, (f, s, w)) --
+        the parfiX/Y/Z scalars and fiffx,fifsx,fifwx (p=False) or fiffxp,fifsxp,fifwxp (p=True).  Host-side, CPU only."""
+        c = FilterCoeffs()
+        f, s, w = (np.zeros(self.n) for _ in range(3))
+        fn = self._L.x3d_filter_axis
+        fn.restype = C.c_int
+        rc = fn(C.c_int(self.n), C.c_int(self.ncl1), C.c_int(self.ncln), C.c_double(float(af)), C.byref(c), C.c_int(1 if p else 0),
+                C.c_void_p(f.ctypes.data), C.c_void_p(s.ctypes.data), C.c_void_p(w.ctypes.data))
+        if rc:
+            raise X3DError(self._L.x3d_last_error().decode())
+        return c, (f, s, w)
+
 
 def _poisson_init(self, nx, ny, nz, bcx, bcy, bcz, xlx, yly, zlz, istret=0, alpha=0.0, beta=0.0):
     """decomp_2d_poisson_init (src/poisson.f90:73); nx,ny,nz are the velocity-mesh node counts"""

@@ -411,6 +411,20 @@ int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean) {
 // ---- schemes() for non-Fortran hosts (src/schemes.f90); CPU only, no context needed -----------------
 // which: 0 first derivative (ff,fs,fw), 1 its p-variant, 2 second derivative, 3 p-variant, 4 cfx6.., 5 cfxp6..,
 //        6 cifx6.., 7 cifxp6.., 8 cfi6.., 9 cfip6.., 10 cifi6.., 11 cifip6..
+int x3d_filter_axis(int n, int ncl1, int ncln, double af, x3d_filter_coeffs *coeffs, int which, double *f, double *s, double *w) {
+  return guard([&] {
+    if (which < 0 || which > 1) throw Error("x3d_filter_axis: bad selector");
+    x3d_filter_coeffs c;
+    LU3 plain, p;
+    make_filter_axis(n, ncl1, ncln, af, c, plain, p);
+    if (coeffs) *coeffs = c;
+    const LU3 &L = which == 1 ? p : plain;
+    if (f) std::copy(L.f.begin(), L.f.end(), f);
+    if (s) std::copy(L.s.begin(), L.s.end(), s);
+    if (w) std::copy(L.w.begin(), L.w.end(), w);
+  });
+}
+
 int x3d_schemes_axis(int n, int ncl1, int ncln, double len, int ifirstder, int isecondder, int ipinter, double nu0nu,
                      double cnu, x3d_deriv_coeffs *coeffs, int which, double *f, double *s, double *w) {
   return guard([&] {

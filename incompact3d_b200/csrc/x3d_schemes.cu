@@ -216,4 +216,43 @@ StretchY make_stretching(int istret, double beta, double yly, int ny, int nym) {
   return S;
 }
 
+// set_filter_coefficients (src/filters.f90:62-219): the parfiX/Y/Z scalars for the filter parameter af and the two
+// prepared left-hand sides (plain: fiffx,fifsx,fifwx; p: fiffxp,fifsxp,fifwxp)
+void make_filter_axis(int n, int ncl1, int ncln, double af, x3d_filter_coeffs &c, LU3 &plain, LU3 &p) {
+  if (n < 6) throw Error("x3d_filter_axis: n must be at least 6");
+  if (ncl1 < 0 || ncl1 > 2 || ncln < 0 || ncln > 2) throw Error("x3d_filter_axis: bad boundary condition");
+  c = x3d_filter_coeffs{};
+  // interior, Gaitonde & Visbal 1998 (:87-93)
+  c.fiali = af;
+  c.fiai = (11.0 + 10.0 * af) / 16.0;
+  c.fibi = 0.5 * (15.0 + 34.0 * af) / 32.0;
+  c.fici = 0.5 * (-3.0 + 6.0 * af) / 16.0;
+  c.fidi = 0.5 * (1.0 - 2.0 * af) / 32.0;
+  // boundary points 1 / n: not filtered; 2 / n-1: third order; 3 / n-2: fifth order (:94-138)
+  c.fial1 = 0.0; c.fia1 = 1.0; c.fib1 = 0.0; c.fic1 = 0.0; c.fid1 = 0.0;
+  c.fial2 = af; c.fia2 = 1.0 / 8.0 + 3.0 / 4.0 * af; c.fib2 = 5.0 / 8.0 + 3.0 / 4.0 * af; c.fic2 = 3.0 / 8.0 + af / 4.0; c.fid2 = -1.0 / 8.0 + af / 4.0;
+  c.fial3 = af; c.fia3 = -1.0 / 32.0 + af / 16.0; c.fib3 = 5.0 / 32.0 + 11.0 / 16.0 * af; c.fic3 = 11.0 / 16.0 + 5.0 * af / 8.0;
+  c.fid3 = 5.0 / 16.0 + 3.0 * af / 8.0; c.fie3 = -5.0 / 32.0 + 5.0 * af / 16.0; c.fif3 = 1.0 / 32.0 - af / 16.0;
+  c.fialn = 0.0; c.fian = 1.0; c.fibn = 0.0; c.ficn = 0.0; c.fidn = 0.0;
+  c.fialm = c.fial2; c.fiam = c.fia2; c.fibm = c.fib2; c.ficm = c.fic2; c.fidm = c.fid2;
+  c.fialp = c.fial3; c.fiap = c.fia3; c.fibp = c.fib3; c.ficp = c.fic3; c.fidp = c.fid3; c.fiep = c.fie3; c.fifp = c.fif3;
+  // tridiagonal left-hand side, :140-196 (0-based rows)
+  Tri t(n);
+  const double al = c.fiali;
+  if (ncl1 == 0) { t.f[0] = al; t.f[1] = al; t.c[0] = 2.0; t.c[1] = 1.0; t.b[0] = al; t.b[1] = al; }
+  else if (ncl1 == 1) { t.f[0] = al + al; t.f[1] = al; t.c[0] = 1.0; t.c[1] = 1.0; t.b[0] = al; t.b[1] = al; }
+  else { t.f[0] = c.fial1; t.f[1] = c.fial2; t.c[0] = 1.0; t.c[1] = 1.0; t.b[0] = c.fial2; t.b[1] = al; }
+  for (int i = 2; i <= n - 4; ++i) { t.f[i] = al; t.c[i] = 1.0; t.b[i] = al; }   // do i = 3, n-3 (after the ends in the reference; disjoint rows)
+  if (ncln == 0) { t.f[n - 3] = al; t.f[n - 2] = al; t.f[n - 1] = 0.0; t.c[n - 3] = 1.0; t.c[n - 2] = 1.0; t.c[n - 1] = 1.0 + al * al;
+                   t.b[n - 3] = al; t.b[n - 2] = al; t.b[n - 1] = 0.0; }
+  else if (ncln == 1) { t.f[n - 3] = al; t.f[n - 2] = al; t.f[n - 1] = 0.0; t.c[n - 3] = 1.0; t.c[n - 2] = 1.0; t.c[n - 1] = 1.0;
+                        t.b[n - 3] = al; t.b[n - 2] = al + al; t.b[n - 1] = 0.0; }
+  else { t.f[n - 3] = al; t.f[n - 2] = c.fialm; t.f[n - 1] = 0.0; t.c[n - 3] = 1.0; t.c[n - 2] = 1.0; t.c[n - 1] = 1.0;
+         t.b[n - 3] = c.fialm; t.b[n - 2] = c.fialn; t.b[n - 1] = 0.0; }
+  p = factor(t);                       // prepare(fb, fc, ffp, fsp, fwp, n), :203
+  if (ncl1 == 1) t.f[0] = 0.0;         // :205-210
+  if (ncln == 1) t.b[n - 2] = 0.0;
+  plain = factor(t);                   // prepare(fb, fc, ff, fs, fw, n)
+}
+
 }  // namespace x3d

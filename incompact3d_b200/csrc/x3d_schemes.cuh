@@ -38,4 +38,7 @@ struct StretchY {
 };
 StretchY make_stretching(int istret, double beta, double yly, int ny, int nym);
 
+// set_filter_coefficients (src/filters.f90:62-219)
+void make_filter_axis(int n, int ncl1, int ncln, double af, x3d_filter_coeffs &c, LU3 &plain, LU3 &p);
+
 }  // namespace x3d

@@ -48,3 +48,19 @@ def test_product_schemes_match_reference_golden(golden_dir):
                 assert getattr(P.c, cn) == pytest.approx(v, rel=2e-15, abs=1e-300), (tag, nm)
                 n_checked += 1
     assert n_checked > 1000
+
+
+@pytest.mark.parametrize("bc", ["00", "11", "12", "21", "22"])
+@pytest.mark.parametrize("af", [0.45, 0.3, -0.1])
+@pytest.mark.parametrize("n", [12, 65])
+def test_product_filter_coefficients_match_oracle(bc, af, n):
+    """x3d_filter_axis (set_filter_coefficients, src/filters.f90:62-219) against the oracle, which is pinned to the
+    reference's statements by tests/golden/schemes.npz"""
+    P = AxisSchemes(n, int(bc[0]), int(bc[1]), 2.0)
+    O = ol.Axis(n, int(bc[0]), int(bc[1]), 2.0, af=af)
+    for p, names in ((False, ("fiff", "fifs", "fifw")), (True, ("fiffp", "fifsp", "fifwp"))):
+        c, lu = P.filter(af, p=p)
+        for name, _ in ol.FilterCoeffs._fields_:
+            assert getattr(c, name) == pytest.approx(getattr(O.fc, name), rel=1e-15, abs=1e-300), name
+        for g, nm in zip(lu, names):
+            np.testing.assert_allclose(g, O.arr(nm), rtol=4e-15, atol=1e-300, err_msg=nm)

@@ -20,10 +20,13 @@ sys.path.insert(0, ROOT)
 
 
 def parse(name):
-    """-> (family, axis letter, bc) ; family in d1, d2, dvp, ivp, dpv, ipv"""
+    """-> (family, axis letter, bc) ; family in d1, d2, fil, dvp, ivp, dpv, ipv"""
     m = re.match(r"^der([xyz])(\1?)_(\d\d)$", name)
     if m:
         return ("d2" if m.group(2) else "d1"), m.group(1), m.group(3)
+    m = re.match(r"^fil([xyz])_(\d\d)$", name)
+    if m:
+        return "fil", m.group(1), m.group(2)
     m = re.match(r"^(der|inter)([xyz])(vp|pv)$", name)
     return ("d" if m.group(1) == "der" else "i") + m.group(3), m.group(2), "00"
 
@@ -35,6 +38,11 @@ def call_op(x3d, A, name, fam, ax, u, t, dims, npaire):
     n, nm = A.n, A.nm
     p = "p" if npaire == 1 else ""
     fn = getattr(x3d, name)
+    if fam == "fil":
+        c, (f, s, w) = A.filter(0.45, p=(npaire == 1))
+        x3d.set_filter_coeffs(axis, c)
+        fn(t, u, None, None, f, s, w, nx, ny, nz, npaire, 0.0)
+        return
     if fam in ("d1", "d2"):
         f, s, w = A.lu(fam + p)
         if fam == "d1" and ax == "y":
