@@ -322,6 +322,11 @@ int x3d_schemes_axis(int n, int ncl1, int ncln, double len, int ifirstder, int i
 int x3d_filter_axis(int n, int ncl1, int ncln, double af, x3d_filter_coeffs *coeffs, int which, double *f, double *s,
                     double *w);
 
+/* stretching() (src/stretching.f90:96-318) likewise: out8 = yp, ypi, ppy, pp2y, pp4y, ppyi, pp2yi, pp4yi (ny entries
+ * each, what x3d_set_stretching takes), alpha = the mod_stret parameter x3d_poisson_init needs; istret 1, 2, 3;
+ * nym = ny - 1 with walls in y, ny when periodic                                                                  */
+int x3d_stretching(int istret, double beta, double yly, int ny, int nym, double *out8, double *alpha);
+
 #ifdef __cplusplus
 }
 #endif

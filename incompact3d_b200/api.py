@@ -211,6 +211,21 @@ class AxisSchemes:
         return c, (f, s, w)
 
 
+def stretching(istret, beta, yly, ny, nym):
+    """`stretching()` (src/stretching.f90:96-318) for hosts that are not the reference's Fortran: returns
+    ({yp, ypi, ppy, pp2y, pp4y, ppyi, pp2yi, pp4yi}, alpha).  Host-side, CPU only."""
+    L = _lib.load()
+    out = np.zeros(8 * int(ny))
+    alpha = C.c_double()
+    fn = L.x3d_stretching
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    if fn(int(istret), float(beta), float(yly), int(ny), int(nym), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(alpha)):
+        raise X3DError(L.x3d_last_error().decode())
+    names = ("yp", "ypi", "ppy", "pp2y", "pp4y", "ppyi", "pp2yi", "pp4yi")
+    return {nm: out[q * ny:(q + 1) * ny].copy() for q, nm in enumerate(names)}, alpha.value
+
+
 def _poisson_init(self, nx, ny, nz, bcx, bcy, bcz, xlx, yly, zlz, istret=0, alpha=0.0, beta=0.0):
     """decomp_2d_poisson_init (src/poisson.f90:73); nx,ny,nz are the velocity-mesh node counts"""
     p = _lib.PoissonParams(int(nx), int(ny), int(nz), int(bcx), int(bcy), int(bcz), float(xlx), float(yly), float(zlz),

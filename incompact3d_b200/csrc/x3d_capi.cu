@@ -411,6 +411,16 @@ int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean) {
 // ---- schemes() for non-Fortran hosts (src/schemes.f90); CPU only, no context needed -----------------
 // which: 0 first derivative (ff,fs,fw), 1 its p-variant, 2 second derivative, 3 p-variant, 4 cfx6.., 5 cfxp6..,
 //        6 cifx6.., 7 cifxp6.., 8 cfi6.., 9 cfip6.., 10 cifi6.., 11 cifip6..
+int x3d_stretching(int istret, double beta, double yly, int ny, int nym, double *out8, double *alpha) {
+  return guard([&] {
+    if (istret < 1 || istret > 3 || ny < 3 || !out8) throw Error("x3d_stretching: bad argument");
+    const StretchY S = make_stretching(istret, beta, yly, ny, nym);
+    const std::vector<double> *v[8] = {&S.yp, &S.ypi, &S.ppy, &S.pp2y, &S.pp4y, &S.ppyi, &S.pp2yi, &S.pp4yi};
+    for (int q = 0; q < 8; ++q) std::copy(v[q]->begin(), v[q]->begin() + ny, out8 + static_cast<size_t>(q) * ny);
+    if (alpha) *alpha = S.alpha;
+  });
+}
+
 int x3d_filter_axis(int n, int ncl1, int ncln, double af, x3d_filter_coeffs *coeffs, int which, double *f, double *s, double *w) {
   return guard([&] {
     if (which < 0 || which > 1) throw Error("x3d_filter_axis: bad selector");

@@ -64,3 +64,22 @@ def test_product_filter_coefficients_match_oracle(bc, af, n):
             assert getattr(c, name) == pytest.approx(getattr(O.fc, name), rel=1e-15, abs=1e-300), name
         for g, nm in zip(lu, names):
             np.testing.assert_allclose(g, O.arr(nm), rtol=4e-15, atol=1e-300, err_msg=nm)
+
+
+@pytest.mark.parametrize("istret", [1, 2, 3])
+@pytest.mark.parametrize("ny,nym", [(65, 64), (129, 128), (64, 64)])
+def test_product_stretching_matches_oracle(istret, ny, nym):
+    """x3d_stretching (stretching(), src/stretching.f90:96-318) against the oracle, which tests/golden/poisson.npz pins
+    to the reference's statements"""
+    import ctypes as C
+    from incompact3d_b200 import stretching
+    got, alpha = stretching(istret, 0.259065151, 2.0, ny, nym)
+    L = ol.lib()
+    dp = C.POINTER(C.c_double)
+    L.x3do_stretching.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+    ref = np.zeros(8 * ny)
+    ra = C.c_double()
+    assert L.x3do_stretching(istret, 0.259065151, 2.0, ny, nym, ref.ctypes.data_as(dp), C.byref(ra)) == 0
+    for q, nm in enumerate(("yp", "ypi", "ppy", "pp2y", "pp4y", "ppyi", "pp2yi", "pp4yi")):
+        np.testing.assert_allclose(got[nm], ref[q * ny:(q + 1) * ny], rtol=2e-15, atol=1e-300, err_msg=nm)
+    assert alpha == pytest.approx(ra.value, rel=1e-15)
