@@ -2,14 +2,22 @@
 """bench.py -- TGV grid-point-steps/s of the B200-native Xcompact3d hot path.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W     # CPU reference arm (oracle port)
+    python bench.py --impl reference --steps K --warmup W     # CPU reference arm (oracle port), SAME configuration
 
 A "step" is one full RK3 time step (3 sub-steps: momentum RHS -> intt -> pre_correc ->
 divergence -> spectral Poisson -> gradp -> cor_vel) of the periodic Taylor-Green vortex,
 Re=1600, on 512^3 nodes (BASELINE.json configs[1]).  Synthetic data: the analytic TGV field.
-`value` times the device-resident solver (fields in HBM); `e2e` drives the same step through
-the C ABI with HOST (pinned) velocity arrays, H2D + D2H inside the timed region.
-Prints ONE JSON line (rank 0).
+
+  value     device-resident solver (fields in HBM), CUDA events on the library's stream, max over ranks
+  e2e       the same step as host jobs through the C ABI (x3d_solver_advance_host): every step's 3 velocity arrays
+            are copied H2D from pinned host memory and the result D2H inside the timed region; consecutive jobs are
+            independent (three host-resident ensemble members advanced in turn), so the copies of neighbouring jobs
+            overlap the kernels.  `e2e.serial` is the strictly serial H2D -> step -> D2H figure.
+  parity    after the timed region the GPU solver (same rank layout) and the CPU oracle are stepped from the same
+            TGV state at --parity-n^3 and compared (max|du|/max|u|, diagnostics); the run FAILS above 1e-11.
+  roofline  the kernel class with the largest share of the step (per-launch CUDA events, one instrumented step)
+  nvlink    N > 1: bytes each GPU sends to its peers per step through the transposes / their device time
+Prints ONE JSON line (rank 0).  Other cases: --case channel (BASELINE configs[2], 256x129x128 stretched).
 """
 from __future__ import annotations
 
@@ -26,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "TGV grid-point-steps/sec"
 UNIT = "grid-point-steps/s"
+PARITY_TOL = 1e-11
 
 
 def parse():
@@ -34,11 +43,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--case", default="tgv", choices=["tgv", "channel"])
     ap.add_argument("--n", type=int, default=512, help="nodes per direction (periodic TGV)")
-    ap.add_argument("--cpu-n", type=int, default=256, help="box size of the bounded CPU sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-n", type=int, default=256, help="box size of the in-bench GPU-vs-oracle parity run (also the "
+                    "bounded CPU sample of cpu_baseline)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock budget of the reference arm's timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (parity + cpu_baseline)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+def host_threads():
+    """cores this process may use -- NOT $OMP_NUM_THREADS (torch.distributed.run exports OMP_NUM_THREADS=1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------------------------------
@@ -92,58 +112,147 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(n, steps, warmup):
-    """time the oracle port (C++/OpenMP restatement of the reference step) on the host cores"""
-    import ctypes as C
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as ol
+# workloads
+def workload(args):
     import numpy as np
-    L = ol.lib()
-    L.x3do_solver_create.restype = C.c_void_p
-    L.x3do_solver_create.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] + [C.c_double] * 5 + [C.c_int] * 5 + [C.c_double]
-    length = 2 * np.pi
-    dt = 0.005 * 64.0 / n  # CFL kept as the mesh is refined (SURVEY 8d)
-    s = L.x3do_solver_create(n, n, n, (C.c_int * 6)(0, 0, 0, 0, 0, 0), length, length, length, 1600.0, dt, 5, 4, 4, 3, 0, 0.0)
-    if not s:
-        raise RuntimeError(L.x3do_last_error().decode())
-    s = C.c_void_p(s)
-    L.x3do_solver_init_tgv(s)
-    for _ in range(warmup):
-        L.x3do_solver_step(s, 1)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        L.x3do_solver_step(s, 1)
-    dtw = time.perf_counter() - t0
-    out = (C.c_double * 4)()
-    L.x3do_solver_postprocess_tgv(s, out)
-    L.x3do_solver_destroy(s)
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return dict(value=n ** 3 * steps / dtw, seconds=dtw, cores=cores, eek=out[0])
+    if args.case == "tgv":
+        n = args.n
+        length = 2 * np.pi
+        return dict(name=f"TGV periodic {n}^3 Re=1600 RK3 dt={0.005 * 64.0 / n:g} (BASELINE configs[1])", dims=(n, n, n), ncl=(0,) * 6,
+                    lens=(length,) * 3, re=1600.0, dt=0.005 * 64.0 / n, itimescheme=5, isecondder=4, istret=0, beta=0.0, itype=0)
+    # BASELINE configs[2]: channel Re_tau=180, 256x129x128, stretched y (examples/Channel/input_DNS_Re180_LR_explicittime.i3d x2)
+    return dict(name="Channel 256x129x128 istret=2 beta=0.259065151 Re=4200 RK3 dt=0.005 isecondder=5, constant flow rate (BASELINE configs[2])",
+                dims=(256, 129, 128), ncl=(0, 0, 2, 2, 0, 0), lens=(8.0, 2.0, 4.0), re=4200.0, dt=0.005, itimescheme=5, isecondder=5,
+                istret=2, beta=0.259065151, itype=3)
+
+
+class Oracle:
+    """the CPU restatement of the reference step (oracle/, C++/OpenMP) -- the checker and the CPU baseline"""
+
+    def __init__(self, w, dims=None):
+        import ctypes as C
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        self.C = C
+        self.L = L = ol.lib()
+        L.x3do_set_threads.argtypes = [C.c_int]
+        self.cores = L.x3do_set_threads(host_threads())
+        nx, ny, nz = dims or w["dims"]
+        self.dims = (nx, ny, nz)
+        L.x3do_solver_create_case.restype = C.c_void_p
+        L.x3do_solver_create_case.argtypes = ([C.c_int] * 3 + [C.POINTER(C.c_int)] + [C.c_double] * 5 + [C.c_int] * 5 + [C.c_double]
+                                              + [C.c_int, C.c_double, C.c_double])
+        s = L.x3do_solver_create_case(nx, ny, nz, (C.c_int * 6)(*w["ncl"]), *[float(v) for v in w["lens"]], float(w["re"]), float(w["dt"]),
+                                      w["itimescheme"], 4, w["isecondder"], 3, w["istret"], float(w["beta"]), w["itype"], 4.0, 0.44)
+        if not s:
+            raise RuntimeError(L.x3do_last_error().decode())
+        self.s = C.c_void_p(s)
+        self.itype = w["itype"]
+
+    def init(self):
+        if self.itype == 3:
+            self.L.x3do_solver_init_channel(self.s)
+        else:
+            self.L.x3do_solver_init_tgv(self.s)
+
+    def step(self, k=1):
+        if self.L.x3do_solver_step(self.s, k):
+            raise RuntimeError(self.L.x3do_last_error().decode())
+
+    def velocity(self):
+        import numpy as np
+        dp = self.C.POINTER(self.C.c_double)
+        out = [np.zeros(self.dims, order="F") for _ in range(3)]
+        self.L.x3do_solver_get_velocity(self.s, *[a.ctypes.data_as(dp) for a in out])
+        return out
+
+    def diagnostics(self):
+        out = (self.C.c_double * 4)()
+        self.L.x3do_solver_postprocess_tgv(self.s, out)
+        return dict(eek=out[0], eps=out[1], eps2=out[2], enst=out[3])
+
+    def close(self):
+        self.L.x3do_solver_destroy(self.s)
+
+
+ORACLE_WHAT = ("oracle C++/OpenMP restatement of the reference step (the Fortran/MPI build cannot be built on this image: no Fortran "
+               "compiler, no MPI, 2DECOMP&FFT un-vendored)")
 
 
 def run_reference(args):
+    """the reference's CPU implementation of the path, all host cores, SAME workload as the GPU arm; every timed step is
+    a full step of that workload, the number of timed steps is bounded by --ref-budget-s"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_n
-    steps, warmup = args.steps, args.warmup
-    r = cpu_reference_run(n, steps, warmup)
-    sample = (f"periodic TGV {n}^3 (same Re, RK3, CFL-scaled dt), {steps} full RK3 steps after {warmup} warm-up, "
-              f"oracle C++/OpenMP restatement of the reference step (the Fortran/MPI build cannot be built here: "
-              f"no Fortran compiler, no MPI, 2DECOMP&FFT un-vendored)")
+    w = workload(args)
+    o = Oracle(w)
+    o.init()
+    t0 = time.perf_counter()
+    o.step(1)                                   # warm-up (first touch of every array)
+    t_warm = time.perf_counter() - t0
+    steps = int(max(1, min(args.steps, (args.ref_budget_s - t_warm) // max(t_warm, 1e-9))))
+    t0 = time.perf_counter()
+    o.step(steps)
+    dtw = time.perf_counter() - t0
+    diag = o.diagnostics() if w["itype"] == 0 else None
+    o.close()
+    npts = w["dims"][0] * w["dims"][1] * w["dims"][2]
+    value = npts * steps / dtw
+    sample = (f"{w['name']}: {steps} full steps timed after 1 warm-up step ({dtw:.1f} s; --steps {args.steps} capped by the "
+              f"{args.ref_budget_s:.0f} s budget), {o.cores} OpenMP threads; {ORACLE_WHAT}")
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "steps_requested": args.steps, "ms_per_step": 1e3 * dtw / steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TGV periodic {args.n}^3 Re=1600 RK3 (BASELINE configs[1]); CPU arm runs a bounded {n}^3 sample"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "config": {"workload": w["name"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": o.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "diagnostics_after_run": diag,
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
+def alg_bytes(name, npts, nsp):
+    """ALGORITHMIC bytes of one launch of a kernel class: npts = local grid points,
+    nsp = local complex spectral modes"""
+    if name.startswith("compact_"):
+        return 16.0 * npts                      # read u, write t
+    if name.startswith("accumulate_"):
+        return 24.0 * npts                      # read u, read-modify-write t
+    if name.startswith("momentum_fused"):
+        return (48.0 + (96.0 if "+intt" in name else 0.0)) * npts   # 3 velocities in, 3 results out (+ intt: 6 in, 6 out)
+    if name.startswith("elementwise"):
+        return 104.0 * npts                     # intt of RK3: 13 array passes on average over the sub-steps
+    if name.startswith("fft_z"):
+        return 8.0 * npts + 16.0 * nsp
+    if name.startswith("fft_xy") or name.startswith("poisson_spectral"):
+        return 32.0 * nsp
+    if name.startswith("transpose"):
+        return 16.0 * npts
+    return None
+
+
+def make_solver(X3D, local, w, dims, world, rank, dist, nccl_unique_id):
+    x = X3D(local)
+    nx, ny, nz = dims
+    if world > 1:
+        # 2-D pencil decomposition with p_row=1, p_col=N (slabs): on NVSwitch every byte costs the same
+        # whichever peer it goes to, and 1xN moves the fewest bytes (x<->y transposes become local)
+        obj = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        x.decomp_init(nx, ny, nz, 1, world, rank, world, obj[0])
+    x.solver_init(nx, ny, nz, ncl=w["ncl"], xlx=w["lens"][0], yly=w["lens"][1], zlz=w["lens"][2], re=w["re"], dt=w["dt"],
+                  itimescheme=w["itimescheme"], isecondder=w["isecondder"], istret=w["istret"], beta=w["beta"], itype=w["itype"],
+                  p_row=1, p_col=world)
+    if w["itype"] == 3:
+        x.solver_init_channel()
+    else:
+        x.solver_init_tgv()
+    return x
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -157,23 +266,21 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
-    from incompact3d_b200 import X3D
+    from incompact3d_b200 import X3D, nccl_unique_id
 
-    n = args.n
-    length = 2 * np.pi
-    dt = 0.005 * 64.0 / n
-    x = X3D(local)
-    if world > 1:
-        # 2-D pencil decomposition with p_row=1, p_col=N (slabs): on NVSwitch every byte costs the same
-        # whichever peer it goes to, and 1xN moves the fewest bytes (x<->y transposes become local)
-        from incompact3d_b200 import nccl_unique_id
-        obj = [nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        x.decomp_init(n, n, n, 1, world, rank, world, obj[0])
-    x.solver_init(n, n, n, ncl=(0,) * 6, xlx=length, yly=length, zlz=length, re=1600.0, dt=dt, p_row=1, p_col=world)
-    x.solver_init_tgv()
+    w = workload(args)
+    nx, ny, nz = w["dims"]
+    npts = nx * ny * nz
+
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    x = make_solver(X3D, local, w, w["dims"], world, rank, dist, nccl_unique_id)
     stream = torch.cuda.ExternalStream(x.stream)
-    npts = n ** 3
 
     def barrier():
         x.sync()
@@ -181,12 +288,20 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    # ---- N > 1: the production transposes (peer stores over NVLink between library-owned pencils, every copy mode)
+    #      checked bit for bit on the decomposition of this run before anything is timed
+    bit_exact = None
+    if world > 1:
+        bad = x.transpose_selftest()
+        bit_exact = allmax(bad) == 0.0
+
     for _ in range(args.warmup):
         x.solver_step(1)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
     l0 = x.launch_count
+    b0 = x.decomp_stats()[0] if world > 1 else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -194,92 +309,171 @@ def run_b200(args):
     e1.record(stream)
     e1.synchronize()
     barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:  # device time, max over ranks
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = allmax(e0.elapsed_time(e1))   # device time, max over ranks
     launches = x.launch_count - l0
+    nv_bytes = (x.decomp_stats()[0] - b0) / args.steps if world > 1 else 0
     clk = clocks.stop()
     value = npts * args.steps / (ms * 1e-3)
-    diag = x.solver_diagnostics_tgv()
+    diag = x.solver_diagnostics_tgv() if w["itype"] == 0 else None
 
-    # ---- roofline of the dominant kernel, timed live in one extra instrumented step -------------
-    roof = x.profile_step() if hasattr(x, "profile_step") else None
+    # ---- roofline of the dominant kernel class, timed live in one extra instrumented step -------------
+    roof = x.profile_step()
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = None
-    if roof:
-        comp = [r for r in roof if r["name"].startswith("compact_")]
-        k = max(comp, key=lambda r: r["total_ms"])
-        achieved = 16.0 * (npts / world) / (k["avg_ms"] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel class at 512^3 on one GPU, from the
-        # `ncu --set full` capture summarised in profiles/r1f_ops_ncu_summary.txt (k_pair: 1.0738 GB + 1.0290 GB;
-        # k_contig: 1.0739 + 1.0279).  It equals the algorithmic 2 x 8 B x 512^3 = 2.147 GB to within the write-back
-        # still in L2 at kernel end: no re-reads.
-        traffic = 2.1029e9 if (n == 512 and world == 1) else None
-        roofline = {"bound": "hbm", "kernel": k["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "ncu --set full, profiles/r1f_ops_ncu_summary.txt" if traffic else None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
-                    "algorithmic_bytes_per_launch": 16.0 * npts / world,
-                    "note": "dominant compact-operator kernel class; 16 B per output point (SURVEY 8d); per-launch CUDA events "
-                            "on the launching stream during one extra instrumented step", "launches_per_step": k["count"],
-                    "share_of_step": k["total_ms"] / sum(r["total_ms"] for r in roof),
-                    "classes": roof}
+    nzl = x._solver_shape[2]
+    npl = nx * ny * max(nzl, 0)
+    nspl = nx * ny * (nz // 2 + 1) / world
+    for r in roof:
+        ab = alg_bytes(r["name"], npl, nspl)
+        r["alg_bytes_per_launch"] = ab
+        r["frac_of_hbm_peak"] = (ab / (r["avg_ms"] * 1e-3) / 1e9 / peak) if (ab and r["avg_ms"] > 0 and not r["name"].startswith("transpose_p2p")) else None
+    tot_ms = sum(r["total_ms"] for r in roof)
+    cand = [r for r in roof if not r["name"].startswith("transpose_p2p") and r["alg_bytes_per_launch"]]
+    k = max(cand, key=lambda r: r["total_ms"])
+    achieved = k["alg_bytes_per_launch"] / (k["avg_ms"] * 1e-3) / 1e9
+    traffic, tsrc = None, None
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tj) and world == 1 and args.case == "tgv":
+        T = json.load(open(tj))
+        ent = T.get("classes", {}).get(k["name"])
+        if ent and T.get("n") == args.n:
+            traffic, tsrc = ent["dram_bytes_per_launch"], f"profiles/ncu_traffic.json ({T.get('source')})"
+    roofline = {"bound": "hbm", "kernel": k["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": k["alg_bytes_per_launch"],
+                "note": "kernel class with the largest share of the step (all classes considered); algorithmic bytes per class from "
+                        "DESIGN.md section 4; per-launch CUDA events on the launching stream during one extra instrumented step",
+                "launches_per_step": k["count"], "share_of_step": k["total_ms"] / tot_ms, "classes": roof}
+    nvlink = None
+    if world > 1:
+        tms = sum(r["total_ms"] for r in roof if r["name"].startswith("transpose_"))
+        gbs = nv_bytes / (tms * 1e-3) / 1e9 if tms > 0 else None
+        nvlink = {"bytes_per_gpu_per_step": nv_bytes, "ms": tms, "gbs_per_direction": gbs, "frac_of_900": gbs / 900.0 if gbs else None,
+                  "share_of_step": tms / tot_ms,
+                  "note": "bytes each GPU stores into its peers' pencils per step (transposes) / device time of the transpose scopes "
+                          "(between their two flag barriers) in the instrumented step; 900 GB/s = NVLink 5 per direction"}
 
-    # ---- e2e: the same step driven with HOST velocity arrays through the C ABI -------------------------
+    # ---- e2e: host jobs through the C ABI, H2D + D2H of every step inside the timed region ---------------------
     e2e = None
     if not args.no_e2e:
-        nzl = x._solver_shape[2]
-        hu, hv, hw = (torch.empty((max(nzl, 1), n, n), dtype=torch.float64).pin_memory() for _ in range(3))
-        x.solver_get_velocity(hu, hv, hw)
-        k2 = max(2, min(args.steps, 5))
-        for _ in range(1):
-            x.solver_set_velocity(hu, hv, hw); x.solver_step(1); x.solver_get_velocity(hu, hv, hw)
+        shape = (max(nzl, 1), ny, nx)
+        sets = [[torch.empty(shape, dtype=torch.float64).pin_memory() for _ in range(3)] for _ in range(3)]
+        x.solver_get_velocity(*sets[0])
+        for s in sets[1:]:
+            for a, b in zip(s, sets[0]):
+                a.copy_(b)
+        # strictly serial: H2D -> step -> D2H, one job at a time
+        x.solver_set_velocity(*sets[0]); x.solver_step(1); x.solver_get_velocity(*sets[0])
+        barrier()
+        ks = 2
+        t0 = time.perf_counter()
+        for _ in range(ks):
+            x.solver_set_velocity(*sets[0])
+            x.solver_step(1)
+            x.solver_get_velocity(*sets[0])
+        barrier()
+        t_serial = allmax(time.perf_counter() - t0) / ks
+        # pipelined: three host-resident members advanced in turn, copies overlap the neighbouring jobs' kernels
+        k2 = max(6, min(args.steps, 12))
+        for j in range(3):
+            x.solver_advance_host(sets[j % 3], sets[j % 3], 1)
+        x.solver_host_sync()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(k2):
-            x.solver_set_velocity(hu, hv, hw)   # H2D of the step's inputs (pinned host memory)
-            x.solver_step(1)
-            x.solver_get_velocity(hu, hv, hw)   # D2H of the step's result
+        for j in range(k2):
+            x.solver_advance_host(sets[j % 3], sets[j % 3], 1)
+        x.solver_host_sync()
         barrier()
-        te = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([te], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            te = float(t.item())
+        te = allmax(time.perf_counter() - t0)
         e2e = {"value": npts * k2 / te, "unit": UNIT, "h2d_bytes_per_step": 3 * npts * 8, "d2h_bytes_per_step": 3 * npts * 8,
-               "steps": k2, "note": "x3d_solver_set_velocity(host) + x3d_solver_step + x3d_solver_get_velocity(host) per step"}
+               "steps": k2, "ms_per_step": 1e3 * te / k2,
+               "serial": {"value": npts / t_serial, "ms_per_step": 1e3 * t_serial,
+                          "note": "x3d_solver_set_velocity(host) + x3d_solver_step + x3d_solver_get_velocity(host), one after the other"},
+               "note": "x3d_solver_advance_host(host in, host out) per step: H2D of the step's three velocity arrays from pinned host memory, "
+                       "the step, D2H of the result, all inside the timed region; three host-resident ensemble members are advanced in "
+                       "turn (job j reads and writes member j mod 3), so the copies run on their own streams beside the kernels of the "
+                       "neighbouring jobs; wall clock between barriers, max over ranks"}
+        del sets
+    x.close()
 
-    cpu = None
-    if not args.no_cpu_baseline and rank == 0:
-        try:
-            steps_cpu = 4
-            r = cpu_reference_run(args.cpu_n, steps_cpu, 1)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                   "sample": f"periodic TGV {args.cpu_n}^3, {steps_cpu} RK3 steps after 1 warm-up ({r['seconds']:.1f} s), oracle "
-                             f"C++/OpenMP restatement of the reference step (no Fortran/MPI toolchain on the box)"}
-        except Exception as e:  # the baseline is reported, never fatal
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    # ---- parity + cpu_baseline: GPU solver (same rank layout) vs the oracle from the same state, bounded size ----
+    parity, cpu = None, None
+    if not args.no_cpu_baseline:
+        pd = (args.parity_n,) * 3 if args.case == "tgv" else w["dims"]
+        wp = dict(w)
+        if args.case == "tgv":
+            wp["dt"] = 0.005 * 64.0 / args.parity_n
+        nps = 3
+        xp = make_solver(X3D, local, wp, pd, world, rank, dist, nccl_unique_id)
+        xp.solver_step(nps)
+        gu = xp.solver_get_velocity()
+        gd = xp.solver_diagnostics_tgv() if w["itype"] == 0 else {}
+        z0, nzlp = xp.solver_zstart, xp._solver_shape[2]
+        xp.close()
+        ref = [torch.empty((pd[2], pd[1], pd[0]), dtype=torch.float64, device="cuda") for _ in range(3)]
+        rd = torch.zeros(4, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            try:
+                o = Oracle(wp, pd)
+                o.init()
+                t0 = time.perf_counter(); o.step(1); t1 = time.perf_counter()
+                o.step(nps - 1)
+                t2 = time.perf_counter()
+                for r_, a in zip(ref, o.velocity()):
+                    r_.copy_(torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))))
+                if w["itype"] == 0:
+                    od = o.diagnostics()
+                    rd.copy_(torch.tensor([od["eek"], od["eps"], od["eps2"], od["enst"]], dtype=torch.float64))
+                o.close()
+                pn = pd[0] * pd[1] * pd[2]
+                cpu = {"value": pn * (nps - 1) / (t2 - t1), "unit": UNIT, "cores": o.cores, "kind": "port",
+                       "sample": f"{wp['name'] if args.case != 'tgv' else f'periodic TGV {args.parity_n}^3 (same Re, RK3, CFL-scaled dt)'}: "
+                                 f"{nps - 1} full steps timed ({t2 - t1:.1f} s) after 1 warm-up step ({t1 - t0:.1f} s), {o.cores} OpenMP threads; "
+                                 f"{ORACLE_WHAT}.  The reference arm (--impl reference) times the full-size workload."}
+            except Exception as e:  # the baseline is reported, never fatal; parity then stays unproven
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        if world > 1:
+            for r_ in ref:
+                dist.broadcast(r_, src=0)
+            dist.broadcast(rd, src=0)
+        scale = max(float(r_.abs().max()) for r_ in ref)
+        err = 0.0
+        if nzlp > 0 and scale > 0:
+            for g, r_ in zip(gu, ref):
+                gt = torch.from_numpy(np.ascontiguousarray(g.transpose(2, 1, 0))).cuda()
+                err = max(err, float((gt - r_[z0:z0 + nzlp]).abs().max()) / scale)
+        err = allmax(err)
+        drel = None
+        if w["itype"] == 0 and scale > 0:
+            got = np.array([gd["eek"], gd["eps"], gd["eps2"], gd["enst"]])
+            drel = float(np.abs(got / rd.cpu().numpy() - 1).max())
+        ok = scale > 0 and err < PARITY_TOL and (drel is None or drel < 1e-9) and (not gd or abs(gd["divmax"]) < 1e-10)
+        parity = {"workload": f"{pd[0]}x{pd[1]}x{pd[2]} {args.case}, {nps} steps from the initial field, GPU solver on {world} rank(s) vs the CPU oracle",
+                  "max_du_over_max_u": err, "tol": PARITY_TOL, "diagnostics_rel_err": drel, "gpu_divmax": gd.get("divmax") if gd else None,
+                  "ok": bool(ok)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TGV periodic {n}^3 Re=1600 RK3 dt={dt:g} (BASELINE configs[1])",
-                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), transposes = one kernel storing into peer pencils over NVLink (CUDA IPC), device-side flag barriers"), "l2": "fields are 1 GiB each, far larger than the 126 MB L2; no flush needed",
+        "config": {"workload": w["name"],
+                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), transposes = peer stores into the owners' pencils over NVLink (CUDA IPC) between device-side flag barriers"),
+                   "l2": "fields are far larger than the 126 MB L2 (1 GiB each at 512^3); no flush needed" if npts >= 2 ** 26 else "fields fit the 126 MB L2: an L2-resident, launch-bound configuration",
                    "diagnostics_after_run": diag},
-        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "transposes_bit_exact": bit_exact, "nvlink": nvlink,
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
-    x.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if (parity and not parity["ok"]) or bit_exact is False:
+        sys.exit(3)
 
 
 def main():

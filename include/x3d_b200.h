@@ -240,6 +240,14 @@ int x3d_decomp_init(x3d_ctx *ctx, int nx, int ny, int nz, int p_row, int p_col,
 int x3d_nccl_unique_id(void *out128);
 int x3d_decomp_info_init(x3d_ctx *ctx, int nx, int ny, int nz, int *decomp_id);
 int x3d_decomp_info_get(x3d_ctx *ctx, int decomp_id, x3d_decomp_info *out);
+/* traffic counters since x3d_decomp_init: bytes this rank sent to OTHER ranks through transposes (what crosses
+ * NVLink), and the number of transposed fields                                                              */
+int x3d_decomp_stats(x3d_ctx *ctx, unsigned long long *remote_bytes, unsigned long long *fields);
+/* Self-test of the data plane the device solver uses (collective: every rank calls it): a library-owned source pencil
+ * is filled with the global index of each element, transposed (which: 0 x->y, 1 y->z, 2 z->y, 3 y->x) through the
+ * peer-to-peer path (mode -1: as the solver would; 0 element kernel, 1 copy engines, 2 vector-copy kernel) and the
+ * destination is compared, on the device, with the indices it must hold.  *mismatches = 0 <=> bit-exact.        */
+int x3d_transpose_selftest(x3d_ctx *ctx, int which, int decomp_id, int complex_, int mode, long long *mismatches);
 /* transpose_x_to_y etc. (call sites src/transeq.f90:163,236,318,437); the
  * complex variants are used on the spectral decomposition sp
  * (src/poisson.f90:759).  Bit-exact data movement.                           */
@@ -304,6 +312,15 @@ int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz);
 int x3d_solver_local_shape(x3d_ctx *ctx, int *dims3, int *zstart0);
 /* advance nsteps full time steps (iadvance_time sub-steps each) */
 int x3d_solver_step(x3d_ctx *ctx, int nsteps);
+/* One asynchronous job: copy the host x-pencil velocity (ux_in, uy_in, uz_in) to the device, advance it nsteps time
+ * steps, copy the result to (ux_out, uy_out, uz_out).  Returns once the work is queued; x3d_solver_host_sync waits for
+ * every queued job.  Consecutive jobs are independent of each other (ensemble members, parameter sweeps; the reference
+ * would run them as separate MPI jobs, src/xcompact3d.f90:29-102 each), so the H2D copy of the next job and the D2H
+ * copy of the previous one run on their own streams beside the kernels of the current one.  Host arrays should be
+ * page-locked.  For self-starting schemes (itimescheme 1 and 5): Adams-Bashforth history is not part of a job.   */
+int x3d_solver_advance_host(x3d_ctx *ctx, const double *ux_in, const double *uy_in, const double *uz_in,
+                            double *ux_out, double *uy_out, double *uz_out, int nsteps);
+int x3d_solver_host_sync(x3d_ctx *ctx);
 /* out5 = (eek, eps, eps2, enst, divmax) as postprocess_tgv writes them      */
 int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5);
 /* DIV U max / mean of the current velocity (divergence nlock=2)             */

@@ -413,6 +413,43 @@ def _solver_get_velocity(self, ux=None, uy=None, uz=None):
     return ux, uy, uz
 
 
+def _solver_advance_host(self, vin, vout, nsteps=1):
+    """queue one job: H2D of the host velocity `vin` (3 arrays), nsteps time steps, D2H into `vout`; asynchronous"""
+    keep = []
+    fn = self._L.x3d_solver_advance_host
+    fn.argtypes = [C.c_void_p] * 7 + [C.c_int]
+    self._check(fn(self._h, *[_addr(a, keep) for a in vin], *[_addr(a, keep) for a in vout], int(nsteps)))
+
+
+def _decomp_stats(self):
+    """-> (bytes sent to other ranks by transposes since decomp_init, transposed fields)"""
+    a, b = C.c_ulonglong(), C.c_ulonglong()
+    fn = self._L.x3d_decomp_stats
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    self._check(fn(self._h, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _transpose_selftest(self, decomp_id=0, whiches=(0, 1, 2, 3), modes=(-1, 0, 1, 2)):
+    """bit-exactness of the production transposes between library-owned pencils (collective); -> number of wrong elements"""
+    fn = self._L.x3d_transpose_selftest
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    bad = 0
+    for which in whiches:
+        for cplx in (0, 1):
+            for mode in modes:
+                m = C.c_longlong()
+                self._check(fn(self._h, int(which), int(decomp_id), cplx, int(mode), C.byref(m)))
+                bad += m.value
+    return bad
+
+
+def _solver_host_sync(self):
+    fn = self._L.x3d_solver_host_sync
+    fn.argtypes = [C.c_void_p]
+    self._check(fn(self._h))
+
+
 def _profile_step(self, nsteps=1):
     """run `nsteps` solver steps with per-launch CUDA-event timing; -> list of kernel classes"""
     import json
@@ -450,6 +487,10 @@ X3D.solver_diagnostics_tgv = _solver_diag
 X3D.solver_divergence = _solver_divergence
 X3D.solver_set_velocity = _solver_set_velocity
 X3D.solver_get_velocity = _solver_get_velocity
+X3D.solver_advance_host = _solver_advance_host
+X3D.solver_host_sync = _solver_host_sync
+X3D.decomp_stats = _decomp_stats
+X3D.transpose_selftest = _transpose_selftest
 
 
 # ---------------------------------------------------------------------------------------

@@ -25,6 +25,10 @@ void solver_divergence(Ctx &ctx, double *divmax, double *divmean);
 void solver_set_velocity(Ctx &ctx, const double *ux, const double *uy, const double *uz);
 void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz);
 void solver_local_shape(Ctx &ctx, int *d3, int *z0);
+void solver_advance_host(Ctx &ctx, const double *const in[3], double *const out[3], int nsteps);
+void solver_host_sync(Ctx &ctx);
+long long transpose_selftest(Ctx &ctx, int which, int id, int elem, int mode);
+void decomp_stats(Ctx &ctx, unsigned long long *remote_bytes, unsigned long long *fields);
 void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id);
 int decomp_info_init(Ctx &ctx, int nx, int ny, int nz);
 void decomp_info_get(Ctx &ctx, int id, x3d_decomp_info *out);
@@ -402,6 +406,21 @@ int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz) {
 int x3d_solver_local_shape(x3d_ctx *ctx, int *dims3, int *zstart0) {
   return guard([&] { solver_local_shape(ctx->c, dims3, zstart0); });
 }
+int x3d_solver_advance_host(x3d_ctx *ctx, const double *ux_in, const double *uy_in, const double *uz_in, double *ux_out,
+                            double *uy_out, double *uz_out, int nsteps) {
+  return guard([&] {
+    const double *in[3] = {ux_in, uy_in, uz_in};
+    double *out[3] = {ux_out, uy_out, uz_out};
+    solver_advance_host(ctx->c, in, out, nsteps);
+  });
+}
+int x3d_transpose_selftest(x3d_ctx *ctx, int which, int decomp_id, int complex_, int mode, long long *mismatches) {
+  return guard([&] { *mismatches = transpose_selftest(ctx->c, which, decomp_id, complex_ ? 2 : 1, mode); });
+}
+int x3d_decomp_stats(x3d_ctx *ctx, unsigned long long *remote_bytes, unsigned long long *fields) {
+  return guard([&] { decomp_stats(ctx->c, remote_bytes, fields); });
+}
+int x3d_solver_host_sync(x3d_ctx *ctx) { return guard([&] { solver_host_sync(ctx->c); }); }
 int x3d_solver_step(x3d_ctx *ctx, int nsteps) { return guard([&] { solver_step(ctx->c, nsteps); }); }
 int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5) { return guard([&] { solver_diagnostics_tgv(ctx->c, out5); }); }
 int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean) {

@@ -120,7 +120,10 @@ struct DecompImpl : DecompState {
   int p2p_mode = -1;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // bytes this rank sent to OTHER members (what crosses NVLink) and transposed fields, since x3d_decomp_init
+  unsigned long long stat_remote_bytes = 0, stat_fields = 0;
   DevBuf xchg_send, xchg_recv;
+  DevBuf self_src, self_dst, self_cnt;   // x3d_transpose_selftest
   std::map<std::array<unsigned char, 64>, void *> ipc_opened;
   ~DecompImpl() override {
     for (auto &kv : ipc_opened) cudaIpcCloseMemHandle(kv.second);
@@ -600,10 +603,26 @@ static void run_block_copies(Ctx &ctx, DecompImpl &D, const BlockCopies &bc, int
   ctx.launches++;
 }
 
+static void count_traffic(DecompImpl &D, const TransposePlan &T, int which, int elem, int nf) {
+  const int me = (which == 0 || which == 3) ? D.row : D.col;
+  unsigned long long b = 0;
+  for (int m = 0; m < T.npeers; ++m)
+    if (m != me) b += static_cast<unsigned long long>(T.send.count[m]) * elem * sizeof(double);
+  D.stat_remote_bytes += b * nf;
+  D.stat_fields += nf;
+}
+
+void decomp_stats(Ctx &ctx, unsigned long long *remote_bytes, unsigned long long *fields) {
+  DecompImpl &D = DEC(ctx);
+  *remote_bytes = D.stat_remote_bytes;
+  *fields = D.stat_fields;
+}
+
 // device pointers; src and dst pencils of decomposition `id`
 void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem) {
   DecompImpl &D = DEC(ctx);
   TransposePlan &T = get_plan(ctx, D, id, which);
+  count_traffic(D, T, which, elem, 1);
   const long long ns = static_cast<long long>(T.send.dims[0]) * T.send.dims[1] * T.send.dims[2];
   const long long nr = static_cast<long long>(T.recv.dims[0]) * T.recv.dims[1] * T.recv.dims[2];
   if (T.npeers == 1) {  // the group has one rank: pencils coincide, bit-exact copy
@@ -685,6 +704,7 @@ void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_
     for (int f = 0; f < nf; ++f) transpose_device(ctx, which, d_src[f], d_dst[f], id, elem);
     return;
   }
+  count_traffic(D, T, which, elem, nf);
   const SidePlan &S = T.send;
   const long long ns = static_cast<long long>(S.dims[0]) * S.dims[1] * S.dims[2];
   const int ext = S.dims[S.axis], np = T.npeers;
@@ -718,6 +738,76 @@ void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_
     }
   }
   group_barrier(ctx, G);
+}
+
+// ---- self-test of the production data plane --------------------------------------------------------------
+// Fills a library-owned source pencil with the global linear index of every element (exact in a double), runs the
+// transpose through the path the solver takes (peer stores / block copies / copy engines between library-owned
+// pencils, or NCCL when peer access is unavailable) and counts, on the device, the destination elements that do not
+// hold their own global index.  A transpose is pure data movement: the count must be zero (bit-exact).
+namespace {
+template <int ELEM>
+__global__ void k_pattern(double *__restrict__ a, int d0, int d1, int d2, int o0, int o1, int o2, long long G0, long long G1, int check,
+                          unsigned long long *bad) {
+  const long long tot = static_cast<long long>(d0) * d1 * d2;
+  unsigned long long nbad = 0;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < tot;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % d0), j = static_cast<int>((idx / d0) % d1), k = static_cast<int>(idx / (static_cast<long long>(d0) * d1));
+    const double v = static_cast<double>((i + o0) + G0 * ((j + o1) + G1 * (k + o2)));
+    for (int e = 0; e < ELEM; ++e) {
+      const double want = e == 0 ? v : -(v + 0.5);
+      if (check) nbad += (a[idx * ELEM + e] != want);
+      else a[idx * ELEM + e] = want;
+    }
+  }
+  if (check && nbad) atomicAdd(bad, nbad);
+}
+}  // namespace
+
+// which: 0 x->y, 1 y->z, 2 z->y, 3 y->x; elem 1 (real) / 2 (complex); mode: -1 default, else forces X3D_P2P_MODE for this call
+long long transpose_selftest(Ctx &ctx, int which, int id, int elem, int mode) {
+  DecompImpl &D = DEC(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  if (id < 0 || id >= static_cast<int>(D.infos.size())) throw Error("bad decomposition id");
+  const x3d_decomp_info &I = D.infos[id];
+  const int *sst, *ssz, *dst_, *dsz;
+  switch (which) {
+    case 0: sst = I.xst; ssz = I.xsz; dst_ = I.yst; dsz = I.ysz; break;
+    case 1: sst = I.yst; ssz = I.ysz; dst_ = I.zst; dsz = I.zsz; break;
+    case 2: sst = I.zst; ssz = I.zsz; dst_ = I.yst; dsz = I.ysz; break;
+    case 3: sst = I.yst; ssz = I.ysz; dst_ = I.xst; dsz = I.xsz; break;
+    default: throw Error("bad transpose selector");
+  }
+  const long long ns = static_cast<long long>(ssz[0]) * ssz[1] * ssz[2], nd = static_cast<long long>(dsz[0]) * dsz[1] * dsz[2];
+  DevBuf &src = D.self_src, &dst = D.self_dst, &cnt = D.self_cnt;
+  // fixed-size, symmetric allocations (every rank reserves the same way, so the peer-pointer cache stays collective)
+  src.reserve(std::max<long long>(ns, 1) * elem * sizeof(double));
+  dst.reserve(std::max<long long>(nd, 1) * elem * sizeof(double));
+  cnt.reserve(sizeof(unsigned long long));
+  X3D_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), ctx.stream));
+  X3D_CUDA(cudaMemsetAsync(dst.p, 0xff, std::max<long long>(nd, 1) * elem * sizeof(double), ctx.stream));
+  const long long G0 = D.gdims[id][0], G1 = D.gdims[id][1];
+  auto launch = [&](double *a, const int *sz, const int *st, long long n, int check) {
+    if (n == 0) return;
+    const int g = grid_for(ctx, n);
+    if (elem == 1) k_pattern<1><<<g, 256, 0, ctx.stream>>>(a, sz[0], sz[1], sz[2], st[0] - 1, st[1] - 1, st[2] - 1, G0, G1, check, static_cast<unsigned long long *>(cnt.p));
+    else k_pattern<2><<<g, 256, 0, ctx.stream>>>(a, sz[0], sz[1], sz[2], st[0] - 1, st[1] - 1, st[2] - 1, G0, G1, check, static_cast<unsigned long long *>(cnt.p));
+    X3D_CUDA(cudaGetLastError());
+    ctx.launches++;
+  };
+  launch(static_cast<double *>(src.p), ssz, sst, ns, 0);
+  const int keep = D.p2p_mode;
+  if (mode >= 0) D.p2p_mode = mode;
+  try {
+    transpose_device(ctx, which, static_cast<double *>(src.p), static_cast<double *>(dst.p), id, elem);
+  } catch (...) { D.p2p_mode = keep; throw; }
+  D.p2p_mode = keep;
+  launch(static_cast<double *>(dst.p), dsz, dst_, nd, 1);
+  unsigned long long bad = 0;
+  X3D_CUDA(cudaMemcpyAsync(&bad, cnt.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  return static_cast<long long>(bad);
 }
 
 // host-or-device entry of the C ABI

@@ -11,6 +11,8 @@
 // transfer functions), which removes a 16 B/mode read and 1 GB of HBM at 512^3.
 #include <cufft.h>
 #include <cmath>
+#include <cstdlib>
+#include <algorithm>
 #include "x3d_state.cuh"
 
 namespace x3d {
@@ -44,6 +46,7 @@ struct PoissonImpl : PoissonState {
   double *d_ax = nullptr, *d_bx = nullptr, *d_ay = nullptr, *d_by = nullptr, *d_az = nullptr, *d_bz = nullptr;
   double *d_xk2 = nullptr, *d_yk2 = nullptr, *d_zk2 = nullptr, *d_tx = nullptr, *d_ty = nullptr, *d_tz = nullptr;
   // stretched y mesh (matrice_refinement + inversion5_v1/v2): pre-eliminated pentadiagonal systems
+  bool spec_real = false;   // poisson_000 with identical (re,im) z tables: the spectral step is one real factor per mode
   int istret = 0;
   int pen_nsys = 0, pen_rows = 0;     // istret 1,2: two systems (odd / even modes) of ny/2 rows; istret 3: one of nym rows
   DevBuf pen;                         // [nsys][7][rows][nzh][nx] double2: L1 L2 INV A1 B1, and the last-block terms
@@ -120,6 +123,35 @@ __global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
     c = make_double2(c.x * a.bx[i] + c.y * a.ax[i], -c.y * a.bx[i] + c.x * a.ax[i]);  // :394-398
     if (i + 1 > a.nx / 2 + 1) c = neg(c);
     cw[idx] = c;
+  }
+}
+
+// poisson_000 when the (re,im) halves of the z tables coincide (always the case for a periodic z axis).  The forward
+// half-cell rotations (src/poisson.f90:340-361), the division (:366-377) and the backward rotations (:381-398) then
+// compose to ONE real factor per mode: with W = (bz - i az)(by - i ay) sy (bx - i ax) sx the forward chain is c W,
+// the backward chain is conj(conj(c')(bz - i az))(by + i ay) sy ... = c' conj(W), and c' = -c W / kxyz, so
+//   out = -c |W|^2 / (nx ny nz kxyz),   |W|^2 = (az^2+bz^2)(ay^2+by^2)(ax^2+bx^2)  (= 1 up to rounding; kept).
+// One reciprocal-free division per mode, the row-constant parts of kxyz hoisted per (j,k) row, x tables in registers,
+// no 64-bit index arithmetic.  Agrees with the statement-by-statement form to a few ulp (tests: 1e-11).
+__global__ void __launch_bounds__(256) k_spec_000s(SpecArgs a, double2 *__restrict__ cw) {
+  const int rows = a.ny * a.nzh;
+  for (int i = threadIdx.x; i < a.nx; i += blockDim.x) {
+    const double xk = a.xk2[i], fx = a.tx[i], fx2 = fx * fx;
+    const double wx = a.ax[i] * a.ax[i] + a.bx[i] * a.bx[i];
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int j = row % a.ny, kl = row / a.ny, k = kl + a.k0;
+      const double fy = a.ty[j], fz = a.tz[2 * k];
+      const double A = (fy * fz) * (fy * fz);
+      const double BC = a.yk2[j] * (fz * fz) + a.zk2[2 * k] * (fy * fy);
+      const double wzy = (a.az[k] * a.az[k] + a.bz[k] * a.bz[k]) * (a.ay[j] * a.ay[j] + a.by[j] * a.by[j]);
+      const double kk = fma(xk, A, fx2 * BC);
+      const double g = kk < EPS ? 0.0 : (-a.inv_norm * (wzy * wx)) / kk;   // :366
+      double2 *p = cw + static_cast<long long>(row) * a.nx + i;
+      double2 c = *p;
+      c.x *= g;
+      c.y *= g;
+      *p = c;
+    }
   }
 }
 
@@ -561,6 +593,12 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   auto put = [&](const std::vector<double> &v) { size_t o = h.size(); h.insert(h.end(), v.begin(), v.end()); return o; };
   const size_t o_ax = put(TX.a), o_bx = put(TX.b), o_ay = put(TY.a), o_by = put(TY.b), o_az = put(TZ.a), o_bz = put(TZ.b);
   const size_t o_xk = put(TX.k2), o_yk = put(TY.k2), o_zk = put(TZ.k2), o_tx = put(TX.tf), o_ty = put(TY.tf), o_tz = put(TZ.tf);
+  {
+    bool same = p.bcx == 0 && p.bcy == 0 && p.bcz == 0;
+    for (size_t q = 0; same && q + 1 < TZ.k2.size(); q += 2) same = TZ.k2[q] == TZ.k2[q + 1] && TZ.tf[q] == TZ.tf[q + 1];
+    if (const char *e = getenv("X3D_SPEC_REAL")) same = same && atoi(e) != 0;
+    P->spec_real = same;
+  }
   P->tables.reserve(h.size() * sizeof(double));
   X3D_CUDA(cudaMemcpyAsync(P->tables.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -695,7 +733,8 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
   if (!any) {
     if (nsp > 0) {
       ProfScope ps(ctx, "poisson_spectral(k_spec)");
-      k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
+      if (P->spec_real) k_spec_000s<<<std::min<long long>(static_cast<long long>(ny) * nzhl, 16LL * ctx.sm_count), 256, 0, ctx.stream>>>(a, cw);
+      else k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
       X3D_CUDA(cudaGetLastError()); ctx.launches++;
     }
   } else if (P->bcx == 1 && P->bcy == 0) {  // poisson_100, :472-635

@@ -149,11 +149,30 @@ struct SolverImpl : SolverState {
   // kernels compute.  Off by default: on 2 B200 it gave 42.4 ms per 512^3 step against 42.3 ms on one stream (the
   // hidden copies are paid back by slower kernels beside them and by the extra array intt then reads).
   bool overlap = false;
+  // x3d_solver_advance_host: three velocity sets in rotation (the current one and two spares) so that the H2D copy of
+  // job j+1 and the D2H copy of job j-1 run on their own streams beside the kernels of job j
+  struct VelSet {
+    DevBuf b[3];
+    cudaEvent_t h2d_done = nullptr, d2h_done = nullptr;
+    bool pending = false;           // a D2H copy out of this set has been queued (d2h_done is valid)
+    const void *host_out = nullptr; // its destination (a later job reading that host array must wait for it)
+  };
+  VelSet spare[2];
+  cudaEvent_t cur_d2h = nullptr, ev_step = nullptr;
+  bool cur_pending = false;
+  const void *cur_host_out = nullptr;
+  int next_spare = 0;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   ~SolverImpl() override {
     if (h_red) cudaFreeHost(h_red);
     if (aux) cudaStreamDestroy(aux);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    for (auto &v : spare) { if (v.h2d_done) cudaEventDestroy(v.h2d_done); if (v.d2h_done) cudaEventDestroy(v.d2h_done); }
+    if (cur_d2h) cudaEventDestroy(cur_d2h);
+    if (ev_step) cudaEventDestroy(ev_step);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
   }
@@ -960,6 +979,57 @@ void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz) {
   X3D_CUDA(cudaMemcpyAsync(uy, S.uy.p, bytes, cudaMemcpyDefault, ctx.stream));
   X3D_CUDA(cudaMemcpyAsync(uz, S.uz.p, bytes, cudaMemcpyDefault, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+// One job = copy a host velocity field in, advance it nsteps, copy the result out; asynchronous with respect to the
+// host.  Consecutive jobs are independent (each starts from its own host input), so the copies of neighbouring jobs
+// overlap the kernels of the current one: H2D on s_in, kernels on ctx.stream, D2H on s_out, three device velocity
+// sets in rotation.  Host arrays should be page-locked, otherwise the runtime stages the copies and they serialise.
+// Intended for self-starting time schemes (RK3, Euler): the Adams-Bashforth history is not part of a job.
+void solver_advance_host(Ctx &ctx, const double *const in[3], double *const out[3], int nsteps) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const size_t bytes = S.n * sizeof(double);
+  if (!S.s_in) {
+    X3D_CUDA(cudaStreamCreateWithFlags(&S.s_in, cudaStreamNonBlocking));
+    X3D_CUDA(cudaStreamCreateWithFlags(&S.s_out, cudaStreamNonBlocking));
+    for (auto &v : S.spare) {
+      for (auto &b : v.b) b.reserve(S.ux.bytes);
+      X3D_CUDA(cudaEventCreateWithFlags(&v.h2d_done, cudaEventDisableTiming));
+      X3D_CUDA(cudaEventCreateWithFlags(&v.d2h_done, cudaEventDisableTiming));
+    }
+    X3D_CUDA(cudaEventCreateWithFlags(&S.cur_d2h, cudaEventDisableTiming));
+    X3D_CUDA(cudaEventCreateWithFlags(&S.ev_step, cudaEventDisableTiming));
+  }
+  SolverImpl::VelSet &F = S.spare[S.next_spare];
+  S.next_spare ^= 1;
+  if (F.pending) X3D_CUDA(cudaStreamWaitEvent(S.s_in, F.d2h_done, 0));     // the set's previous result has left it
+  // a job that reads a host array an earlier job still writes waits for that copy
+  for (auto &v : S.spare)
+    if (v.pending && v.host_out == in[0]) X3D_CUDA(cudaStreamWaitEvent(S.s_in, v.d2h_done, 0));
+  if (S.cur_pending && S.cur_host_out == in[0]) X3D_CUDA(cudaStreamWaitEvent(S.s_in, S.cur_d2h, 0));
+  for (int c = 0; c < 3; ++c) X3D_CUDA(cudaMemcpyAsync(F.b[c].p, in[c], bytes, cudaMemcpyDefault, S.s_in));
+  X3D_CUDA(cudaEventRecord(F.h2d_done, S.s_in));
+  X3D_CUDA(cudaStreamWaitEvent(ctx.stream, F.h2d_done, 0));
+  // rotate: the freshly filled set becomes the velocity, the old velocity (its D2H possibly in flight) becomes a spare
+  DevBuf *cur[3] = {&S.ux, &S.uy, &S.uz};
+  for (int c = 0; c < 3; ++c) { std::swap(cur[c]->p, F.b[c].p); std::swap(cur[c]->bytes, F.b[c].bytes); }
+  std::swap(S.cur_d2h, F.d2h_done);
+  std::swap(S.cur_pending, F.pending);
+  std::swap(S.cur_host_out, F.host_out);
+  solver_step(ctx, nsteps);
+  X3D_CUDA(cudaEventRecord(S.ev_step, ctx.stream));
+  X3D_CUDA(cudaStreamWaitEvent(S.s_out, S.ev_step, 0));
+  for (int c = 0; c < 3; ++c) X3D_CUDA(cudaMemcpyAsync(out[c], cur[c]->p, bytes, cudaMemcpyDefault, S.s_out));
+  X3D_CUDA(cudaEventRecord(S.cur_d2h, S.s_out));
+  S.cur_pending = true;
+  S.cur_host_out = out[0];
+}
+void solver_host_sync(Ctx &ctx) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  if (S.s_in) X3D_CUDA(cudaStreamSynchronize(S.s_in));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  if (S.s_out) X3D_CUDA(cudaStreamSynchronize(S.s_out));
 }
 void solver_local_shape(Ctx &ctx, int *d3, int *z0) {
   SolverImpl &S = SOL(ctx);

@@ -2,6 +2,7 @@
 #include <cstring>
 #include <string>
 #include <stdexcept>
+#include <omp.h>
 #include "x3d_oracle.hpp"
 
 using namespace x3do;
@@ -377,6 +378,12 @@ int x3do_solver_gradp(void *sv, double *px, double *py, double *pz, const double
 }
 int x3do_solver_poisson(void *sv, double *pp3) {
   try { static_cast<Solver *>(sv)->po.solve(pp3); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// OpenMP threads of the oracle: torchrun exports OMP_NUM_THREADS=1, which would time the CPU baseline on one core.
+// n > 0 sets the count; returns the count in force.
+int x3do_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
 }
 void x3do_solver_pdims(void *sv, int *d3) { auto *s = static_cast<Solver *>(sv); d3[0] = s->nxm; d3[1] = s->nym; d3[2] = s->nzm; }
 

@@ -39,6 +39,8 @@ def main():
         x = X3D(local)
         x.decomp_init(nx, ny, nz, p_row, p_col, rank, world, fresh_id())
         info = decomp_compute(nx, ny, nz, p_row, p_col, rank)
+        # the production data plane: peer stores / block copies / copy engines between library-owned pencils
+        assert x.transpose_selftest() == 0, ("selftest", p_row, p_col, rank)
         for arr, cplx in ((G, False), (Gc, True)):
             tdt = torch.complex128 if cplx else torch.float64
             for name, s, d in (("transpose_x_to_y", "x", "y"), ("transpose_y_to_z", "y", "z"),
