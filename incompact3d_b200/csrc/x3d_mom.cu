@@ -61,6 +61,33 @@ bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M) {
   return true;
 }
 
+// parameters of pair_solve_cyclic for the periodic system tri(alpha, 1, alpha); scale_num / c multiplies the solution
+static bool make_cyc(double alpha, int n, int L, double scale_num, MomGeom::Cyc &cy) {
+  if (!(std::fabs(alpha) < 0.5) || std::fabs(alpha) < 1e-3) return false;
+  const int nc = (n + L - 1) / L, rem = n - (nc - 1) * L;
+  const double rho = (-1.0 + std::sqrt(1.0 - 4.0 * alpha * alpha)) / (2.0 * alpha);
+  const double c = -alpha / rho;
+  int K = 1;
+  while (std::pow(std::fabs(rho), static_cast<double>(K) * L) >= 1e-18 && K < 16) ++K;
+  if (rem != L) ++K;     // one of the K chunks may be the short last one
+  if (K > 8 || K > nc - 1) return false;
+  cy.rho = rho;
+  cy.rhoL = std::pow(rho, L);
+  cy.rhoR = std::pow(rho, rem);
+  cy.esc = std::pow(rho, -(L - rem));
+  if (!std::isfinite(cy.esc) || std::fabs(cy.esc) > 1e100) return false;
+  const double geo = (1.0 - std::pow(rho, 2 * (L - rem))) / (1.0 - rho * rho);
+  cy.gamma = std::pow(rho, rem + 1) * geo;
+  cy.delta = rho * geo;
+  cy.scale = scale_num / c;
+  cy.K = K;
+  return true;
+}
+bool mom_cyclic_ok(double alpha, int n, int L) {
+  MomGeom::Cyc cy{};
+  return make_cyc(alpha, n, L, 1.0, cy);
+}
+
 bool mom_pair_plan(int n, int L, MomGeom &g, size_t &smem) {
   if (L != 17 && L != 9) return false;
   if ((n & 7) || n < 64) return false;
@@ -111,10 +138,15 @@ bool mom_pair_eligible(int n, int L) {
 // out[0..2] = xnu D2(c) - 1/2 (D1(c a) + a D1(c)) along this axis, a = f[axis]
 void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
                      const double *const f[3], double *const out[3], long long n1, int nline, long long nouter, long long sline,
-                     long long souter, bool add) {
+                     long long souter, bool add, bool cyclic) {
   MomGeom g{};
   size_t smem = 0;
-  if (!M1.ok || !M2.ok || M1.L != M2.L || !mom_pair_plan(nline, M1.L, g, smem)) throw Error("fused momentum kernel: ineligible call");
+  const int L = pick_L_contig(nline);
+  if (!cyclic && (!M1.ok || !M2.ok || M1.L != M2.L || M1.L != L)) throw Error("fused momentum kernel: ineligible call");
+  if (!mom_pair_plan(nline, L, g, smem)) throw Error("fused momentum kernel: ineligible call");
+  g.rem = nline - (g.nc - 1) * L;
+  if (cyclic && !(make_cyc(op1.alpha, nline, L, -0.5, g.cy1) && make_cyc(op2.alpha, nline, L, xnu, g.cy2)))
+    throw Error("fused momentum kernel: cyclic solves are not possible for this scheme");
   g.nbx = static_cast<int>((n1 + 15) / 16);
   g.npos = static_cast<long long>(g.nbx) * nouter;
   g.ia = axis; g.ic1 = (axis + 1) % 3; g.ic2 = (axis + 2) % 3;
@@ -137,19 +169,41 @@ void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, con
     ctx.launches++;
   };
   ProfScope ps(ctx, axis == 1 ? "momentum_fused_y(k_mom_pair)" : "momentum_fused_z(k_mom_pair)");
-  if (M1.L == 17) { if (nt4) launch(k_mom_pair<17, 4, false>); else launch(k_mom_pair<17, 2, false>); }
-  else { if (nt4) launch(k_mom_pair<9, 4, false>); else launch(k_mom_pair<9, 2, false>); }
+  if (cyclic) {
+    if (L == 17) { if (nt4) launch(k_mom_pair<17, 4, false, true, false>); else launch(k_mom_pair<17, 2, false, true, false>); }
+    else { if (nt4) launch(k_mom_pair<9, 4, false, true, false>); else launch(k_mom_pair<9, 2, false, true, false>); }
+  } else {
+    if (L == 17) { if (nt4) launch(k_mom_pair<17, 4, false, false, false>); else launch(k_mom_pair<17, 2, false, false, false>); }
+    else { if (nt4) launch(k_mom_pair<9, 4, false, false, false>); else launch(k_mom_pair<9, 2, false, false, false>); }
+  }
 }
 
 // x lines: fields are (n, nlines) arrays with contiguous lines
 void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
-                  const double *const f[3], double *const out[3], int n, long long nlines, bool add) {
+                  const double *const f[3], double *const out[3], int n, long long nlines, bool add, bool cyclic, const MomIntt *intt) {
   MomGeom g{};
   size_t smem = 0;
-  if (!M1.ok || !M2.ok || M1.L != M2.L || !mom_x_plan(n, M1.L, g, smem)) throw Error("fused x momentum kernel: ineligible call");
+  const int L = pick_L_contig(n);
+  if (!cyclic && (!M1.ok || !M2.ok || M1.L != M2.L || M1.L != L)) throw Error("fused x momentum kernel: ineligible call");
+  if (!mom_x_plan(n, L, g, smem)) throw Error("fused x momentum kernel: ineligible call");
+  g.rem = n - (g.nc - 1) * L;
+  if (cyclic && !(make_cyc(op1.alpha, n, L, -0.5, g.cy1) && make_cyc(op2.alpha, n, L, xnu, g.cy2)))
+    throw Error("fused x momentum kernel: cyclic solves are not possible for this scheme");
+  if (intt && !cyclic) throw Error("fused x momentum kernel: the folded time integration needs the cyclic solves");
   for (int q = 0; q < 3; ++q) {
-    if ((reinterpret_cast<uintptr_t>(f[q]) | reinterpret_cast<uintptr_t>(out[q])) & 15u) throw Error("fused x momentum kernel: unaligned field");
-    g.fin[q] = f[q]; g.fout[q] = out[q];
+    if ((reinterpret_cast<uintptr_t>(f[q]) | (intt ? 0 : reinterpret_cast<uintptr_t>(out[q]))) & 15u) throw Error("fused x momentum kernel: unaligned field");
+    g.fin[q] = f[q]; g.fout[q] = intt ? nullptr : out[q];
+  }
+  if (intt) {
+    for (int q = 0; q < 3; ++q) {
+      g.isum[q] = intt->sum[q]; g.iextra[q] = intt->has_extra ? intt->extra[q] : nullptr; g.iold_in[q] = intt->use_old ? intt->old_in[q] : nullptr;
+      g.iu[q] = intt->u[q]; g.iold_out[q] = intt->store_old ? intt->old_out[q] : nullptr;
+      const uintptr_t all = reinterpret_cast<uintptr_t>(g.isum[q]) | reinterpret_cast<uintptr_t>(g.iextra[q]) | reinterpret_cast<uintptr_t>(g.iold_in[q]) |
+                            reinterpret_cast<uintptr_t>(g.iu[q]) | reinterpret_cast<uintptr_t>(g.iold_out[q]);
+      if (all & 15u) throw Error("fused x momentum kernel: unaligned field");
+    }
+    g.ca = intt->ca; g.cb = intt->cb;
+    g.use_old = intt->use_old; g.store_old = intt->store_old; g.has_extra = intt->has_extra;
   }
   g.nlines = nlines;
   g.npos = (nlines + 15) / 16;
@@ -168,9 +222,17 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
     X3D_CUDA(cudaGetLastError());
     ctx.launches++;
   };
-  ProfScope ps(ctx, "momentum_fused_x(k_mom_pair)");
-  if (M1.L == 17) { if (nt4) launch(k_mom_pair<17, 4, true>); else launch(k_mom_pair<17, 2, true>); }
-  else { if (nt4) launch(k_mom_pair<9, 4, true>); else launch(k_mom_pair<9, 2, true>); }
+  ProfScope ps(ctx, intt ? "momentum_fused_x+intt(k_mom_pair)" : "momentum_fused_x(k_mom_pair)");
+  if (intt) {
+    if (L == 17) { if (nt4) launch(k_mom_pair<17, 4, true, true, true>); else launch(k_mom_pair<17, 2, true, true, true>); }
+    else { if (nt4) launch(k_mom_pair<9, 4, true, true, true>); else launch(k_mom_pair<9, 2, true, true, true>); }
+  } else if (cyclic) {
+    if (L == 17) { if (nt4) launch(k_mom_pair<17, 4, true, true, false>); else launch(k_mom_pair<17, 2, true, true, false>); }
+    else { if (nt4) launch(k_mom_pair<9, 4, true, true, false>); else launch(k_mom_pair<9, 2, true, true, false>); }
+  } else {
+    if (L == 17) { if (nt4) launch(k_mom_pair<17, 4, true, false, false>); else launch(k_mom_pair<17, 2, true, false, false>); }
+    else { if (nt4) launch(k_mom_pair<9, 4, true, false, false>); else launch(k_mom_pair<9, 2, true, false, false>); }
+  }
 }
 
 }  // namespace x3d

@@ -13,14 +13,24 @@ struct MomTable {        // compressed coefficient table of one periodic operato
   ~MomTable();
 };
 bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M);
+// table-free cyclic solves (pair_solve_cyclic, x3d_mom_kernels.cuh) are possible for this scheme and chunking
+bool mom_cyclic_ok(double alpha, int n, int L);
+// time integration folded into the x kernel: N = sum (+ extra) + r_x ; u <- ca N + cb old_in + u ; old_out <- N
+struct MomIntt {
+  const double *sum[3], *extra[3], *old_in[3];
+  double *u[3], *old_out[3];
+  double ca, cb;
+  bool use_old, store_old, has_extra;
+};
 // y / z lines: out[c] (+)= xnu D2(f[c]) - 1/2 (D1(f[c] f[axis]) + f[axis] D1(f[c]))
 void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
                      const double *const f[3], double *const out[3], long long n1, int nline, long long nouter, long long sline,
-                     long long souter, bool add = false);
+                     long long souter, bool add = false, bool cyclic = false);
 bool mom_pair_eligible(int n, int L);
 // x lines (contiguous): f / out are (n, nlines) arrays
 void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &M1, const MomTable &M2, double xnu,
-                  const double *const f[3], double *const out[3], int n, long long nlines, bool add = false);
+                  const double *const f[3], double *const out[3], int n, long long nlines, bool add = false, bool cyclic = false,
+                  const MomIntt *intt = nullptr);
 bool mom_x_eligible(int n, int L);
 
 }  // namespace x3d

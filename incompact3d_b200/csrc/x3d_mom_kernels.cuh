@@ -39,6 +39,23 @@ struct MomGeom {
   int ia, ic1, ic2;     // field index of the advecting velocity and of the two other components
   double xnu;
   int add;              // 0: out = r, 1: out += r (TMA reduce-add stores)
+  // ---- cyclic (table-free) line solves, see pair_solve_cyclic ----
+  struct Cyc {
+    double rho;         // root of alpha rho^2 + rho + alpha = 0 inside the unit circle
+    double rhoL, rhoR;  // rho^L, rho^rem: weight of a whole / of the last (partial) chunk in the carry look-back
+    double esc;         // rho^-(L - rem): rescales what enters / leaves the padded rows of the last chunk
+    double gamma, delta;// what the padded rows of the last chunk (they hold rho^(j+1) y_last after the forward sweep) add to
+                        // its backward start value and to the carry that reaches its last real row, per unit of y_last
+    double scale;       // what the solution is multiplied by when it enters r: xnu / c (D2), -1/2 / c (D1), c = -alpha / rho
+    int K;              // chunks of look-back: |rho|^(K L) < 1e-18
+  } cy1, cy2;
+  int rem;              // rows of the last chunk
+  // ---- time integration folded into the x kernel (INTT), src/time_integrators.f90:71-74,151-157 ----
+  //   N = sum (+ extra) + r_x ;  u <- ca N + cb old + u ;  old <- N (when store_old)
+  const double *isum[3], *iextra[3], *iold_in[3];
+  double *iu[3], *iold_out[3];
+  double ca, cb;
+  int use_old, store_old, has_extra;
 };
 struct MomTabs {        // device: [3][mom_tabs(L) L] double2 each ((s,Pf) (w,fw) (Pb,rs)), and [10][32] scan multipliers
   const double2 *c1, *c2;
@@ -105,6 +122,58 @@ __device__ __forceinline__ void pair_solve_periodic(dd2 (&x)[L], const double2 *
   }
 }
 
+// Cyclic, table-free solve of the periodic compact system  alpha x(i-1) + x(i) + alpha x(i+1) = r(i)  for one chunk
+// pair held in x[].  The circulant matrix factors exactly as  c (I - rho S-)(I - rho S+)  (S-, S+: cyclic shifts,
+// alpha rho^2 + rho + alpha = 0, |rho| < 1, c = -alpha / rho), so the solve is two first-order recurrences with ONE
+// constant multiplier: y(i) = r(i) + rho y(i-1), z(i) = y(i) + rho z(i+1), x = z / c.  Every chunk is the same: no
+// boundary rows, no coefficient table, no Sherman-Morrison correction -- the reference's Thomas + Sherman-Morrison
+// algorithm (src/derive.f90:45-59) solves the same well-conditioned system (condition (1+2 alpha)/(1-2 alpha) <= 5), so
+// the two results agree to a few ulp.  Each sweep runs twice: a Horner pass gives the chunk's zero-carry end value,
+// the K previous (next) chunks' end values are combined by shuffles into the exact carry (|rho|^(K L) < 1e-18 makes the
+// look-back exact in double precision, and cyclic indexing makes it periodic), then the sweep is repeated with the
+// carry.  4 FMA per row and system, no shared-memory traffic.  On return x holds z (the caller applies 1/c).
+template <int L>
+__device__ __forceinline__ void pair_solve_cyclic(dd2 (&x)[L], const MomGeom::Cyc &cy, int lane, int nc) {
+  const double rho = cy.rho;
+  // the last chunk holds rem < L real rows followed by zero right-hand sides.  Its padded rows are not masked: what they
+  // do is known in closed form (pure decay of the last real value) and is taken out with three per-lane constants.
+  const bool last = lane == nc - 1;
+  const double escl = last ? cy.esc : 1.0, gl = last ? cy.gamma : 0.0, dl = last ? cy.delta : 0.0;
+  // ---- forward: y(i) = r(i) + rho y(i-1)
+  dd2 e = x[0];
+  X3D_UNROLL
+  for (int m = 1; m < L; ++m) e = fma2(rho, e, x[m]);
+  e = escl * e;
+  dd2 acc = {0.0, 0.0};
+#pragma unroll 1
+  for (int k = cy.K; k >= 1; --k) {
+    int src = lane - k;
+    src += src < 0 ? nc : 0;
+    const dd2 ev = shfl2(e, src);
+    acc = fma2(src == nc - 1 ? cy.rhoR : cy.rhoL, acc, ev);
+  }
+  dd2 t = acc;
+  X3D_UNROLL
+  for (int m = 0; m < L; ++m) { t = fma2(rho, t, x[m]); x[m] = t; }
+  const dd2 yl = escl * t;   // last chunk: y at its last real row
+  // ---- backward: z(i) = y(i) + rho z(i+1)
+  dd2 b = x[L - 1];
+  X3D_UNROLL
+  for (int m = L - 2; m >= 0; --m) b = fma2(rho, b, x[m]);
+  b = fma2(-gl, yl, b);
+  acc = {0.0, 0.0};
+#pragma unroll 1
+  for (int k = cy.K; k >= 1; --k) {
+    int src = lane + k;
+    src -= src >= nc ? nc : 0;
+    const dd2 bv = shfl2(b, src);
+    acc = fma2(src == nc - 1 ? cy.rhoR : cy.rhoL, acc, bv);
+  }
+  t = escl * fma2(-dl, yl, acc);
+  X3D_UNROLL
+  for (int m = L - 1; m >= 0; --m) { t = fma2(rho, t, x[m]); x[m] = t; }
+}
+
 // how a thread reaches element j of its window (two lines at once) inside a ring slot
 template <bool XD>
 struct TileAcc;
@@ -140,10 +209,14 @@ struct TileAcc<true> {  // x: 16 contiguous lines of pitch n+8 doubles (4 ghosts
   }
 };
 
-template <int L, int NT2, bool XD>
+// CYC: table-free cyclic solves (pair_solve_cyclic) instead of the partitioned Thomas tables.
+// INTT (x lines only): the time integration is folded into the kernel: instead of storing r_x the consumers stream
+// sum (+ extra), the stored right-hand side and u of their two lines, and write u and the new stored right-hand side.
+template <int L, int NT2, bool XD, bool CYC, bool INTT>
 __global__ void __launch_bounds__(MOM_THREADS, 1)
     k_mom_pair(const __grid_constant__ DevOp op1, const __grid_constant__ DevOp op2, const __grid_constant__ MomMaps maps,
-               const MomTabs tb, const MomGeom g) {
+               const MomTabs tb, const __grid_constant__ MomGeom g) {
+  static_assert(!INTT || XD, "the time integration is folded into the x kernel only");
   constexpr int NWIN = L + 2 * HALO;
   constexpr int NB = 3;
   constexpr int MOM_TABS = mom_tabs(L), MOM_H = mom_head(L);
@@ -157,8 +230,12 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
   unsigned long long *done = full + NB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = g.n, nc = g.nc;
-  for (int idx = threadIdx.x; idx < 3 * MOM_TABS * L; idx += blockDim.x) { c1[idx] = tb.c1[idx]; c2[idx] = tb.c2[idx]; }
-  for (int idx = threadIdx.x; idx < 320; idx += blockDim.x) { scan1[idx] = tb.scan1[idx]; scan2[idx] = tb.scan2[idx]; }
+  if constexpr (CYC) {   // no tables; the area stays as padding behind the last slot (the last chunk's window overruns into it)
+    for (int idx = threadIdx.x; idx < 3 * MOM_TABS * L; idx += blockDim.x) { c1[idx] = make_double2(0.0, 0.0); c2[idx] = make_double2(0.0, 0.0); }
+  } else {
+    for (int idx = threadIdx.x; idx < 3 * MOM_TABS * L; idx += blockDim.x) { c1[idx] = tb.c1[idx]; c2[idx] = tb.c2[idx]; }
+    for (int idx = threadIdx.x; idx < 320; idx += blockDim.x) { scan1[idx] = tb.scan1[idx]; scan2[idx] = tb.scan2[idx]; }
+  }
   if (threadIdx.x == 0) {
     X3D_UNROLL
     for (int b = 0; b < NB; ++b) { mbar_init(full + b, 1); mbar_init(done + b, PAIR_WARPS); }
@@ -202,7 +279,10 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
         const int slot = static_cast<int>((p + 1 + q) % 3);
         mbar_wait(done + slot, static_cast<unsigned>(p & 1));
         const unsigned char *src = smem_raw + slot * slot_bytes;
-        if constexpr (XD) {
+        if constexpr (INTT) {
+          // the consumers have written their results to global memory themselves: the slot is free
+          (void)src;
+        } else if constexpr (XD) {
           const long long line0 = pos * 16;
           const int nl = static_cast<int>(g.nlines - line0 < 16 ? g.nlines - line0 : 16);
           double *dst = g.fout[fld[q]] + line0 * n;
@@ -289,15 +369,29 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
             x[m].y = ok ? v1.y : 0.0;
           }
         }
-        pair_solve_periodic<L>(r, s2, w2, b2, scan2, lane, nc, live, op2.alpha, tb.ff2, q0, n);
-        X3D_UNROLL
-        for (int m = 0; m < L; ++m) r[m] = xnu * r[m];
-        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, tb.ff1, q0, n);
-        X3D_UNROLL
-        for (int m = 0; m < L; ++m) {
-          const dd2 a = acc.ld(bufA, m + HALO);
-          r[m].x = fma(-0.5 * a.x, x[m].x, r[m].x);
-          r[m].y = fma(-0.5 * a.y, x[m].y, r[m].y);
+        if constexpr (CYC) {
+          pair_solve_cyclic<L>(r, g.cy2, lane, nc);
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) r[m] = g.cy2.scale * r[m];
+          pair_solve_cyclic<L>(x, g.cy1, lane, nc);
+          const double k1 = g.cy1.scale;
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            const dd2 a = acc.ld(bufA, m + HALO);
+            r[m].x = fma(k1 * a.x, x[m].x, r[m].x);
+            r[m].y = fma(k1 * a.y, x[m].y, r[m].y);
+          }
+        } else {
+          pair_solve_periodic<L>(r, s2, w2, b2, scan2, lane, nc, live, op2.alpha, tb.ff2, q0, n);
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) r[m] = xnu * r[m];
+          pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, tb.ff1, q0, n);
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            const dd2 a = acc.ld(bufA, m + HALO);
+            r[m].x = fma(-0.5 * a.x, x[m].x, r[m].x);
+            r[m].y = fma(-0.5 * a.y, x[m].y, r[m].y);
+          }
         }
       }
       __syncwarp();
@@ -319,11 +413,21 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
             x[m].y = ok ? v.y : 0.0;
           }
         }
-        pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, tb.ff1, q0, n);
-        X3D_UNROLL
-        for (int m = 0; m < L; ++m) {
-          r[m].x = fma(-0.5, x[m].x, r[m].x);
-          r[m].y = fma(-0.5, x[m].y, r[m].y);
+        if constexpr (CYC) {
+          pair_solve_cyclic<L>(x, g.cy1, lane, nc);
+          const double k1 = g.cy1.scale;
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            r[m].x = fma(k1, x[m].x, r[m].x);
+            r[m].y = fma(k1, x[m].y, r[m].y);
+          }
+        } else {
+          pair_solve_periodic<L>(x, s1, w1, b1, scan1, lane, nc, live, op1.alpha, tb.ff1, q0, n);
+          X3D_UNROLL
+          for (int m = 0; m < L; ++m) {
+            r[m].x = fma(-0.5, x[m].x, r[m].x);
+            r[m].y = fma(-0.5, x[m].y, r[m].y);
+          }
         }
       }
       __syncwarp();  // every lane has read its windows of c (and of a when c == a)
@@ -332,9 +436,49 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
         for (int m = 0; m < L; ++m)
           if (q0 + m < n) acc.st(bufC, m + HALO, r[m]);
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(done + slot);
+      if constexpr (INTT) {
+        // time integration of the warp's two lines, streamed with 16-byte coalesced accesses:
+        //   N = sum (+ extra) + r ;  u <- ca N + cb old + u ;  old <- N
+        __syncwarp();
+        const int f = fld[q];
+        const long long line0 = (first + p * step) * 16 + 2 * jw;
+        const double ca = g.ca, cb = g.cb;
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+          if (line0 + l >= g.nlines) break;
+          const double2 *rs = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(bufC) + (2 * jw + l) * g.pitch + HALO);
+          const long long gb = (line0 + l) * static_cast<long long>(n) / 2;
+          const double2 *gs = reinterpret_cast<const double2 *>(g.isum[f]) + gb;
+          const double2 *ge = g.has_extra ? reinterpret_cast<const double2 *>(g.iextra[f]) + gb : nullptr;
+          const double2 *go = g.use_old ? reinterpret_cast<const double2 *>(g.iold_in[f]) + gb : nullptr;
+          double2 *gu = reinterpret_cast<double2 *>(g.iu[f]) + gb;
+          double2 *gn = g.store_old ? reinterpret_cast<double2 *>(g.iold_out[f]) + gb : nullptr;
+#pragma unroll 4
+          for (int i = lane; i < n / 2; i += 32) {
+            const double2 rr = rs[i];
+            double2 N = __ldcs(gs + i);
+            N.x += rr.x; N.y += rr.y;
+            if (ge) { const double2 E = __ldcs(ge + i); N.x = E.x + N.x; N.y = E.y + N.y; }
+            double2 U = gu[i];
+            if (go) {
+              const double2 O = __ldcs(go + i);
+              U.x = ca * N.x + cb * O.x + U.x;
+              U.y = ca * N.y + cb * O.y + U.y;
+            } else {
+              U.x = ca * N.x + U.x;
+              U.y = ca * N.y + U.y;
+            }
+            gu[i] = U;
+            if (gn) __stcs(gn + i, N);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done + slot);
+      } else {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done + slot);
+      }
     }
   }
 }

@@ -145,6 +145,8 @@ struct SolverImpl : SolverState {
   // fused momentum kernels (periodic directions): compressed tables of D1 / D2 per axis
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
+  bool cyclic[3] = {false, false, false};   // table-free cyclic solves in the fused kernels (X3D_MOM_CYC=0: tables)
+  bool fuse_intt = true;                    // time integration folded into the x momentum kernel (X3D_FUSE_INTT=0: k_map pass)
   // several ranks, X3D_OVERLAP=1: the y -> z transposes of the velocity run on `aux` while the x and y momentum
   // kernels compute.  Off by default: on 2 B200 it gave 42.4 ms per 512^3 step against 42.3 ms on one stream (the
   // hidden copies are paid back by slower kernels beside them and by the extra array intt then reads).
@@ -320,8 +322,11 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
       const PreOp &o1 = S->d1[a][0], &o2 = S->d2[a][0];
       const TriTable &T1 = get_tri(ctx, o1.call.f, o1.call.s, o1.call.w, n, L, true, o1.op.alpha, nullptr);
       const TriTable &T2 = get_tri(ctx, o2.call.f, o2.call.s, o2.call.w, n, L, true, o2.op.alpha, nullptr);
-      S->fused[a] = build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]);
+      const char *ec = getenv("X3D_MOM_CYC");
+      S->cyclic[a] = !(ec && atoi(ec) == 0) && mom_cyclic_ok(o1.op.alpha, n, L) && mom_cyclic_ok(o2.op.alpha, n, L);
+      S->fused[a] = S->cyclic[a] || (build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]));
     }
+    if (const char *e2 = getenv("X3D_FUSE_INTT")) S->fuse_intt = atoi(e2) != 0;
   }
   S->ivp_y_add = S->ivp[1]; S->ivp_y_add.op.store_mode = 1;
   S->dvp_z_add = S->dvp[2]; S->dvp_z_add.op.store_mode = 1;
@@ -508,7 +513,8 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
 //    y kernel stores and the x kernel adds into sum[c]; the z kernel follows and its result comes back through the
 //    z -> y transposes into extra[c], which intt adds: extra + (r_y + r_x).
 // Same terms as transeq.f90:312-314,323-325,460-470, summed in a different order.
-static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *extra[3]) {
+// itr > 0: the caller allows the time integration of sub-step itr to be folded into the x kernel; returns true when it was
+static bool momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *extra[3], int itr) {
   const long long n = static_cast<long long>(S.n);
   const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
   const double xnu = S.xnu, half = 0.5;
@@ -545,7 +551,7 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
   auto z_dir = [&](bool into_sum) {  // transeq.f90:236-314 (z pencils)
     const double *fz[3] = {alias ? u : t[0], alias ? v : t[1], alias ? w : t[2]};
     double *oz[3] = {alias ? sum[0] : o[0], alias ? sum[1] : o[1], alias ? sum[2] : o[2]};
-    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, fz, oz, lanes, nz, 1, lanes, lanes * nz, false);
+    launch_mom_pair(ctx, 2, S.d1[2][0].op, S.d2[2][0].op, S.mt1[2], S.mt2[2], xnu, fz, oz, lanes, nz, 1, lanes, lanes * nz, false, S.cyclic[2]);
     if (!alias) {  // transeq.f90:318-320
       if (into_sum) {
         transpose_device_multi(ctx, 2, 3, o, sum, S.id_v, 1);
@@ -557,10 +563,24 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
   };
   if (z_first) z_dir(true);
   // ---- y, transeq.f90:188-219,336-338
-  launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, z_first);
+  launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, z_first, S.cyclic[1]);
   // ---- x, transeq.f90:114-146,442-444
-  if (S.fused[0]) {
-    launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true);
+  bool folded = false;
+  if (S.fused[0] && S.cyclic[0] && S.fuse_intt && itr > 0 && z_first && (S.p.itimescheme == 5 || S.p.itimescheme == 1)) {
+    // x kernel + intt (time_integrators.f90:71-74,151-157): u <- adt N + bdt old + u, old <- N, N = sum (+ extra) + r_x
+    MomIntt I{};
+    double *vel[3] = {B(S.ux), B(S.uy), B(S.uz)}, *old[3] = {B(S.dux[1]), B(S.duy[1]), B(S.duz[1])};
+    const bool rk3 = S.p.itimescheme == 5;
+    I.has_extra = extra[0] != nullptr;
+    I.use_old = rk3 && itr > 1;
+    I.store_old = rk3 && itr < S.iadvance;   // the last sub-step's right-hand side is never read (bdt(1) = 0)
+    I.ca = (!rk3 || itr == 1) ? S.gdt[0] : S.adt[itr - 1];
+    I.cb = I.use_old ? S.bdt[itr - 1] : 0.0;
+    for (int c = 0; c < 3; ++c) { I.sum[c] = sum[c]; I.extra[c] = extra[c]; I.old_in[c] = old[c]; I.u[c] = vel[c]; I.old_out[c] = old[c]; }
+    launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true, true, &I);
+    folded = true;
+  } else if (S.fused[0]) {
+    launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true, S.cyclic[0]);
   } else {  // operator kernels + three elementwise passes
     double *ta = B(S.w[3]), *tb = B(S.w[4]), *tc = B(S.w[5]), *td = B(S.w[6]), *te = B(S.w[7]), *tf = B(S.w[8]);
     double *rx = sum[0], *ry = sum[1], *rz = sum[2];
@@ -577,6 +597,7 @@ static void momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
     X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));
     z_dir(false);
   }
+  return folded;
 }
 
 // Adams-Bashforth 2 / 3 (time_integrators.f90:75-100) for the three components; rhs(q, c) is the current right-hand
@@ -848,8 +869,7 @@ void solver_step(Ctx &ctx, int nsteps) {
       boundary_conditions(ctx, S);
       if (S.fused[1] && S.fused[2]) {
         double *rhs[3] = {B(S.w[0]), B(S.w[1]), B(S.w[2])}, *extra[3];
-        momentum_rhs_fused(ctx, S, rhs, extra);
-        intt3_fused(ctx, S, itr, rhs, extra);
+        if (!momentum_rhs_fused(ctx, S, rhs, extra, itr)) intt3_fused(ctx, S, itr, rhs, extra);
       } else {
         momentum_rhs(ctx, S, B(S.dux[0]), B(S.duy[0]), B(S.duz[0]));
         intt3(ctx, S, itr);
