@@ -299,8 +299,34 @@ typedef struct x3d_solver_params {
   double nu0nu, cnu;
   int p_row, p_col;
   int itype;                      /* 0: box without forcing (TGV); 3: channel (itype_channel, src/module_param.f90):
-                                     constant flow rate channel_cfr, src/Case-Channel.f90:150-170,220-261 */
+                                     constant flow rate channel_cfr, src/Case-Channel.f90:150-170,220-261;
+                                     5: cylinder wake (itype_cyl): inflow / convective outflow, Case-Cylinder-wake.f90 */
 } x3d_solver_params;
+/* Case parameters beyond the mesh and the schemes (call after x3d_solver_init, before stepping).
+ *  channel (itype 3): momentum_forcing_channel, src/Case-Channel.f90:396-420 -- cpg /= 0: constant pressure gradient
+ *    (re is then Re_tau: xnu = 1/re_cent, fcpg = 2/yly (re/re_cent)^2, src/parameters.f90:303-311, and channel_cfr is
+ *    off, src/Case-Channel.f90:157); spin-up rotation wrotation while itime < spinup_time and iin <= 2.
+ *  cylinder (itype 5): u1, u2, inflow_noise of inflow / outflow, src/Case-Cylinder-wake.f90:100-203.
+ *  immersed boundary: iibm 0 | 2 (lagpol* in front of every derivative of momentum_rhs_eq, src/derive.f90:23-24) |
+ *    3 (cubspl*); ubcx, ubcy, ubcz = the body's velocity, used for lind and by the ep1 mask in divergence
+ *    (src/navier.f90:285-293).  The geometry goes in through x3d_set_ibm_geometry, the mask through
+ *    x3d_solver_set_ibm_mask.                                                                                   */
+typedef struct x3d_case_params {
+  int cpg; double wrotation; int spinup_time; int iin;
+  double u1, u2, inflow_noise;
+  int iibm; double ubcx, ubcy, ubcz;
+} x3d_case_params;
+int x3d_solver_set_case(x3d_ctx *ctx, const x3d_case_params *c);
+/* ep1 of this rank's x-pencil (nx, ny, nz_local), host or device pointer (genepsi3d's output; 1 inside the body) */
+int x3d_solver_set_ibm_mask(x3d_ctx *ctx, const double *ep1);
+/* the random planes bxo, byo, bzo (ny, nz_local) that inflow() scales by inflow_noise (NULL = zero) */
+int x3d_solver_set_inflow_noise(x3d_ctx *ctx, const double *bxo, const double *byo, const double *bzo);
+/* wall velocities of the x faces for pre_correc (src/navier.f90:564-595): bxx1 bxy1 bxz1 bxxn bxyn bxzn, (ny, nz_local)
+ * planes; NULL keeps a plane.  The cylinder case overwrites them every sub-step (inflow / outflow).             */
+int x3d_solver_set_wall_velocity_x(x3d_ctx *ctx, const double *const planes6[6]);
+int x3d_solver_get_wall_velocity_x(x3d_ctx *ctx, double *const planes6[6]);
+/* init_cyl with iin = 0 (src/Case-Cylinder-wake.f90:205-279): uniform stream ux = u1 */
+int x3d_solver_init_cyl(x3d_ctx *ctx);
 int x3d_solver_init(x3d_ctx *ctx, const x3d_solver_params *p);
 int x3d_solver_init_tgv(x3d_ctx *ctx);
 /* init_channel with iin = 0 (src/Case-Channel.f90:71-94): ux = 1 - y^2, uz = sin(x) + cos(z) */

@@ -53,6 +53,12 @@ class SolverParams(C.Structure):
                 ("p_row", C.c_int), ("p_col", C.c_int), ("itype", C.c_int)]
 
 
+class CaseParams(C.Structure):
+    _fields_ = [("cpg", C.c_int), ("wrotation", C.c_double), ("spinup_time", C.c_int), ("iin", C.c_int),
+                ("u1", C.c_double), ("u2", C.c_double), ("inflow_noise", C.c_double),
+                ("iibm", C.c_int), ("ubcx", C.c_double), ("ubcy", C.c_double), ("ubcz", C.c_double)]
+
+
 _lib = None
 
 

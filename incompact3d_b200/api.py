@@ -413,6 +413,56 @@ def _solver_get_velocity(self, ux=None, uy=None, uz=None):
     return ux, uy, uz
 
 
+def _solver_set_case(self, cpg=0, wrotation=0.0, spinup_time=0, iin=0, u1=1.0, u2=1.0, inflow_noise=0.0, iibm=0, ubc=(0.0, 0.0, 0.0)):
+    """case parameters beyond mesh and schemes: channel forcing (src/Case-Channel.f90:396-420), cylinder inflow / outflow
+    (src/Case-Cylinder-wake.f90:100-203), immersed boundary (iibm, body velocity)"""
+    c = _lib.CaseParams(int(cpg), float(wrotation), int(spinup_time), int(iin), float(u1), float(u2), float(inflow_noise), int(iibm),
+                        float(ubc[0]), float(ubc[1]), float(ubc[2]))
+    fn = self._L.x3d_solver_set_case
+    fn.argtypes = [C.c_void_p, C.POINTER(_lib.CaseParams)]
+    self._check(fn(self._h, C.byref(c)))
+
+
+def _solver_set_ibm_mask(self, ep1):
+    keep = []
+    fn = self._L.x3d_solver_set_ibm_mask
+    fn.argtypes = [C.c_void_p, C.c_void_p]
+    self._check(fn(self._h, _addr(ep1, keep)))
+
+
+def _solver_set_inflow_noise(self, bxo=None, byo=None, bzo=None):
+    keep = []
+    fn = self._L.x3d_solver_set_inflow_noise
+    fn.argtypes = [C.c_void_p] * 4
+    self._check(fn(self._h, _addr(bxo, keep), _addr(byo, keep), _addr(bzo, keep)))
+
+
+def _solver_wall_velocity_x(self, planes=None):
+    """set (planes = 6 arrays or None entries) or get (planes = None -> list of 6 arrays) bxx1 bxy1 bxz1 bxxn bxyn bxzn"""
+    keep = []
+    arr = (C.c_void_p * 6)()
+    if planes is None:
+        out = [np.zeros((self._solver_shape[1], self._solver_shape[2]), order="F") for _ in range(6)]
+        for q in range(6):
+            arr[q] = out[q].ctypes.data
+        fn = self._L.x3d_solver_get_wall_velocity_x
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        self._check(fn(self._h, arr))
+        return out
+    for q in range(6):
+        a = _addr(planes[q], keep)
+        arr[q] = a.value if a is not None else None
+    fn = self._L.x3d_solver_set_wall_velocity_x
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    self._check(fn(self._h, arr))
+
+
+def _solver_init_cyl(self):
+    fn = self._L.x3d_solver_init_cyl
+    fn.argtypes = [C.c_void_p]
+    self._check(fn(self._h))
+
+
 def _solver_advance_host(self, vin, vout, nsteps=1):
     """queue one job: H2D of the host velocity `vin` (3 arrays), nsteps time steps, D2H into `vout`; asynchronous"""
     keep = []
@@ -488,6 +538,11 @@ X3D.solver_divergence = _solver_divergence
 X3D.solver_set_velocity = _solver_set_velocity
 X3D.solver_get_velocity = _solver_get_velocity
 X3D.solver_advance_host = _solver_advance_host
+X3D.solver_set_case = _solver_set_case
+X3D.solver_set_ibm_mask = _solver_set_ibm_mask
+X3D.solver_set_inflow_noise = _solver_set_inflow_noise
+X3D.solver_wall_velocity_x = _solver_wall_velocity_x
+X3D.solver_init_cyl = _solver_init_cyl
 X3D.solver_host_sync = _solver_host_sync
 X3D.decomp_stats = _decomp_stats
 X3D.transpose_selftest = _transpose_selftest

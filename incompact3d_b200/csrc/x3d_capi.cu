@@ -27,6 +27,11 @@ void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz);
 void solver_local_shape(Ctx &ctx, int *d3, int *z0);
 void solver_advance_host(Ctx &ctx, const double *const in[3], double *const out[3], int nsteps);
 void solver_host_sync(Ctx &ctx);
+void solver_set_case(Ctx &ctx, const x3d_case_params &c);
+void solver_set_ibm_mask(Ctx &ctx, const double *ep1);
+void solver_set_inflow_noise(Ctx &ctx, const double *bxo, const double *byo, const double *bzo);
+void solver_wall_velocity_x(Ctx &ctx, const double *const in6[6], double *const out6[6]);
+void solver_init_cyl(Ctx &ctx);
 long long transpose_selftest(Ctx &ctx, int which, int id, int elem, int mode);
 void decomp_stats(Ctx &ctx, unsigned long long *remote_bytes, unsigned long long *fields);
 void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int rank, int nranks, const void *nccl_id);
@@ -420,6 +425,20 @@ int x3d_transpose_selftest(x3d_ctx *ctx, int which, int decomp_id, int complex_,
 int x3d_decomp_stats(x3d_ctx *ctx, unsigned long long *remote_bytes, unsigned long long *fields) {
   return guard([&] { decomp_stats(ctx->c, remote_bytes, fields); });
 }
+int x3d_solver_set_case(x3d_ctx *ctx, const x3d_case_params *c) {
+  return guard([&] { if (!c) throw Error("null params"); solver_set_case(ctx->c, *c); });
+}
+int x3d_solver_set_ibm_mask(x3d_ctx *ctx, const double *ep1) { return guard([&] { solver_set_ibm_mask(ctx->c, ep1); }); }
+int x3d_solver_set_inflow_noise(x3d_ctx *ctx, const double *bxo, const double *byo, const double *bzo) {
+  return guard([&] { solver_set_inflow_noise(ctx->c, bxo, byo, bzo); });
+}
+int x3d_solver_set_wall_velocity_x(x3d_ctx *ctx, const double *const planes6[6]) {
+  return guard([&] { solver_wall_velocity_x(ctx->c, planes6, nullptr); });
+}
+int x3d_solver_get_wall_velocity_x(x3d_ctx *ctx, double *const planes6[6]) {
+  return guard([&] { solver_wall_velocity_x(ctx->c, nullptr, planes6); });
+}
+int x3d_solver_init_cyl(x3d_ctx *ctx) { return guard([&] { solver_init_cyl(ctx->c); }); }
 int x3d_solver_host_sync(x3d_ctx *ctx) { return guard([&] { solver_host_sync(ctx->c); }); }
 int x3d_solver_step(x3d_ctx *ctx, int nsteps) { return guard([&] { solver_step(ctx->c, nsteps); }); }
 int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5) { return guard([&] { solver_diagnostics_tgv(ctx->c, out5); }); }

@@ -443,33 +443,65 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
         const int f = fld[q];
         const long long line0 = (first + p * step) * 16 + 2 * jw;
         const double ca = g.ca, cb = g.cb;
+        // all loads of a batch (8 x 32 lanes x 16 bytes per array) are issued before the first use: the warp has
+        // nothing else to overlap the HBM latency with, so it needs the bytes in flight (the solve's registers are dead here)
+        constexpr int NBT = 8;
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
           if (line0 + l >= g.nlines) break;
           const double2 *rs = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(bufC) + (2 * jw + l) * g.pitch + HALO);
           const long long gb = (line0 + l) * static_cast<long long>(n) / 2;
           const double2 *gs = reinterpret_cast<const double2 *>(g.isum[f]) + gb;
-          const double2 *ge = g.has_extra ? reinterpret_cast<const double2 *>(g.iextra[f]) + gb : nullptr;
-          const double2 *go = g.use_old ? reinterpret_cast<const double2 *>(g.iold_in[f]) + gb : nullptr;
+          const double2 *ge = reinterpret_cast<const double2 *>(g.iextra[f]) + gb;
+          const double2 *go = reinterpret_cast<const double2 *>(g.iold_in[f]) + gb;
           double2 *gu = reinterpret_cast<double2 *>(g.iu[f]) + gb;
-          double2 *gn = g.store_old ? reinterpret_cast<double2 *>(g.iold_out[f]) + gb : nullptr;
-#pragma unroll 4
-          for (int i = lane; i < n / 2; i += 32) {
-            const double2 rr = rs[i];
-            double2 N = __ldcs(gs + i);
-            N.x += rr.x; N.y += rr.y;
-            if (ge) { const double2 E = __ldcs(ge + i); N.x = E.x + N.x; N.y = E.y + N.y; }
-            double2 U = gu[i];
-            if (go) {
-              const double2 O = __ldcs(go + i);
-              U.x = ca * N.x + cb * O.x + U.x;
-              U.y = ca * N.y + cb * O.y + U.y;
-            } else {
-              U.x = ca * N.x + U.x;
-              U.y = ca * N.y + U.y;
+          double2 *gn = reinterpret_cast<double2 *>(g.iold_out[f]) + gb;
+          const int nh = n / 2;
+#pragma unroll 1
+          for (int i0 = 0; i0 < nh; i0 += 32 * NBT) {
+            double2 Sv[NBT], Uv[NBT], Ov[NBT];
+            X3D_UNROLL
+            for (int t = 0; t < NBT; ++t) {
+              const int i = i0 + lane + 32 * t;
+              Sv[t] = i < nh ? __ldcs(gs + i) : make_double2(0.0, 0.0);
             }
-            gu[i] = U;
-            if (gn) __stcs(gn + i, N);
+            X3D_UNROLL
+            for (int t = 0; t < NBT; ++t) {
+              const int i = i0 + lane + 32 * t;
+              Uv[t] = i < nh ? gu[i] : make_double2(0.0, 0.0);
+            }
+            if (g.use_old) {
+              X3D_UNROLL
+              for (int t = 0; t < NBT; ++t) {
+                const int i = i0 + lane + 32 * t;
+                Ov[t] = i < nh ? __ldcs(go + i) : make_double2(0.0, 0.0);
+              }
+            } else {
+              X3D_UNROLL
+              for (int t = 0; t < NBT; ++t) Ov[t] = make_double2(0.0, 0.0);
+            }
+            if (g.has_extra) {
+              X3D_UNROLL
+              for (int t = 0; t < NBT; ++t) {
+                const int i = i0 + lane + 32 * t;
+                if (i < nh) { const double2 E = __ldcs(ge + i); Sv[t].x = E.x + Sv[t].x; Sv[t].y = E.y + Sv[t].y; }
+              }
+            }
+            X3D_UNROLL
+            for (int t = 0; t < NBT; ++t) {
+              const int i = i0 + lane + 32 * t;
+              if (i < nh) {
+                const double2 rr = rs[i];
+                double2 N = Sv[t];
+                if (g.has_extra) { N.x = N.x + rr.x; N.y = N.y + rr.y; }   // extra + (sum + r) as intt3_fused
+                else { N.x += rr.x; N.y += rr.y; }
+                double2 U = Uv[t];
+                U.x = ca * N.x + cb * Ov[t].x + U.x;
+                U.y = ca * N.y + cb * Ov[t].y + U.y;
+                gu[i] = U;
+                if (g.store_old) __stcs(gn + i, N);
+              }
+            }
           }
         }
         __syncwarp();

@@ -23,6 +23,20 @@ void decomp_shape(Ctx &ctx, int *p_row, int *p_col, int *rank, int *nranks);
 
 namespace {
 
+// max / min of a strided plane (outflow celerity, Case-Cylinder-wake.f90:146-157): out[0] = max, out[1] = -min
+__global__ void k_plane_minmax(const double *__restrict__ a, long long n, long long stride, double *__restrict__ out) {
+  double mx = -1609.0, mn = 1609.0;
+  for (long long q = threadIdx.x; q < n; q += blockDim.x) { const double v = a[q * stride]; mx = fmax(mx, v); mn = fmin(mn, v); }
+  __shared__ double s1[32], s2[32];
+  for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o)); mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o)); }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = mx; s2[threadIdx.x >> 5] = mn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) { mx = fmax(mx, s1[w]); mn = fmin(mn, s2[w]); }
+    out[0] = mx; out[1] = -mn;
+  }
+}
+
 template <class F>
 __global__ void k_map(long long n, F f) {
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n;
@@ -142,6 +156,12 @@ struct SolverImpl : SolverState {
   // (navier.f90:325,339) and t -= op(u) for cor_vel folded into the last pressure-gradient operators (:242-244,426-430)
   PreOp ivp_y_add, dvp_z_add, dpv_x_sub, ipv_x_sub;
   bool fuse_sums = true;      // X3D_FUSE_SUMS=0 restores the separate elementwise passes
+  // case glue: channel forcing, cylinder inflow / outflow, immersed boundary (x3d_solver_set_case)
+  x3d_case_params cs{};
+  double fcpg = 0.0;
+  DevBuf bwx;                 // wall velocities of the x faces: bxx1 bxy1 bxz1 bxxn bxyn bxzn, (ny, nzl) each
+  DevBuf bnoise;              // bxo byo bzo (ny, nzl)
+  DevBuf ep1;                 // (nx, ny, nzl)
   // fused momentum kernels (periodic directions): compressed tables of D1 / D2 per axis
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
@@ -237,7 +257,10 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   // Dirichlet faces (ncl = 2) are no-slip walls (zero wall velocity, Case-Channel.f90:67); inflow / outflow planes
   // would need the case arrays b?? (cylinder glue)
   if (p.istret != 0 && S->A[1].periodic) throw Error("x3d_solver_init: a stretched y mesh needs non-periodic y");
-  if (p.itype != 0 && p.itype != 3) throw Error("x3d_solver_init: itype 0 (box) and 3 (channel) are implemented");
+  if (p.itype != 0 && p.itype != 3 && p.itype != 5) throw Error("x3d_solver_init: itype 0 (box), 3 (channel) and 5 (cylinder) are implemented");
+  if (p.itype == 5 && (p.nclx1 != 2 || p.nclxn != 2)) throw Error("x3d_solver_init: the cylinder case needs nclx1 = nclxn = 2 (inflow / outflow)");
+  if (p.p_row > 0 && p.p_col > 0 && (p.p_row != pr || p.p_col != pc))
+    throw Error("x3d_solver_init: p_row x p_col differs from the process grid of x3d_decomp_init");
   ctx.iibm = 0; ctx.istret = p.istret; ctx.iimplicit = 0;
   if (p.istret != 0) S->st = make_stretching(p.istret, p.beta, p.yly, p.ny, S->A[1].nm);
   S->nxm = S->A[0].nm; S->nym = S->A[1].nm; S->nzm = S->A[2].nm;
@@ -347,6 +370,12 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
     X3D_CUDA(cudaMemcpyAsync(S->d_pp.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
     X3D_CUDA(cudaStreamSynchronize(ctx.stream));
   }
+  if (p.nclx1 == 2 || p.nclxn == 2) {
+    const size_t nb = 6 * std::max<size_t>(static_cast<size_t>(p.ny) * nzl, 1) * sizeof(double);
+    S->bwx.reserve(nb);
+    X3D_CUDA(cudaMemsetAsync(S->bwx.p, 0, S->bwx.bytes, ctx.stream));
+  }
+  S->cs.u1 = 1.0; S->cs.u2 = 1.0;
   {
     const size_t ndpd = 4 * (static_cast<size_t>(p.ny) * nzl + static_cast<size_t>(p.nx) * nzl + static_cast<size_t>(p.nx) * p.ny);
     S->dpd.reserve(std::max<size_t>(ndpd, 1) * sizeof(double));
@@ -417,8 +446,39 @@ void solver_init_channel(Ctx &ctx) {
 }
 
 // boundary_conditions_channel (Case-Channel.f90:150-170, cpg = F, idir_stream = 1): channel_cfr(ux, 2/3), :220-261
-static void boundary_conditions(Ctx &ctx, SolverImpl &S) {
-  if (S.p.itype != 3) return;
+static void boundary_conditions(Ctx &ctx, SolverImpl &S, int itr) {
+  if (S.p.itype == 5) {  // boundary_conditions_cyl, Case-Cylinder-wake.f90:84-98: inflow (:100-133), outflow (:135-203)
+    const int nx = S.p.nx, ny = S.p.ny, nzl = S.nzl;
+    const long long nyz = static_cast<long long>(ny) * nzl;
+    if (nyz == 0) return;
+    double *bw = B(S.bwx);
+    const double *bn = S.bnoise.p ? B(S.bnoise) : nullptr;
+    const double u1 = S.cs.u1, u2 = S.cs.u2, noise = S.cs.inflow_noise;
+    const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+    double *mm = B(S.red_out) + 10;
+    k_plane_minmax<<<1, 1024, 0, ctx.stream>>>(u + (nx - 2), nyz, nx, mm);   // uxmax / uxmin over the plane nx - 1 (1-based)
+    X3D_CUDA(cudaGetLastError()); ctx.launches++;
+    allreduce(ctx, mm, 2, true);
+    const double g = S.gdt[itr - 1], udx = 1.0 / S.A[0].d;
+    const int mode = u1 == 0.0 ? 0 : (u1 == 1.0 ? 1 : (u1 == 2.0 ? 2 : 3));
+    map(ctx, nyz, [=] __device__(long long q) {
+      bw[q] = u1 + (bn ? bn[q] : 0.0) * noise;
+      bw[nyz + q] = 0.0 + (bn ? bn[nyz + q] : 0.0) * noise;
+      bw[2 * nyz + q] = 0.0 + (bn ? bn[2 * nyz + q] : 0.0) * noise;
+      const double uxmax = mm[0], uxmin = -mm[1];
+      double cx;
+      if (mode == 0) cx = (0.5 * (uxmax + uxmin)) * g * udx;
+      else if (mode == 1) cx = uxmax * g * udx;
+      else if (mode == 2) cx = u2 * g * udx;
+      else cx = (0.5 * (u1 + u2)) * g * udx;
+      const long long p1 = q * nx + nx - 1, p0 = p1 - 1;
+      bw[3 * nyz + q] = u[p1] - cx * (u[p1] - u[p0]);
+      bw[4 * nyz + q] = v[p1] - cx * (v[p1] - v[p0]);
+      bw[5 * nyz + q] = w[p1] - cx * (w[p1] - w[p0]);
+    });
+    return;
+  }
+  if (S.p.itype != 3 || S.cs.cpg) return;   // Case-Channel.f90:157: channel_cfr only without a constant pressure gradient
   const long long n = static_cast<long long>(S.n);
   const int nx = S.p.nx, ny = S.p.ny;
   double *u = B(S.ux);
@@ -443,20 +503,29 @@ static void boundary_conditions(Ctx &ctx, SolverImpl &S) {
 static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, double *duz1) {
   const long long n = static_cast<long long>(S.n);                                   // x / y pencil
   const long long nz3 = static_cast<long long>(S.p.nx) * S.nyl * S.p.nz;             // z pencil
-  const double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  double *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+  // iibm = 2 / 3: every collocated derivative first rebuilds its input inside the bodies, in place -- the velocity
+  // arrays included (src/derive.f90:23-24); lind = product of the body velocities (src/transeq.f90:120-146)
+  const int iibm = S.cs.iibm;
+  const double bx = S.cs.ubcx, by = S.cs.ubcy, bz = S.cs.ubcz;
+  auto run = [&](const PreOp &P, const double *in, double *out, double lind = 0.0) {
+    if (iibm == 2) lagpol_device(ctx, P.call.axis, const_cast<double *>(in), P.call.dims_in[0], P.call.dims_in[1], P.call.dims_in[2]);
+    else if (iibm == 3) cubspl_device(ctx, P.call.axis, const_cast<double *>(in), P.call.dims_in[0], P.call.dims_in[1], P.call.dims_in[2], lind);
+    x3d::run(ctx, P, in, out);
+  };
   double *ta = B(S.w[0]), *tb = B(S.w[1]), *tc = B(S.w[2]), *td = B(S.w[3]), *te = B(S.w[4]), *tf = B(S.w[5]);
   double *tg1 = B(S.w[6]), *th1 = B(S.w[7]), *ti1 = B(S.w[8]), *tg2 = B(S.w[9]), *th2 = B(S.w[10]), *ti2 = B(S.w[11]);
   double *tg3 = B(S.w[12]), *th3 = B(S.w[13]), *ti3 = B(S.w[14]);
   const double xnu = S.xnu, half = 0.5;
   // x, :114-146
   map(ctx, n, [=] __device__(long long q) { const double a = u[q]; ta[q] = a * a; tb[q] = a * v[q]; tc[q] = a * w[q]; });
-  run(ctx, S.d1[0][1], ta, td); run(ctx, S.d1[0][0], tb, te); run(ctx, S.d1[0][0], tc, tf);
-  run(ctx, S.d1[0][0], u, ta); run(ctx, S.d1[0][1], v, tb); run(ctx, S.d1[0][1], w, tc);
+  run(S.d1[0][1], ta, td, bx * bx); run(S.d1[0][0], tb, te, bx * by); run(S.d1[0][0], tc, tf, bx * bz);
+  run(S.d1[0][0], u, ta, bx); run(S.d1[0][1], v, tb, by); run(S.d1[0][1], w, tc, bz);
   map(ctx, n, [=] __device__(long long q) { const double a = u[q]; tg1[q] = td[q] + a * ta[q]; th1[q] = te[q] + a * tb[q]; ti1[q] = tf[q] + a * tc[q]; });
   // y, :188-219
   map(ctx, n, [=] __device__(long long q) { const double a = v[q]; td[q] = u[q] * a; te[q] = a * a; tf[q] = w[q] * a; });
-  run(ctx, S.d1[1][0], td, tg2); run(ctx, S.d1[1][1], te, th2); run(ctx, S.d1[1][0], tf, ti2);
-  run(ctx, S.d1[1][1], u, td); run(ctx, S.d1[1][0], v, te); run(ctx, S.d1[1][1], w, tf);
+  run(S.d1[1][0], td, tg2, bx * by); run(S.d1[1][1], te, th2, by * by); run(S.d1[1][0], tf, ti2, bz * by);
+  run(S.d1[1][1], u, td, bx); run(S.d1[1][0], v, te, by); run(S.d1[1][1], w, tf, bz);
   map(ctx, n, [=] __device__(long long q) { const double a = v[q]; tg2[q] = tg2[q] + a * td[q]; th2[q] = th2[q] + a * te[q]; ti2[q] = ti2[q] + a * tf[q]; });
   // z, :236-314 (transpose_y_to_z of the three velocity components, :236-238)
   const double *u3 = TR(ctx, S, 1, u, ta, S.id_v), *v3 = TR(ctx, S, 1, v, tb, S.id_v), *w3 = TR(ctx, S, 1, w, tc, S.id_v);
@@ -464,13 +533,13 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
     double *pa = td, *pb = te, *pc = tf;
     map(ctx, nz3, [=] __device__(long long q) { const double a = w3[q]; pa[q] = u3[q] * a; pb[q] = v3[q] * a; pc[q] = a * a; });
   }
-  run(ctx, S.d1[2][0], td, tg3); run(ctx, S.d1[2][0], te, th3); run(ctx, S.d1[2][1], tf, ti3);
-  run(ctx, S.d1[2][1], u3, td); run(ctx, S.d1[2][1], v3, te); run(ctx, S.d1[2][0], w3, tf);
+  run(S.d1[2][0], td, tg3, bx * bz); run(S.d1[2][0], te, th3, by * bz); run(S.d1[2][1], tf, ti3, bz * bz);
+  run(S.d1[2][1], u3, td, bx); run(S.d1[2][1], v3, te, by); run(S.d1[2][0], w3, tf, bz);
   map(ctx, nz3, [=] __device__(long long q) {  // convective z terms, :272-274
     const double a = w3[q];
     tg3[q] = tg3[q] + a * td[q]; th3[q] = th3[q] + a * te[q]; ti3[q] = ti3[q] + a * tf[q];
   });
-  run(ctx, S.d2[2][1], u3, td); run(ctx, S.d2[2][1], v3, te); run(ctx, S.d2[2][0], w3, tf);  // :301-303
+  run(S.d2[2][1], u3, td, bx); run(S.d2[2][1], v3, te, by); run(S.d2[2][0], w3, tf, bz);  // :301-303
   map(ctx, nz3, [=] __device__(long long q) {  // :312-314
     tg3[q] = xnu * td[q] - half * tg3[q]; th3[q] = xnu * te[q] - half * th3[q]; ti3[q] = xnu * tf[q] - half * ti3[q];
   });
@@ -478,7 +547,7 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
   const double *zx = TR(ctx, S, 2, tg3, td, S.id_v), *zy = TR(ctx, S, 2, th3, te, S.id_v), *zz = TR(ctx, S, 2, ti3, tf, S.id_v);
   map(ctx, n, [=] __device__(long long q) { tg2[q] = zx[q] - half * tg2[q]; th2[q] = zy[q] - half * th2[q]; ti2[q] = zz[q] - half * ti2[q]; });
   // y diffusion, :336-433
-  run(ctx, S.d2[1][1], u, td); run(ctx, S.d2[1][0], v, te); run(ctx, S.d2[1][1], w, tf);
+  run(S.d2[1][1], u, td, bx); run(S.d2[1][0], v, te, by); run(S.d2[1][1], w, tf, bz);
   if (S.p.istret != 0) {  // td = td pp2y - pp4y dery(u), :339-372 (the dery carries its ppy factor)
     const double *pp2 = B(S.d_pp), *pp4 = B(S.d_pp) + S.p.ny;
     const int nx_ = S.p.nx, ny_ = S.p.ny;
@@ -486,8 +555,9 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
     const PreOp *ops[3] = {&S.d1[1][1], &S.d1[1][0], &S.d1[1][1]};
     const double *fld[3] = {u, v, w};
     double *dst[3] = {td, te, tf};
+    const double lin[3] = {bx, by, bz};
     for (int c = 0; c < 3; ++c) {
-      run(ctx, *ops[c], fld[c], tj);
+      run(*ops[c], fld[c], tj, lin[c]);
       double *t2 = dst[c];
       map(ctx, n, [=] __device__(long long q) {
         const int j = static_cast<int>((q / nx_) % ny_);
@@ -496,13 +566,24 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
     }
   }
   // x diffusion and final sum, :442-470
-  run(ctx, S.d2[0][0], u, ta); run(ctx, S.d2[0][1], v, tb); run(ctx, S.d2[0][1], w, tc);
+  run(S.d2[0][0], u, ta, bx); run(S.d2[0][1], v, tb, by); run(S.d2[0][1], w, tc, bz);
   map(ctx, n, [=] __device__(long long q) {
     const double ax = xnu * td[q] + tg2[q], ay = xnu * te[q] + th2[q], az = xnu * tf[q] + ti2[q];
     dux1[q] = ax - half * tg1[q] + xnu * ta[q];
     duy1[q] = ay - half * th1[q] + xnu * tb[q];
     duz1[q] = az - half * ti1[q] + xnu * tc[q];
   });
+  // momentum_forcing_channel (the end of momentum_rhs_eq, src/transeq.f90:539 -> src/Case-Channel.f90:396-420, idir_stream = 1)
+  if (S.p.itype == 3) {
+    if (S.cs.cpg) {
+      const double f = S.fcpg;
+      map(ctx, n, [=] __device__(long long q) { dux1[q] = dux1[q] + f; });
+    }
+    if (S.itime < S.cs.spinup_time && S.cs.iin <= 2 && S.cs.wrotation != 0.0) {
+      const double wr = S.cs.wrotation;
+      map(ctx, n, [=] __device__(long long q) { dux1[q] = dux1[q] - wr * v[q]; duy1[q] = duy1[q] + wr * u[q]; });
+    }
+  }
 }
 
 // Fused form of momentum_rhs for periodic y and z: per direction one kernel forms
@@ -717,11 +798,25 @@ static void pre_correc(Ctx &ctx, SolverImpl &S, int itr) {
     double *dx_ = d, *dy_ = d + 4 * nyz, *dz_ = d + 4 * nyz + 4 * nxz;
     const bool dx1 = S.p.nclx1 == 2, dxn = S.p.nclxn == 2, dy1 = S.p.ncly1 == 2, dyn = S.p.nclyn == 2;
     const bool dz1 = S.p.nclz1 == 2 && S.z0 == 0, dzn = S.p.nclzn == 2 && S.z0 + nzl == S.p.nz;
+    double *bw = B(S.bwx);   // bxx1 bxy1 bxz1 bxxn bxyn bxzn
+    // inflow / outflow flow-rate balance, navier.f90:534-560 (channel, uniform, abl with nclx = 2 on both sides; not itype_cyl)
+    if (S.p.itype == 3 && dx1 && dxn && nyz > 0) {
+      double *partial = B(S.red_partial), *dout = B(S.red_out) + 13;
+      const int nb = gridn(ctx, nyz) > 4096 ? 4096 : gridn(ctx, nyz);
+      k_reduce_partial<2><<<nb, 256, 0, ctx.stream>>>(nyz, [=] __device__(long long q, double *acc) { acc[0] += bw[q]; acc[1] += bw[3 * nyz + q]; }, partial);
+      X3D_CUDA(cudaGetLastError()); ctx.launches++;
+      k_reduce_final<2><<<1, 256, 0, ctx.stream>>>(nb, partial, dout);
+      X3D_CUDA(cudaGetLastError()); ctx.launches++;
+      allreduce(ctx, dout, 2, false);
+      const double inv = 1.0 / (static_cast<double>(ny) * static_cast<double>(S.p.nz));
+      map(ctx, nyz, [=] __device__(long long q) { bw[3 * nyz + q] = bw[3 * nyz + q] - dout[1] * inv + dout[0] * inv; });
+    }
     if (dx1 || dxn)
-      map(ctx, nyz, [=] __device__(long long q) {  // q = j + ny k ; planes: dpdyx1, dpdzx1, dpdyxn, dpdzxn
-        if (dx1) { const double a = dx_[q] * g, b = dx_[nyz + q] * g; dx_[q] = a; dx_[nyz + q] = b; u[q * nx] = 0.0; v[q * nx] = a; w[q * nx] = b; }
+      map(ctx, nyz, [=] __device__(long long q) {  // q = j + ny k ; planes: dpdyx1, dpdzx1, dpdyxn, dpdzxn (navier.f90:564-595)
+        if (dx1) { const double a = dx_[q] * g, b = dx_[nyz + q] * g; dx_[q] = a; dx_[nyz + q] = b;
+                   u[q * nx] = bw[q]; v[q * nx] = bw[nyz + q] + a; w[q * nx] = bw[2 * nyz + q] + b; }
         if (dxn) { const double a = dx_[2 * nyz + q] * g, b = dx_[3 * nyz + q] * g; dx_[2 * nyz + q] = a; dx_[3 * nyz + q] = b;
-                   u[q * nx + nx - 1] = 0.0; v[q * nx + nx - 1] = a; w[q * nx + nx - 1] = b; }
+                   u[q * nx + nx - 1] = bw[3 * nyz + q]; v[q * nx + nx - 1] = bw[4 * nyz + q] + a; w[q * nx + nx - 1] = bw[5 * nyz + q] + b; }
       });
     if (dy1 || dyn)
       map(ctx, nxz, [=] __device__(long long q) {  // q = i + nx k ; planes: dpdxy1, dpdzy1, dpdxyn, dpdzyn
@@ -761,9 +856,21 @@ static void pre_correc(Ctx &ctx, SolverImpl &S, int itr) {
 static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   double *pp1 = B(S.w[0]), *pgy1 = B(S.w[1]), *pgz1 = B(S.w[2]), *upi2 = B(S.w[3]), *duy = B(S.w[4]), *po3 = B(S.w[5]);
   double *t1 = B(S.w[6]), *t2 = B(S.w[7]);
-  run(ctx, S.dvp[0], B(S.ux), pp1);    // :297
-  run(ctx, S.ivp[0], B(S.uy), pgy1);   // :313
-  run(ctx, S.ivp[0], B(S.uz), pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
+  const double *ta1 = B(S.ux), *tb1 = B(S.uy), *tc1 = B(S.uz);
+  if (S.cs.iibm != 0) {  // :285-293: (1 - ep1) u + ep1 ubc
+    if (!S.ep1.p) throw Error("solver: iibm /= 0 without x3d_solver_set_ibm_mask");
+    double *a = B(S.w[11]), *b = B(S.w[12]), *c = B(S.w[13]);
+    const double *ep = B(S.ep1), *u = B(S.ux), *v = B(S.uy), *w = B(S.uz);
+    const double ubx = S.cs.ubcx, uby = S.cs.ubcy, ubz = S.cs.ubcz, one = 1.0;
+    map(ctx, static_cast<long long>(S.n), [=] __device__(long long q) {
+      const double e = ep[q];
+      a[q] = (one - e) * u[q] + e * ubx; b[q] = (one - e) * v[q] + e * uby; c[q] = (one - e) * w[q] + e * ubz;
+    });
+    ta1 = a; tb1 = b; tc1 = c;
+  }
+  run(ctx, S.dvp[0], ta1, pp1);    // :297
+  run(ctx, S.ivp[0], tb1, pgy1);   // :313
+  run(ctx, S.ivp[0], tc1, pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
   run(ctx, S.dvp[1], pgy1, duy);       // :322
   if (S.fuse_sums) {
     run(ctx, S.ivp_y_add, pp1, duy);   // :321 + :325: duy += interyvp(pp1), accumulated by the operator's store
@@ -866,8 +973,8 @@ void solver_step(Ctx &ctx, int nsteps) {
   for (int st = 0; st < nsteps; ++st) {
     S.itime += 1;
     for (int itr = 1; itr <= S.iadvance; ++itr) {  // xcompact3d.f90:46-88
-      boundary_conditions(ctx, S);
-      if (S.fused[1] && S.fused[2]) {
+      boundary_conditions(ctx, S, itr);
+      if (S.fused[1] && S.fused[2] && S.cs.iibm == 0) {
         double *rhs[3] = {B(S.w[0]), B(S.w[1]), B(S.w[2])}, *extra[3];
         if (!momentum_rhs_fused(ctx, S, rhs, extra, itr)) intt3_fused(ctx, S, itr, rhs, extra);
       } else {
@@ -1000,6 +1107,64 @@ void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz) {
   X3D_CUDA(cudaMemcpyAsync(uz, S.uz.p, bytes, cudaMemcpyDefault, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
 }
+// x3d_solver_set_case: channel forcing, cylinder inflow / outflow, immersed boundary
+void solver_set_case(Ctx &ctx, const x3d_case_params &c) {
+  SolverImpl &S = SOL(ctx);
+  if (c.iibm != 0 && c.iibm != 2 && c.iibm != 3) throw Error("x3d_solver_set_case: iibm 0, 2 (lagpol) and 3 (cubspl) are implemented");
+  if (c.iibm != 0 && S.nranks > 1) throw Error("x3d_solver_set_case: the immersed-boundary step runs on one rank");
+  if (c.cpg && S.p.itype != 3) throw Error("x3d_solver_set_case: cpg is a channel option");
+  S.cs = c;
+  S.xnu = 1.0 / S.p.re;
+  S.fcpg = 0.0;
+  if (c.cpg) {  // src/parameters.f90:303-311
+    const double re_cent = pow(S.p.re / 0.116, 1.0 / 0.88);
+    S.xnu = 1.0 / re_cent;
+    S.fcpg = 2.0 / S.p.yly * ((S.p.re / re_cent) * (S.p.re / re_cent));
+  }
+  ctx.iibm = 0;   // the solver runs the pre-pass itself (the operator entry points would run it a second time)
+}
+void solver_set_ibm_mask(Ctx &ctx, const double *ep1) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  S.ep1.reserve(std::max<size_t>(S.n, 1) * sizeof(double));
+  X3D_CUDA(cudaMemcpyAsync(S.ep1.p, ep1, S.n * sizeof(double), cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+void solver_set_inflow_noise(Ctx &ctx, const double *bxo, const double *byo, const double *bzo) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  const size_t nyz = static_cast<size_t>(S.p.ny) * S.nzl;
+  S.bnoise.reserve(3 * std::max<size_t>(nyz, 1) * sizeof(double));
+  X3D_CUDA(cudaMemsetAsync(S.bnoise.p, 0, S.bnoise.bytes, ctx.stream));
+  const double *src[3] = {bxo, byo, bzo};
+  for (int q = 0; q < 3; ++q)
+    if (src[q]) X3D_CUDA(cudaMemcpyAsync(B(S.bnoise) + q * nyz, src[q], nyz * sizeof(double), cudaMemcpyDefault, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+void solver_wall_velocity_x(Ctx &ctx, const double *const in6[6], double *const out6[6]) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  if (!S.bwx.p) throw Error("solver: the x faces are not Dirichlet faces");
+  const size_t nyz = static_cast<size_t>(S.p.ny) * S.nzl;
+  for (int q = 0; q < 6; ++q) {
+    if (in6 && in6[q]) X3D_CUDA(cudaMemcpyAsync(B(S.bwx) + q * nyz, in6[q], nyz * sizeof(double), cudaMemcpyDefault, ctx.stream));
+    if (out6 && out6[q]) X3D_CUDA(cudaMemcpyAsync(out6[q], B(S.bwx) + q * nyz, nyz * sizeof(double), cudaMemcpyDefault, ctx.stream));
+  }
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+// init_cyl with iin = 0, Case-Cylinder-wake.f90:205-279: uniform stream u1
+void solver_init_cyl(Ctx &ctx) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  double *ux = B(S.ux), *uy = B(S.uy), *uz = B(S.uz);
+  const double u1 = S.cs.u1;
+  map(ctx, static_cast<long long>(S.n), [=] __device__(long long q) { ux[q] = 0.0 + u1; uy[q] = 0.0; uz[q] = 0.0; });
+  for (int q = 0; q < S.ntime; ++q)
+    for (DevBuf *b : {&S.dux[q], &S.duy[q], &S.duz[q]}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
+  for (DevBuf *b : {&S.px, &S.py, &S.pz, &S.pp3, &S.dpd}) X3D_CUDA(cudaMemsetAsync(b->p, 0, b->bytes, ctx.stream));
+  S.itime = 0;
+}
+
 // One job = copy a host velocity field in, advance it nsteps, copy the result out; asynchronous with respect to the
 // host.  Consecutive jobs are independent (each starts from its own host input), so the copies of neighbouring jobs
 // overlap the kernels of the current one: H2D on s_in, kernels on ctx.stream, D2H on s_out, three device velocity

@@ -1,4 +1,5 @@
 // capi.cpp -- C entry points of the oracle for ctypes (TEST INFRASTRUCTURE).
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <stdexcept>
@@ -262,6 +263,27 @@ int x3do_solver_set_ibm_geometry(void *sv, int axis, int nobjmax, int npif, int 
     I.set = true;
     return 0;
   } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// channel forcing of the assembled step (momentum_forcing_channel, Case-Channel.f90:396-420); with cpg the viscosity and
+// the pressure gradient follow parameters.f90:303-311 as in Solver::init
+void x3do_solver_set_channel_forcing(void *sv, int cpg, double wrotation, int spinup_time, int iin) {
+  auto *s = static_cast<Solver *>(sv);
+  s->p.cpg = cpg != 0; s->p.wrotation = wrotation; s->p.spinup_time = spinup_time; s->p.iin = iin;
+  s->xnu = 1.0 / s->p.re;
+  s->fcpg = 0.0;
+  if (s->p.cpg) {
+    const double re_cent = std::pow(s->p.re / 0.116, 1.0 / 0.88);
+    s->xnu = 1.0 / re_cent;
+    s->fcpg = 2.0 / s->p.yly * ((s->p.re / re_cent) * (s->p.re / re_cent));
+  }
+}
+// inflow noise of the assembled cylinder step: the random planes bxo, byo, bzo (ny, nz) and their amplitude
+void x3do_solver_set_inflow_noise(void *sv, double inflow_noise, const double *bxo, const double *byo, const double *bzo) {
+  auto *s = static_cast<Solver *>(sv);
+  s->p.inflow_noise = inflow_noise;
+  if (bxo) std::memcpy(s->bxo.data(), bxo, s->bxo.size() * 8);
+  if (byo) std::memcpy(s->byo.data(), byo, s->byo.size() * 8);
+  if (bzo) std::memcpy(s->bzo.data(), bzo, s->bzo.size() * 8);
 }
 void x3do_solver_init_cyl(void *sv, double u1, double u2) {
   auto *s = static_cast<Solver *>(sv);
