@@ -27,6 +27,7 @@ void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz);
 void solver_local_shape(Ctx &ctx, int *d3, int *z0);
 void solver_advance_host(Ctx &ctx, const double *const in[3], double *const out[3], int nsteps);
 void solver_host_sync(Ctx &ctx);
+void decomp_check(Ctx &ctx);
 void solver_set_case(Ctx &ctx, const x3d_case_params &c);
 void solver_set_ibm_mask(Ctx &ctx, const double *ep1);
 void solver_set_inflow_noise(Ctx &ctx, const double *bxo, const double *byo, const double *bzo);
@@ -53,8 +54,16 @@ struct x3d_ctx {
 
 static thread_local std::string g_last_error;
 
+// every entry point selects the context's device; the caller's current device is put back on the way out
+struct DeviceRestore {
+  int dev = -1;
+  DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+  ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 template <class F>
 static int guard(F &&f) {
+  DeviceRestore keep;
   try {
     f();
     return 0;
@@ -107,6 +116,7 @@ int x3d_sync(x3d_ctx *ctx) {
   return guard([&] {
     X3D_CUDA(cudaSetDevice(ctx->c.device));
     X3D_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    decomp_check(ctx->c);
   });
 }
 unsigned long long x3d_stream(x3d_ctx *ctx) { return reinterpret_cast<unsigned long long>(ctx->c.stream); }
@@ -406,7 +416,7 @@ int x3d_solver_set_velocity(x3d_ctx *ctx, const double *ux, const double *uy, co
   return guard([&] { solver_set_velocity(ctx->c, ux, uy, uz); });
 }
 int x3d_solver_get_velocity(x3d_ctx *ctx, double *ux, double *uy, double *uz) {
-  return guard([&] { solver_get_velocity(ctx->c, ux, uy, uz); });
+  return guard([&] { solver_get_velocity(ctx->c, ux, uy, uz); decomp_check(ctx->c); });
 }
 int x3d_solver_local_shape(x3d_ctx *ctx, int *dims3, int *zstart0) {
   return guard([&] { solver_local_shape(ctx->c, dims3, zstart0); });
@@ -441,7 +451,7 @@ int x3d_solver_get_wall_velocity_x(x3d_ctx *ctx, double *const planes6[6]) {
 int x3d_solver_init_cyl(x3d_ctx *ctx) { return guard([&] { solver_init_cyl(ctx->c); }); }
 int x3d_solver_host_sync(x3d_ctx *ctx) { return guard([&] { solver_host_sync(ctx->c); }); }
 int x3d_solver_step(x3d_ctx *ctx, int nsteps) { return guard([&] { solver_step(ctx->c, nsteps); }); }
-int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5) { return guard([&] { solver_diagnostics_tgv(ctx->c, out5); }); }
+int x3d_solver_diagnostics_tgv(x3d_ctx *ctx, double *out5) { return guard([&] { solver_diagnostics_tgv(ctx->c, out5); decomp_check(ctx->c); }); }
 int x3d_solver_divergence(x3d_ctx *ctx, double *divmax, double *divmean) {
   return guard([&] { solver_divergence(ctx->c, divmax, divmean); });
 }

@@ -8,7 +8,7 @@ namespace x3d {
 // transposes find the allocation a pointer belongs to (cudaIpcGetMemHandle needs the base)
 void register_alloc(void *p, size_t n);
 void unregister_alloc(void *p);
-bool find_alloc(const void *q, void **base, size_t *size);
+bool find_alloc(const void *q, void **base, size_t *size, unsigned long long *gen = nullptr);
 
 struct DevBuf {
   void *p = nullptr;

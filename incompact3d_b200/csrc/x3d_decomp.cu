@@ -106,9 +106,14 @@ struct DecompImpl : DecompState {
     DevBuf flags;                         // my flag array [np] (peers store their epoch here)
     DevBuf d_peer_flags;                  // device array [np] of pointers to every member's flag array
     unsigned long long epoch = 0;
-    std::map<const void *, DevBuf> dst_cache;   // local destination pointer -> device array [np] of member pointers
-    std::map<const void *, bool> dst_bad;
-    std::map<const void *, std::vector<void *>> dst_host;   // the same member pointers on the host (block copies)
+    long long timeout_cycles = 0;
+    int *d_status = nullptr;
+    // keyed by (local destination pointer, number of the allocation it lies in): an address reused by a later
+    // allocation is a different buffer and is exchanged again (entries of released buffers are never hit)
+    using Key = std::pair<const void *, unsigned long long>;
+    std::map<Key, DevBuf> dst_cache;            // -> device array [np] of member pointers
+    std::map<Key, bool> dst_bad;
+    std::map<Key, std::vector<void *>> dst_host;   // the same member pointers on the host (block copies)
   };
   Group grp_row, grp_col;
   bool p2p = false;
@@ -118,6 +123,10 @@ struct DecompImpl : DecompState {
   // 512^3 step, ~630 GB/s per direction), one kernel for all members below that, where the per-copy launch cost of
   // the engines would show.  X3D_P2P_MODE overrides.
   int p2p_mode = -1;
+  // device-side barrier: give up after this many clock cycles and raise *status (mapped host memory) instead of
+  // spinning for ever; the host turns the flag into an error at its next synchronisation point (decomp_check)
+  long long barrier_timeout_cycles = 0;
+  int *h_status = nullptr, *d_status = nullptr;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // bytes this rank sent to OTHER members (what crosses NVLink) and transposed fields, since x3d_decomp_init
@@ -127,6 +136,7 @@ struct DecompImpl : DecompState {
   std::map<std::array<unsigned char, 64>, void *> ipc_opened;
   ~DecompImpl() override {
     for (auto &kv : ipc_opened) cudaIpcCloseMemHandle(kv.second);
+    if (h_status) cudaFreeHost(h_status);
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -293,8 +303,31 @@ void decomp_init(Ctx &ctx, int nx, int ny, int nz, int p_row, int p_col, int ran
     const char *e = getenv("X3D_P2P");
     D->p2p = !(e && atoi(e) == 0);
     if (const char *m = getenv("X3D_P2P_MODE")) D->p2p_mode = atoi(m);
+    {
+      double secs = 120.0;
+      if (const char *t = getenv("X3D_BARRIER_TIMEOUT_S")) secs = atof(t);
+      int khz = 1900000;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx.device);
+      D->barrier_timeout_cycles = static_cast<long long>(secs * 1e3 * static_cast<double>(khz));
+      X3D_CUDA(cudaHostAlloc(&D->h_status, sizeof(int), cudaHostAllocMapped));
+      *D->h_status = 0;
+      X3D_CUDA(cudaHostGetDevicePointer(&D->d_status, D->h_status, 0));
+    }
+    // every rank must take the same path afterwards: agree on the outcome over the world communicator after each group
+    auto agree = [&]() {
+      int mine = D->p2p ? 1 : 0, *d_flag = nullptr;
+      X3D_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+      X3D_CUDA(cudaMemcpyAsync(d_flag, &mine, sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+      X3D_NCCL(N.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, D->world, ctx.stream));
+      X3D_CUDA(cudaMemcpyAsync(&mine, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+      X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+      cudaFree(d_flag);
+      D->p2p = mine != 0;
+    };
     if (D->p2p) p2p_setup_group(ctx, *D, D->grp_row, D->comm_row, p_row, D->row);
+    agree();
     if (D->p2p) p2p_setup_group(ctx, *D, D->grp_col, D->comm_col, p_col, D->col);
+    agree();
   }
   ctx.decomp = std::move(D);
 }
@@ -363,7 +396,7 @@ struct XchgRec {            // what every member publishes about one of its buff
 
 // one thread per group member: publish my epoch in the member's flag array, wait for the member's epoch in mine
 __global__ void k_group_barrier(unsigned long long *const *__restrict__ peer_flags, unsigned long long *my_flags, int me, int np,
-                                unsigned long long epoch) {
+                                unsigned long long epoch, long long timeout_cycles, int *status) {
   const int m = threadIdx.x;
   if (m >= np) return;
   __threadfence_system();
@@ -373,8 +406,14 @@ __global__ void k_group_barrier(unsigned long long *const *__restrict__ peer_fla
   const long long t0 = clock64();
   do {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flags + m) : "memory");
-    if (clock64() - t0 > 20000000000LL) asm volatile("trap;");  // ~10 s: a member never arrived -> fail instead of hanging
-  } while (seen < epoch);
+    if (seen >= epoch) break;
+    __nanosleep(100);
+    if (clock64() - t0 > timeout_cycles) {   // a member never arrived: report and go on instead of hanging or trapping
+      *reinterpret_cast<volatile int *>(status) = 1 + m;
+      __threadfence_system();
+      break;
+    }
+  } while (true);
 }
 
 // element (i,j,k) of the local source pencil -> destination pencil of the member that owns it
@@ -442,7 +481,7 @@ __global__ void __launch_bounds__(256) k_p2p_blocks(const __grid_constant__ Bloc
 static void group_barrier(Ctx &ctx, DecompImpl::Group &G) {
   G.epoch++;
   k_group_barrier<<<1, 32, 0, ctx.stream>>>(static_cast<unsigned long long *const *>(G.d_peer_flags.p),
-                                             static_cast<unsigned long long *>(G.flags.p), G.me, G.np, G.epoch);
+                                             static_cast<unsigned long long *>(G.flags.p), G.me, G.np, G.epoch, G.timeout_cycles, G.d_status);
   X3D_CUDA(cudaGetLastError());
   ctx.launches++;
 }
@@ -506,7 +545,9 @@ static bool exchange_pointers(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, con
 
 static void p2p_setup_group(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, ncclComm_t comm, int np, int me) {
   G.np = np; G.me = me; G.comm = comm;
+  G.timeout_cycles = D.barrier_timeout_cycles; G.d_status = D.d_status;
   if (np <= 1) return;
+  if (np > 32) { D.p2p = false; return; }   // the flag barrier has one thread per member: larger groups use NCCL
   G.flags.reserve(sizeof(unsigned long long) * 32);
   X3D_CUDA(cudaMemsetAsync(G.flags.p, 0, sizeof(unsigned long long) * 32, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -518,20 +559,24 @@ static void p2p_setup_group(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, ncclC
 }
 
 // member pointers of a destination buffer (device array), exchanged once per buffer; nullptr -> use NCCL
-static void *const *p2p_dst(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, const void *dst) {
+static void *const *p2p_dst(Ctx &ctx, DecompImpl &D, DecompImpl::Group &G, const void *dst, const std::vector<void *> **hosts = nullptr) {
   // Only buffers the library allocated itself take this path: they are allocated by the same code on every
   // member, so cache hits and misses (= collective pointer exchanges) happen on all members together.  A
   // caller-owned buffer (e.g. a framework tensor) has no such symmetry and always uses the NCCL exchange.
   void *base = nullptr;
   size_t size = 0;
-  if (!find_alloc(dst, &base, &size)) return nullptr;
-  auto it = G.dst_cache.find(dst);
-  if (it != G.dst_cache.end()) return static_cast<void *const *>(it->second.p);
-  if (G.dst_bad.count(dst)) return nullptr;
+  unsigned long long gen = 0;
+  if (!find_alloc(dst, &base, &size, &gen)) return nullptr;
+  const DecompImpl::Group::Key key{dst, gen};
+  if (hosts) *hosts = nullptr;
+  auto it = G.dst_cache.find(key);
+  if (it != G.dst_cache.end()) { if (hosts) *hosts = &G.dst_host[key]; return static_cast<void *const *>(it->second.p); }
+  if (G.dst_bad.count(key)) return nullptr;
   std::vector<void *> ptrs;
-  if (!exchange_pointers(ctx, D, G, dst, ptrs)) { G.dst_bad[dst] = true; return nullptr; }
-  G.dst_host[dst] = ptrs;
-  DevBuf &b = G.dst_cache[dst];
+  if (!exchange_pointers(ctx, D, G, dst, ptrs)) { G.dst_bad[key] = true; return nullptr; }
+  G.dst_host[key] = ptrs;
+  if (hosts) *hosts = &G.dst_host[key];
+  DevBuf &b = G.dst_cache[key];
   b.reserve(sizeof(void *) * G.np);
   X3D_CUDA(cudaMemcpyAsync(b.p, ptrs.data(), sizeof(void *) * G.np, cudaMemcpyHostToDevice, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -618,8 +663,10 @@ void decomp_stats(Ctx &ctx, unsigned long long *remote_bytes, unsigned long long
   *fields = D.stat_fields;
 }
 
-// device pointers; src and dst pencils of decomposition `id`
-void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem) {
+// device pointers; src and dst pencils of decomposition `id`.  allow_p2p = false: the destination is not allocated the
+// same way on every rank (the staging buffer of host-pointer calls grows with each rank's own sizes), so the collective
+// pointer exchange of the peer-to-peer path could be entered by some ranks only: NCCL exchange instead.
+static void transpose_device_impl(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem, bool allow_p2p) {
   DecompImpl &D = DEC(ctx);
   TransposePlan &T = get_plan(ctx, D, id, which);
   count_traffic(D, T, which, elem, 1);
@@ -632,7 +679,8 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
   if (!D.have_nccl) throw Error("transpose: this context was initialised without a NCCL id (pack/unpack only)");
   if (D.p2p) {
     DecompImpl::Group &G = (which == 0 || which == 3) ? D.grp_row : D.grp_col;
-    void *const *peers = p2p_dst(ctx, D, G, d_dst);
+    const std::vector<void *> *hosts = nullptr;
+    void *const *peers = allow_p2p ? p2p_dst(ctx, D, G, d_dst, &hosts) : nullptr;
     if (peers) {
       const SidePlan &S = T.send;
       const int ext = S.dims[S.axis], np = T.npeers;
@@ -641,7 +689,7 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
       group_barrier(ctx, G);  // every member has finished with its destination pencil
       BlockCopies bc;
       int nb = 0;
-      if (D.p2p_mode != 0 && block_copies(T, G, d_src, G.dst_host[d_dst], elem, bc, nb)) {
+      if (D.p2p_mode != 0 && block_copies(T, G, d_src, *hosts, elem, bc, nb)) {
         ProfScope ps(ctx, "transpose_p2p(block copies)");
         run_block_copies(ctx, D, bc, nb);
       } else if (ns > 0) {
@@ -688,6 +736,20 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
   boxcopy<false>(ctx, T.recv, rb, d_dst, elem);
 }
 
+void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, int id, int elem) {
+  transpose_device_impl(ctx, which, d_src, d_dst, id, elem, true);
+}
+
+// the barrier kernels report a member that never arrived through mapped host memory: turn it into an error
+void decomp_check(Ctx &ctx) {
+  auto *D = dynamic_cast<DecompImpl *>(ctx.decomp.get());
+  if (!D || !D->h_status) return;
+  const int st = *reinterpret_cast<volatile int *>(D->h_status);
+  if (st != 0)
+    throw Error("pencil transpose: group member " + std::to_string(st - 1) + " did not reach a device-side barrier within "
+                "X3D_BARRIER_TIMEOUT_S (default 120 s); the data of this context is no longer valid");
+}
+
 // several fields through the same transpose: one pair of group barriers around all the peer-store kernels
 void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_src, double *const *d_dst, int id, int elem) {
   DecompImpl &D = DEC(ctx);
@@ -695,9 +757,10 @@ void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_
   bool p2p = D.p2p && D.have_nccl && T.npeers > 1 && nf > 1;
   DecompImpl::Group &G = (which == 0 || which == 3) ? D.grp_row : D.grp_col;
   std::vector<void *const *> peers(nf, nullptr);
+  std::vector<const std::vector<void *> *> hosts(nf, nullptr);
   if (p2p)
     for (int f = 0; f < nf; ++f) {  // every member resolves every field (collective on a first use), then all agree
-      peers[f] = p2p_dst(ctx, D, G, d_dst[f]);
+      peers[f] = p2p_dst(ctx, D, G, d_dst[f], &hosts[f]);
       if (!peers[f]) p2p = false;
     }
   if (!p2p) {
@@ -714,7 +777,7 @@ void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_
   std::vector<BlockCopies> bcs(nf);
   std::vector<int> nbs(nf, 0);
   bool blocks = D.p2p_mode != 0;
-  for (int f = 0; f < nf && blocks; ++f) blocks = block_copies(T, G, d_src[f], G.dst_host[d_dst[f]], elem, bcs[f], nbs[f]);
+  for (int f = 0; f < nf && blocks; ++f) blocks = block_copies(T, G, d_src[f], *hosts[f], elem, bcs[f], nbs[f]);
   if (blocks) {
     ProfScope ps(ctx, "transpose_p2p(block copies)");
     for (int f = 0; f < nf; ++f) run_block_copies(ctx, D, bcs[f], nbs[f]);
@@ -822,7 +885,7 @@ void transpose(Ctx &ctx, int which, const double *src, double *dst, int id, int 
   double *dd = dst;
   if (!sdev) { ctx.stage_in.reserve(bs); X3D_CUDA(cudaMemcpyAsync(ctx.stage_in.p, src, bs, cudaMemcpyHostToDevice, ctx.stream)); ds = static_cast<double *>(ctx.stage_in.p); }
   if (!ddev) { ctx.stage_out.reserve(br); dd = static_cast<double *>(ctx.stage_out.p); }
-  transpose_device(ctx, which, ds, dd, id, elem);
+  transpose_device_impl(ctx, which, ds, dd, id, elem, ddev);
   if (!ddev) X3D_CUDA(cudaMemcpyAsync(dst, dd, br, cudaMemcpyDeviceToHost, ctx.stream));
   if (!sdev || !ddev) X3D_CUDA(cudaStreamSynchronize(ctx.stream));
 }

@@ -249,7 +249,11 @@ void set_ibm_geometry(Ctx &ctx, int axis, int nobjmax, int npif, int izap, int n
                       const double *xf, const int *nipif, const int *nfpif, const double *coords, int ncoords, double d, double len) {
   if (axis < 0 || axis > 2 || nobjmax < 1 || na < 1 || nb < 1 || !nobj || !xi || !xf || !nipif || !nfpif) throw Error("x3d_set_ibm_geometry: bad argument");
   if (npif < 1 || 2 * npif + 2 > 10) throw Error("x3d_set_ibm_geometry: npif must be 1..4 (xa, ya hold 10 points, src/ibm.f90:97)");
-  if (axis == 1 && !coords) throw Error("x3d_set_ibm_geometry: lagpoly needs yp");
+  if (axis == 1 && !coords && !ctx.st_yp.empty()) {   // the host's yp went in through x3d_set_stretching
+    coords = ctx.st_yp.data();
+    ncoords = static_cast<int>(ctx.st_yp.size());
+  }
+  if (axis == 1 && !coords) throw Error("x3d_set_ibm_geometry: lagpoly needs yp (pass it here or call x3d_set_stretching first)");
   X3D_CUDA(cudaSetDevice(ctx.device));
   Ctx::IbmAxis &G = ctx.ibm[axis];
   G.nobjmax = nobjmax; G.npif = npif; G.izap = izap; G.na = na; G.nb = nb; G.d = d; G.len = len; G.ncoords = coords ? ncoords : 0;

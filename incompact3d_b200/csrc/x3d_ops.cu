@@ -24,24 +24,27 @@ Ctx::~Ctx() {
 
 // ---- registry of library-owned device allocations -------------------------------------------------
 static std::mutex g_alloc_mu;
-static std::map<uintptr_t, size_t> g_allocs;
+struct AllocRec { size_t size; unsigned long long gen; };
+static std::map<uintptr_t, AllocRec> g_allocs;
+static unsigned long long g_alloc_gen = 0;   // every allocation gets its own number: a reused address is a new buffer
 void register_alloc(void *p, size_t n) {
   std::lock_guard<std::mutex> lk(g_alloc_mu);
-  g_allocs[reinterpret_cast<uintptr_t>(p)] = n;
+  g_allocs[reinterpret_cast<uintptr_t>(p)] = AllocRec{n, ++g_alloc_gen};
 }
 void unregister_alloc(void *p) {
   std::lock_guard<std::mutex> lk(g_alloc_mu);
   g_allocs.erase(reinterpret_cast<uintptr_t>(p));
 }
-bool find_alloc(const void *q, void **base, size_t *size) {
+bool find_alloc(const void *q, void **base, size_t *size, unsigned long long *gen) {
   std::lock_guard<std::mutex> lk(g_alloc_mu);
   const uintptr_t a = reinterpret_cast<uintptr_t>(q);
   auto it = g_allocs.upper_bound(a);
   if (it == g_allocs.begin()) return false;
   --it;
-  if (a >= it->first + it->second) return false;
+  if (a >= it->first + it->second.size) return false;
   *base = reinterpret_cast<void *>(it->first);
-  *size = it->second;
+  *size = it->second.size;
+  if (gen) *gen = it->second.gen;
   return true;
 }
 
@@ -195,9 +198,8 @@ void run_op(Ctx &ctx, OpCall &call, const double *u, double *t) {
         ctx.launches++;
         X3D_CUDA(cudaStreamSynchronize(ctx.stream));
         t_needs_upload = true;
-      } else {
-        return;  // nothing to do, t untouched
       }
+      // else: nothing to do for t (it stays untouched); a rebuilt input still goes back to the caller below
     } else {
       launch_line_op(ctx, op, call, d_u, d_t);
       t_needs_upload = true;

@@ -19,7 +19,8 @@ struct LineGeom {
 template <int KIND, int NT, int L, int LX, int NCMAX, int MINB>
 static void launch_strided_one(Ctx &ctx, const DevOp &op, const LineGeom &g, const TriTable &T, const double *u, double *t) {
   auto kern = k_strided<KIND, NT, L, LX, NCMAX, MINB>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};     // the attribute is per device
+  bool &configured = configured_dev[ctx.device & 63];
   if (!configured) {
     // leave most of the unified L1/shared array to L1 (coefficient rows are served from it)
     X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 25));
@@ -83,7 +84,8 @@ static void launch_tile_one(Ctx &ctx, const DevOp &op, const LineGeom &g, const 
   tg.nbx = (g.n1 + LX - 1) / LX;
   tg.ntiles = static_cast<long long>(tg.nbx) * g.nouter;
   const size_t smem = (static_cast<size_t>(NB) * tg.rows_slot * LX + 2 * 32 * (LX + 1) + 2 * LX + NB) * sizeof(double);
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};   // the attribute is per device: one record per device ordinal
+  size_t &configured = configured_dev[ctx.device & 63];
   static int per_sm = 1;
   const int threads = ((LX * T.nc + 31) / 32) * 32;
   if (smem > configured) {
@@ -147,7 +149,8 @@ static void launch_pair_one(Ctx &ctx, const DevOp &op, const LineGeom &g, const 
   PairGeom pg;
   size_t smem = 0;
   if (!pair_plan(op, g, L, u, t, pg, smem)) throw Error("internal: k_pair launched on an ineligible call");
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};   // the attribute is per device: one record per device ordinal
+  size_t &configured = configured_dev[ctx.device & 63];
   if (smem > configured) {
     X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
@@ -208,7 +211,8 @@ static void launch_contig_one(Ctx &ctx, const DevOp &op, const LineGeom &g, cons
   const int COEF = (7 * NP + (chead > 0 ? (2 * T.c_head_rs + 2) * L : 0) + 1) & ~1;
   const size_t smem = static_cast<size_t>(COEF + WPB * (NB * NBUF + 8) + WPB * NB) * sizeof(double);
   auto kern = k_contig<KIND, NT, L, WPB, NB, MINB, TMA>;
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};   // the attribute is per device: one record per device ordinal
+  size_t &configured = configured_dev[ctx.device & 63];
   if (smem > configured) {
     X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
