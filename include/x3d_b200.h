@@ -325,6 +325,10 @@ int x3d_solver_set_inflow_noise(x3d_ctx *ctx, const double *bxo, const double *b
  * planes; NULL keeps a plane.  The cylinder case overwrites them every sub-step (inflow / outflow).             */
 int x3d_solver_set_wall_velocity_x(x3d_ctx *ctx, const double *const planes6[6]);
 int x3d_solver_get_wall_velocity_x(x3d_ctx *ctx, double *const planes6[6]);
+/* apply_spatial_filter (src/tools.f90:600-675) on the solver's velocity: filx / fily / filz with the npaire pairing of
+ * the reference (the component along the filtered direction is odd), transposes included; ifilter 1 (all), 2 (x and
+ * z), 3 (y); af = the parameter of set_filter_coefficients (src/filters.f90:62-219)                             */
+int x3d_solver_apply_spatial_filter(x3d_ctx *ctx, int ifilter, double af);
 /* init_cyl with iin = 0 (src/Case-Cylinder-wake.f90:205-279): uniform stream ux = u1 */
 int x3d_solver_init_cyl(x3d_ctx *ctx);
 int x3d_solver_init(x3d_ctx *ctx, const x3d_solver_params *p);

@@ -457,6 +457,13 @@ def _solver_wall_velocity_x(self, planes=None):
     self._check(fn(self._h, arr))
 
 
+def _solver_apply_spatial_filter(self, ifilter=1, af=0.45):
+    """reference procedure `apply_spatial_filter(ux1,uy1,uz1,phi1)` (src/tools.f90:600-675) on the solver's velocity"""
+    fn = self._L.x3d_solver_apply_spatial_filter
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    self._check(fn(self._h, int(ifilter), float(af)))
+
+
 def _solver_init_cyl(self):
     fn = self._L.x3d_solver_init_cyl
     fn.argtypes = [C.c_void_p]
@@ -543,6 +550,7 @@ X3D.solver_set_ibm_mask = _solver_set_ibm_mask
 X3D.solver_set_inflow_noise = _solver_set_inflow_noise
 X3D.solver_wall_velocity_x = _solver_wall_velocity_x
 X3D.solver_init_cyl = _solver_init_cyl
+X3D.solver_apply_spatial_filter = _solver_apply_spatial_filter
 X3D.solver_host_sync = _solver_host_sync
 X3D.decomp_stats = _decomp_stats
 X3D.transpose_selftest = _transpose_selftest

@@ -28,6 +28,7 @@ void solver_local_shape(Ctx &ctx, int *d3, int *z0);
 void solver_advance_host(Ctx &ctx, const double *const in[3], double *const out[3], int nsteps);
 void solver_host_sync(Ctx &ctx);
 void decomp_check(Ctx &ctx);
+void solver_apply_spatial_filter(Ctx &ctx, int ifilter, double af);
 void solver_set_case(Ctx &ctx, const x3d_case_params &c);
 void solver_set_ibm_mask(Ctx &ctx, const double *ep1);
 void solver_set_inflow_noise(Ctx &ctx, const double *bxo, const double *byo, const double *bzo);
@@ -447,6 +448,9 @@ int x3d_solver_set_wall_velocity_x(x3d_ctx *ctx, const double *const planes6[6])
 }
 int x3d_solver_get_wall_velocity_x(x3d_ctx *ctx, double *const planes6[6]) {
   return guard([&] { solver_wall_velocity_x(ctx->c, nullptr, planes6); });
+}
+int x3d_solver_apply_spatial_filter(x3d_ctx *ctx, int ifilter, double af) {
+  return guard([&] { solver_apply_spatial_filter(ctx->c, ifilter, af); });
 }
 int x3d_solver_init_cyl(x3d_ctx *ctx) { return guard([&] { solver_init_cyl(ctx->c); }); }
 int x3d_solver_host_sync(x3d_ctx *ctx) { return guard([&] { solver_host_sync(ctx->c); }); }

@@ -156,6 +156,10 @@ struct SolverImpl : SolverState {
   // (navier.f90:325,339) and t -= op(u) for cor_vel folded into the last pressure-gradient operators (:242-244,426-430)
   PreOp ivp_y_add, dvp_z_add, dpv_x_sub, ipv_x_sub;
   bool fuse_sums = true;      // X3D_FUSE_SUMS=0 restores the separate elementwise passes
+  // apply_spatial_filter (src/tools.f90:600-675): filter operators per axis for the current filter parameter
+  PreOp fil[3][2];            // [axis][npaire]
+  LU3 fil_lu[3][2];
+  double fil_af = -1.0;
   // case glue: channel forcing, cylinder inflow / outflow, immersed boundary (x3d_solver_set_case)
   x3d_case_params cs{};
   double fcpg = 0.0;
@@ -1107,6 +1111,55 @@ void solver_get_velocity(Ctx &ctx, double *ux, double *uy, double *uz) {
   X3D_CUDA(cudaMemcpyAsync(uz, S.uz.p, bytes, cudaMemcpyDefault, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
 }
+// apply_spatial_filter, src/tools.f90:600-675 (called from the time loop when ifilter /= 0, src/xcompact3d.f90), on the
+// solver's velocity; af = the filter parameter of set_filter_coefficients (src/filters.f90:62-219, `filter(C_filter)`).
+// ifilter: 1 all directions, 2 x and z, 3 y only.
+void solver_apply_spatial_filter(Ctx &ctx, int ifilter, double af) {
+  SolverImpl &S = SOL(ctx);
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  if (ifilter < 1 || ifilter > 3) throw Error("x3d_solver_apply_spatial_filter: ifilter 1, 2 or 3");
+  const auto &p = S.p;
+  if (S.fil_af != af) {
+    const int nn[3] = {p.nx, p.ny, p.nz};
+    const int dxy[3] = {p.nx, p.ny, S.nzl}, dzp[3] = {p.nx, S.nyl, p.nz};
+    for (int a = 0; a < 3; ++a) {
+      make_filter_axis(nn[a], S.A[a].ncl1, S.A[a].ncln, af, ctx.fc[a], S.fil_lu[a][0], S.fil_lu[a][1]);
+      ctx.have_fc[a] = true;
+      for (int np = 0; np < 2; ++np) prep(ctx, S.fil[a][np], FIL, a, S.A[a], np, S.fil_lu[a][np], a == 2 ? dzp : dxy);
+    }
+    S.fil_af = af;
+  }
+  const long long n = static_cast<long long>(S.n);
+  double *vel[3] = {B(S.ux), B(S.uy), B(S.uz)};
+  double *f1[3] = {B(S.w[0]), B(S.w[1]), B(S.w[2])}, *f2[3] = {B(S.w[3]), B(S.w[4]), B(S.w[5])};
+  const int iibm = S.cs.iibm;
+  const double ubc[3] = {S.cs.ubcx, S.cs.ubcy, S.cs.ubcz};
+  auto fil = [&](int axis, int c, double *in, double *out) {   // the component along the axis is odd: npaire = 0 (:624-626,641-643,658-660)
+    const PreOp &P = S.fil[axis][c == axis ? 0 : 1];
+    if (iibm == 2) lagpol_device(ctx, axis, in, P.call.dims_in[0], P.call.dims_in[1], P.call.dims_in[2]);
+    else if (iibm == 3) cubspl_device(ctx, axis, in, P.call.dims_in[0], P.call.dims_in[1], P.call.dims_in[2], ubc[c]);
+    run(ctx, P, in, out);
+  };
+  double *cur[3] = {vel[0], vel[1], vel[2]};
+  if (ifilter == 1 || ifilter == 2) { for (int c = 0; c < 3; ++c) { fil(0, c, cur[c], f1[c]); cur[c] = f1[c]; } }
+  if (ifilter == 1 || ifilter == 3) { for (int c = 0; c < 3; ++c) { fil(1, c, cur[c], f2[c]); cur[c] = f2[c]; } }
+  if (ifilter == 1 || ifilter == 2) {
+    double *other[3];
+    for (int c = 0; c < 3; ++c) other[c] = (cur[c] == f2[c]) ? f1[c] : f2[c];
+    if (S.nranks == 1) {
+      for (int c = 0; c < 3; ++c) { fil(2, c, cur[c], other[c]); cur[c] = other[c]; }
+    } else {  // transpose_y_to_z, filz, transpose_z_to_y (:649-670)
+      double *z1[3] = {B(S.w[6]), B(S.w[7]), B(S.w[8])}, *z2[3] = {B(S.w[9]), B(S.w[10]), B(S.w[11])};
+      transpose_device_multi(ctx, 1, 3, cur, z1, S.id_v, 1);
+      for (int c = 0; c < 3; ++c) fil(2, c, z1[c], z2[c]);
+      transpose_device_multi(ctx, 2, 3, z2, other, S.id_v, 1);
+      for (int c = 0; c < 3; ++c) cur[c] = other[c];
+    }
+  }
+  for (int c = 0; c < 3; ++c)
+    if (cur[c] != vel[c]) X3D_CUDA(cudaMemcpyAsync(vel[c], cur[c], n * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+}
+
 // x3d_solver_set_case: channel forcing, cylinder inflow / outflow, immersed boundary
 void solver_set_case(Ctx &ctx, const x3d_case_params &c) {
   SolverImpl &S = SOL(ctx);
