@@ -38,6 +38,11 @@ struct PoissonImpl : PoissonState {
   int nyl = 0, nzl = 0, nzhl = 0, k0 = 0;
   DevBuf cwz, rwork2;
   cufftHandle plan_r2c = 0, plan_c2r = 0, plan_xy = 0;
+  // poisson_000: the x-y transforms and the spectral factor run plane-chunk by plane-chunk (forward FFT, factor, inverse
+  // FFT of fft_chunk planes before the next chunk) so that a chunk stays in the 126 MB L2 between the three passes and
+  // the spectral array crosses HBM once in each direction instead of three times.  X3D_FFT_CHUNK=0 turns it off.
+  cufftHandle plan_xy_chunk = 0, plan_xy_rem = 0;
+  int fft_chunk = 0;
   bool plans = false;
   DevBuf cw, cwb, rwork, tables, fftwork, maps;
   int *d_map[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [backward][axis]
@@ -52,6 +57,8 @@ struct PoissonImpl : PoissonState {
   DevBuf pen;                         // [nsys][7][rows][nzh][nx] double2: L1 L2 INV A1 B1, and the last-block terms
   ~PoissonImpl() override {
     if (plans) { cufftDestroy(plan_r2c); cufftDestroy(plan_c2r); cufftDestroy(plan_xy); }
+    if (plan_xy_chunk) cufftDestroy(plan_xy_chunk);
+    if (plan_xy_rem) cufftDestroy(plan_xy_rem);
   }
 };
 
@@ -133,13 +140,14 @@ __global__ void k_spec_000(SpecArgs a, double2 *__restrict__ cw) {
 //   out = -c |W|^2 / (nx ny nz kxyz),   |W|^2 = (az^2+bz^2)(ay^2+by^2)(ax^2+bx^2)  (= 1 up to rounding; kept).
 // One reciprocal-free division per mode, the row-constant parts of kxyz hoisted per (j,k) row, x tables in registers,
 // no 64-bit index arithmetic.  Agrees with the statement-by-statement form to a few ulp (tests: 1e-11).
-__global__ void __launch_bounds__(256) k_spec_000s(SpecArgs a, double2 *__restrict__ cw) {
-  const int rows = a.ny * a.nzh;
+__global__ void __launch_bounds__(256) k_spec_000s(SpecArgs a, double2 *__restrict__ cw, int kbeg, int kcnt) {
+  // planes kbeg .. kbeg + kcnt - 1 of the local spectral array (cw points at plane kbeg)
+  const int rows = a.ny * kcnt;
   for (int i = threadIdx.x; i < a.nx; i += blockDim.x) {
     const double xk = a.xk2[i], fx = a.tx[i], fx2 = fx * fx;
     const double wx = a.ax[i] * a.ax[i] + a.bx[i] * a.bx[i];
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-      const int j = row % a.ny, kl = row / a.ny, k = kl + a.k0;
+      const int j = row % a.ny, kl = row / a.ny, k = kl + kbeg + a.k0;
       const double fy = a.ty[j], fz = a.tz[2 * k];
       const double A = (fy * fz) * (fy * fz);
       const double BC = a.yk2[j] * (fz * fz) + a.zk2[2 * k] * (fy * fy);
@@ -658,7 +666,27 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   }
   int nyx[2] = {ny, nx};
   if (nzhl > 0) { X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, nzhl, &ws)); wmax = std::max(wmax, ws); }
+  if (!(p.bcx || p.bcy || p.bcz) && P->spec_real && nzhl > 0) {
+    int ch = 8;
+    // a chunk must fit the L2 with room to spare: at most ~48 MB of complex planes
+    const long long plane_bytes = static_cast<long long>(nx) * ny * 16;
+    while (ch > 1 && ch * plane_bytes > (48ll << 20)) ch /= 2;
+    if (const char *e = getenv("X3D_FFT_CHUNK")) ch = atoi(e);
+    if (ch > 0 && ch < nzhl && plane_bytes <= (48ll << 20)) {
+      P->fft_chunk = ch;
+      X3D_CUFFT(cufftCreate(&P->plan_xy_chunk));
+      X3D_CUFFT(cufftSetAutoAllocation(P->plan_xy_chunk, 0));
+      X3D_CUFFT(cufftMakePlanMany(P->plan_xy_chunk, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, ch, &ws)); wmax = std::max(wmax, ws);
+      if (nzhl % ch) {
+        X3D_CUFFT(cufftCreate(&P->plan_xy_rem));
+        X3D_CUFFT(cufftSetAutoAllocation(P->plan_xy_rem, 0));
+        X3D_CUFFT(cufftMakePlanMany(P->plan_xy_rem, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, nzhl % ch, &ws)); wmax = std::max(wmax, ws);
+      }
+    }
+  }
   P->fftwork.reserve(wmax ? wmax : 16);
+  for (cufftHandle h : {P->plan_xy_chunk, P->plan_xy_rem})
+    if (h) { X3D_CUFFT(cufftSetWorkArea(h, P->fftwork.p)); X3D_CUFFT(cufftSetStream(h, ctx.stream)); }
   X3D_CUFFT(cufftSetWorkArea(P->plan_r2c, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_c2r, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_xy, P->fftwork.p));
   X3D_CUFFT(cufftSetStream(P->plan_r2c, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_c2r, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_xy, ctx.stream));
   const size_t nsp_y = static_cast<size_t>(nx) * ny * std::max(nzhl, 1);       // spectral y-pencil
@@ -720,7 +748,22 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cwz)));
   }
   if (multi) transpose_device(ctx, 2, reinterpret_cast<double *>(cwz), reinterpret_cast<double *>(cw), P->id_sp, 2);  // z -> y
-  if (nzhl > 0) {
+  const bool chunked = !any && P->fft_chunk > 0 && nzhl > 0;
+  if (chunked) {
+    // forward x-y FFT, spectral factor, inverse x-y FFT, one L2-resident chunk of planes after the other
+    ProfScope ps(ctx, "fft_xy_fwd+spectral+fft_xy_inv(cuFFT + k_spec, L2-resident plane chunks)");
+    const long long plane = static_cast<long long>(nx) * ny;
+    for (int k0 = 0; k0 < nzhl; k0 += P->fft_chunk) {
+      const int cnt = std::min(P->fft_chunk, nzhl - k0);
+      cufftHandle h = cnt == P->fft_chunk ? P->plan_xy_chunk : P->plan_xy_rem;
+      cufftDoubleComplex *pc = reinterpret_cast<cufftDoubleComplex *>(cw + k0 * plane);
+      X3D_CUFFT(cufftExecZ2Z(h, pc, pc, CUFFT_FORWARD));
+      k_spec_000s<<<std::min<long long>(static_cast<long long>(ny) * cnt, 16LL * ctx.sm_count), 256, 0, ctx.stream>>>(a, cw + k0 * plane, k0, cnt);
+      X3D_CUDA(cudaGetLastError()); ctx.launches++;
+      X3D_CUFFT(cufftExecZ2Z(h, pc, pc, CUFFT_INVERSE));
+    }
+  }
+  if (nzhl > 0 && !chunked) {
     ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
     X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_FORWARD));
   }
@@ -730,10 +773,12 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     k_spec_stage<<<gs, 256, 0, ctx.stream>>>(a, mode, in, out);
     X3D_CUDA(cudaGetLastError()); ctx.launches++;
   };
-  if (!any) {
+  if (chunked) {
+    // done above
+  } else if (!any) {
     if (nsp > 0) {
       ProfScope ps(ctx, "poisson_spectral(k_spec)");
-      if (P->spec_real) k_spec_000s<<<std::min<long long>(static_cast<long long>(ny) * nzhl, 16LL * ctx.sm_count), 256, 0, ctx.stream>>>(a, cw);
+      if (P->spec_real) k_spec_000s<<<std::min<long long>(static_cast<long long>(ny) * nzhl, 16LL * ctx.sm_count), 256, 0, ctx.stream>>>(a, cw, 0, nzhl);
       else k_spec_000<<<gs, 256, 0, ctx.stream>>>(a, cw);
       X3D_CUDA(cudaGetLastError()); ctx.launches++;
     }
@@ -759,7 +804,7 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     stage(S_PREX, cw, cwb);
     stage(S_PREY | S_ROTZ_B, cwb, cw);
   }
-  if (nzhl > 0) {
+  if (nzhl > 0 && !chunked) {
     ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
     X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_INVERSE));
   }
