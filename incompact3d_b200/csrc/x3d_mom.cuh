@@ -33,4 +33,11 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
                   const MomIntt *intt = nullptr);
 bool mom_x_eligible(int n, int L);
 
+// fused pairs of periodic staggered operators on y / z lines (x3d_stag_kernels.cuh, x3d_stag.cu)
+//   mode 0: outA = opA(inA) + opB(inB), (opA, opB) = (inter?vp, der?vp);  mode 1: outA = opA(inA), outB = opB(inA), (inter?pv, der?pv)
+bool stag_pair_eligible(Ctx &ctx, const DevOp &opA, const DevOp &opB, long long n1, int nline, long long sline, long long souter, long long nouter);
+void launch_stag_pair(Ctx &ctx, int mode, int axis, const DevOp &opA, const DevOp &opB, const double *inA, const double *inB, double *outA,
+                      double *outB, long long n1, int nline, long long nouter, long long sline, long long souter);
+void stag_release(Ctx *ctx);
+
 }  // namespace x3d

@@ -17,7 +17,9 @@ void launch_kind_DPV(Ctx &, const DevOp &, const LineGeom &, const TriTable &, c
 void launch_kind_IPV(Ctx &, const DevOp &, const LineGeom &, const TriTable &, const double *, double *);
 
 Ctx::Ctx() {}
+void stag_release(Ctx *ctx);
 Ctx::~Ctx() {
+  stag_release(this);
   tri_cache.clear();
   if (stream) cudaStreamDestroy(stream);
 }

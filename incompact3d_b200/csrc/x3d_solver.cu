@@ -170,6 +170,7 @@ struct SolverImpl : SolverState {
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
   bool cyclic[3] = {false, false, false};   // table-free cyclic solves in the fused kernels (X3D_MOM_CYC=0: tables)
+  bool stag[3] = {false, false, false};     // fused pairs of staggered operators on periodic y / z lines (X3D_FUSE_STAG=0: off)
   bool fuse_intt = true;                    // time integration folded into the x momentum kernel (X3D_FUSE_INTT=0: k_map pass)
   // several ranks, X3D_OVERLAP=1: the y -> z transposes of the velocity run on `aux` while the x and y momentum
   // kernels compute.  Off by default: on 2 B200 it gave 42.4 ms per 512^3 step against 42.3 ms on one stream (the
@@ -354,6 +355,18 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
       S->fused[a] = S->cyclic[a] || (build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]));
     }
     if (const char *e2 = getenv("X3D_FUSE_INTT")) S->fuse_intt = atoi(e2) != 0;
+  }
+  {
+    const char *e = getenv("X3D_FUSE_STAG");
+    const bool want = !(e && atoi(e) == 0);
+    const long long nxm = S->nxm;
+    if (want) {
+      // y lines of (nxm, ny, nzl) arrays; z lines of (nxm, nyml, nz) arrays
+      S->stag[1] = S->A[1].periodic && stag_pair_eligible(ctx, S->ivp[1].op, S->dvp[1].op, nxm, p.ny, nxm, nxm * p.ny, nzl) &&
+                   stag_pair_eligible(ctx, S->ipv[1].op, S->dpv[1].op, nxm, p.ny, nxm, nxm * p.ny, nzl);
+      S->stag[2] = S->A[2].periodic && stag_pair_eligible(ctx, S->ivp[2].op, S->dvp[2].op, nxm * nyml, p.nz, nxm * nyml, 0, 1) &&
+                   stag_pair_eligible(ctx, S->ipv[2].op, S->dpv[2].op, nxm * nyml, p.nz, nxm * nyml, 0, 1);
+    }
   }
   S->ivp_y_add = S->ivp[1]; S->ivp_y_add.op.store_mode = 1;
   S->dvp_z_add = S->dvp[2]; S->dvp_z_add.op.store_mode = 1;
@@ -875,6 +888,10 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   run(ctx, S.dvp[0], ta1, pp1);    // :297
   run(ctx, S.ivp[0], tb1, pgy1);   // :313
   run(ctx, S.ivp[0], tc1, pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
+  const long long nxm_ = S.nxm;
+  if (S.stag[1]) {                     // :321-325 in one kernel: duy = interyvp(pp1) + deryvp(pgy1)
+    launch_stag_pair(ctx, 0, 1, S.ivp[1].op, S.dvp[1].op, pp1, pgy1, duy, nullptr, nxm_, S.p.ny, S.nzl, nxm_, nxm_ * S.p.ny);
+  } else {
   run(ctx, S.dvp[1], pgy1, duy);       // :322
   if (S.fuse_sums) {
     run(ctx, S.ivp_y_add, pp1, duy);   // :321 + :325: duy += interyvp(pp1), accumulated by the operator's store
@@ -882,6 +899,7 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
     run(ctx, S.ivp[1], pp1, upi2);     // :321
     const long long n2 = static_cast<long long>(S.nxm) * S.nym * S.nzl;
     map(ctx, n2, [=] __device__(long long q) { duy[q] = duy[q] + upi2[q]; });  // :325
+  }
   }
   run(ctx, S.ivp[1], pgz1, upi2);      // :327
   const double *duy3 = duy, *uzp3 = upi2;
@@ -891,8 +909,12 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
     transpose_device_multi(ctx, 1, 2, src, dst, S.id_p3, 1);
     duy3 = t1; uzp3 = t2;
   }
-  run(ctx, S.ivp[2], duy3, out);       // :333
   const long long n3 = static_cast<long long>(S.n3);
+  if (nlock != 2 && S.stag[2] && n3 > 0) {   // :333-339 in one kernel: out = interzvp(duy3) + derzvp(uzp3)
+    launch_stag_pair(ctx, 0, 2, S.ivp[2].op, S.dvp[2].op, duy3, uzp3, out, nullptr, nxm_ * S.nyml, S.p.nz, 1, nxm_ * S.nyml, 0);
+    return;
+  }
+  run(ctx, S.ivp[2], duy3, out);       // :333
   if (nlock != 2 && S.fuse_sums) {
     run(ctx, S.dvp_z_add, uzp3, out);  // :335 + :339: out += derzvp(uzp3)
     return;
@@ -920,8 +942,13 @@ static bool fused_cor_vel(const SolverImpl &S) {
 static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
   double *ppi3 = B(S.w[0]), *pgz3 = B(S.w[1]), *ppi2 = B(S.w[2]), *pgy2 = B(S.w[3]), *pgzi2 = B(S.w[4]);
   double *t1 = B(S.w[5]), *t2 = B(S.w[6]);
-  run(ctx, S.ipv[2], pp3, ppi3);   // :404
-  run(ctx, S.dpv[2], pp3, pgz3);   // :406
+  const long long nxm_ = S.nxm;
+  if (S.stag[2] && S.n3 > 0) {     // :404-406 in one kernel: one read of pp3
+    launch_stag_pair(ctx, 1, 2, S.ipv[2].op, S.dpv[2].op, pp3, nullptr, ppi3, pgz3, nxm_ * S.nyml, S.p.nz, 1, nxm_ * S.nyml, 0);
+  } else {
+    run(ctx, S.ipv[2], pp3, ppi3);   // :404
+    run(ctx, S.dpv[2], pp3, pgz3);   // :406
+  }
   const double *pgz2 = pgz3, *pp2 = ppi3;
   if (S.nranks > 1) {  // :410-411
     const double *src[2] = {pgz3, ppi3};
@@ -929,8 +956,12 @@ static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
     transpose_device_multi(ctx, 2, 2, src, dst, S.id_p3, 1);
     pgz2 = t1; pp2 = t2;
   }
-  run(ctx, S.ipv[1], pp2, ppi2);   // :413
-  run(ctx, S.dpv[1], pp2, pgy2);   // :415
+  if (S.stag[1]) {                 // :413-415 in one kernel: one read of pp2
+    launch_stag_pair(ctx, 1, 1, S.ipv[1].op, S.dpv[1].op, pp2, nullptr, ppi2, pgy2, nxm_, S.p.ny, S.nzl, nxm_, nxm_ * S.p.ny);
+  } else {
+    run(ctx, S.ipv[1], pp2, ppi2);   // :413
+    run(ctx, S.dpv[1], pp2, pgy2);   // :415
+  }
   run(ctx, S.ipv[1], pgz2, pgzi2); // :417  (transpose_y_to_x :422-424 is local)
   if (fused_cor_vel(S)) {  // cor_vel (:242-244) folded in: u -= derxpv(ppi2), v -= interxpv(pgy2), w -= interxpv(pgzi2)
     run(ctx, S.dpv_x_sub, ppi2, B(S.ux));
