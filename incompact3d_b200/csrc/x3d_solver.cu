@@ -175,7 +175,7 @@ struct SolverImpl : SolverState {
   // several ranks, X3D_OVERLAP=1: the y -> z transposes of the velocity run on `aux` while the x and y momentum
   // kernels compute.  Off by default: on 2 B200 it gave 42.4 ms per 512^3 step against 42.3 ms on one stream (the
   // hidden copies are paid back by slower kernels beside them and by the extra array intt then reads).
-  bool overlap = false;
+  int overlap = 0;   // 0 off | 1: y and x kernels beside the forward transposes | 2: the y kernel beside them, then z, then x (+ intt)
   // x3d_solver_advance_host: three velocity sets in rotation (the current one and two spares) so that the H2D copy of
   // job j+1 and the D2H copy of job j-1 run on their own streams beside the kernels of job j
   struct VelSet {
@@ -373,7 +373,7 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   S->dpv_x_sub = S->dpv[0]; S->dpv_x_sub.op.store_mode = 2;
   S->ipv_x_sub = S->ipv[0]; S->ipv_x_sub.op.store_mode = 2;
   if (const char *e = getenv("X3D_FUSE_SUMS")) S->fuse_sums = atoi(e) != 0;
-  if (const char *e = getenv("X3D_OVERLAP")) S->overlap = atoi(e) != 0;
+  if (const char *e = getenv("X3D_OVERLAP")) S->overlap = atoi(e);
   x3d_poisson_params pp{};
   pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
   pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
@@ -662,9 +662,15 @@ static bool momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
   if (z_first) z_dir(true);
   // ---- y, transeq.f90:188-219,336-338
   launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, z_first, S.cyclic[1]);
+  bool z_pending = !z_first;
+  if (z_pending && S.overlap == 2) {   // the forward transposes ran beside the y kernel: z now, x (+ intt) last
+    X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));
+    z_dir(false);
+    z_pending = false;
+  }
   // ---- x, transeq.f90:114-146,442-444
   bool folded = false;
-  if (S.fused[0] && S.cyclic[0] && S.fuse_intt && itr > 0 && z_first && (S.p.itimescheme == 5 || S.p.itimescheme == 1)) {
+  if (S.fused[0] && S.cyclic[0] && S.fuse_intt && itr > 0 && !z_pending && (S.p.itimescheme == 5 || S.p.itimescheme == 1)) {
     // x kernel + intt (time_integrators.f90:71-74,151-157): u <- adt N + bdt old + u, old <- N, N = sum (+ extra) + r_x
     MomIntt I{};
     double *vel[3] = {B(S.ux), B(S.uy), B(S.uz)}, *old[3] = {B(S.dux[1]), B(S.duy[1]), B(S.duz[1])};
@@ -691,7 +697,7 @@ static bool momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
       rx[q] = rx[q] + (xnu * ta[q] - half * td[q]); ry[q] = ry[q] + (xnu * tb[q] - half * te[q]); rz[q] = rz[q] + (xnu * tc[q] - half * tf[q]);
     });
   }
-  if (!z_first) {
+  if (z_pending) {
     X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));
     z_dir(false);
   }

@@ -61,15 +61,15 @@ def main():
     # the z -> y transposes) run
     # X3D_P2P_MODE (read by x3d_decomp_init): the block copies of the y<->z transposes through the vector-copy kernel
     # (what these small pencils take by default) and through the copy engines (what 512^3 pencils take)
-    for nn, ncl, p2p_mode in (((32, 24, 40), (0,) * 6, None), ((33, 25, 33), (1,) * 6, "1"), ((24, 176, 168), (0,) * 6, None),
-                              ((24, 176, 168), (0,) * 6, "1")):
+    for nn, ncl, p2p_mode, overlap in (((32, 24, 40), (0,) * 6, None, "0"), ((33, 25, 33), (1,) * 6, "1", "0"), ((24, 176, 168), (0,) * 6, None, "0"),
+                                       ((24, 176, 168), (0,) * 6, "1", "1"), ((176, 176, 168), (0,) * 6, None, "2")):
         length = 2 * np.pi
         if p2p_mode is None:
             os.environ.pop("X3D_P2P_MODE", None)
         else:
             os.environ["X3D_P2P_MODE"] = p2p_mode
         # X3D_OVERLAP (read by x3d_solver_init): forward velocity transposes on a second stream, for the last case
-        os.environ["X3D_OVERLAP"] = "1" if (p2p_mode is not None and nn[1] >= 168) else "0"
+        os.environ["X3D_OVERLAP"] = overlap   # 2: the y kernel beside the forward transposes, x + intt with the z part as an extra term
         x = X3D(local)
         x.decomp_init(*nn, 1, world, rank, world, fresh_id())
         x.solver_init(*nn, ncl=ncl, xlx=length, yly=length, zlz=length, re=1600.0, dt=0.002, p_row=1, p_col=world)
