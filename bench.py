@@ -246,6 +246,8 @@ def alg_bytes(name, npts, nsp):
         # 3 velocities in, 3 results out.  With the time integration folded in: u, v, w and the running sum in, the stored
         # right-hand side in (2 of 3 RK3 sub-steps), u, v, w out, the stored right-hand side out (2 of 3) = 104 B on average
         return (104.0 if "+intt" in name else 48.0) * npts
+    if name.startswith("staggered_"):
+        return 24.0 * npts                      # two inputs + one output, or one input + two outputs
     if name.startswith("elementwise"):
         return 104.0 * npts                     # intt of RK3: 13 array passes on average over the sub-steps
     if name.startswith("fft_z"):

@@ -174,6 +174,54 @@ __device__ __forceinline__ void pair_solve_cyclic(dd2 (&x)[L], const MomGeom::Cy
   for (int m = L - 1; m >= 0; --m) { t = fma2(rho, t, x[m]); x[m] = t; }
 }
 
+// Two independent cyclic solves (different operators, same lines) interleaved statement by statement: every sweep is a
+// serial chain of dependent FMAs, and with 8 consumer warps per SM two chains per thread (the two lanes of the pair) do
+// not cover the FP64 latency (ncu: fp64 pipe 54 %, stall reason "wait"); four do.  Same arithmetic as two calls of
+// pair_solve_cyclic; the look-back runs max(K1, K2) rounds for both (further terms are part of the exact sum).
+template <int L>
+__device__ __forceinline__ void pair_solve_cyclic2(dd2 (&x1)[L], const MomGeom::Cyc &c1, dd2 (&x2)[L], const MomGeom::Cyc &c2, int lane, int nc) {
+  const double r1 = c1.rho, r2 = c2.rho;
+  const bool last = lane == nc - 1;
+  const double e1s = last ? c1.esc : 1.0, g1 = last ? c1.gamma : 0.0, d1 = last ? c1.delta : 0.0;
+  const double e2s = last ? c2.esc : 1.0, g2 = last ? c2.gamma : 0.0, d2 = last ? c2.delta : 0.0;
+  const int K = c1.K > c2.K ? c1.K : c2.K;
+  dd2 e1 = x1[0], e2 = x2[0];
+  X3D_UNROLL
+  for (int m = 1; m < L; ++m) { e1 = fma2(r1, e1, x1[m]); e2 = fma2(r2, e2, x2[m]); }
+  e1 = e1s * e1; e2 = e2s * e2;
+  dd2 a1 = {0.0, 0.0}, a2 = {0.0, 0.0};
+#pragma unroll 1
+  for (int k = K; k >= 1; --k) {
+    int src = lane - k;
+    src += src < 0 ? nc : 0;
+    const dd2 v1 = shfl2(e1, src), v2 = shfl2(e2, src);
+    const bool sl = src == nc - 1;
+    a1 = fma2(sl ? c1.rhoR : c1.rhoL, a1, v1);
+    a2 = fma2(sl ? c2.rhoR : c2.rhoL, a2, v2);
+  }
+  dd2 t1 = a1, t2 = a2;
+  X3D_UNROLL
+  for (int m = 0; m < L; ++m) { t1 = fma2(r1, t1, x1[m]); x1[m] = t1; t2 = fma2(r2, t2, x2[m]); x2[m] = t2; }
+  const dd2 y1 = e1s * t1, y2 = e2s * t2;
+  dd2 b1 = x1[L - 1], b2 = x2[L - 1];
+  X3D_UNROLL
+  for (int m = L - 2; m >= 0; --m) { b1 = fma2(r1, b1, x1[m]); b2 = fma2(r2, b2, x2[m]); }
+  b1 = fma2(-g1, y1, b1); b2 = fma2(-g2, y2, b2);
+  a1 = {0.0, 0.0}; a2 = {0.0, 0.0};
+#pragma unroll 1
+  for (int k = K; k >= 1; --k) {
+    int src = lane + k;
+    src -= src >= nc ? nc : 0;
+    const dd2 v1 = shfl2(b1, src), v2 = shfl2(b2, src);
+    const bool sl = src == nc - 1;
+    a1 = fma2(sl ? c1.rhoR : c1.rhoL, a1, v1);
+    a2 = fma2(sl ? c2.rhoR : c2.rhoL, a2, v2);
+  }
+  t1 = e1s * fma2(-d1, y1, a1); t2 = e2s * fma2(-d2, y2, a2);
+  X3D_UNROLL
+  for (int m = L - 1; m >= 0; --m) { t1 = fma2(r1, t1, x1[m]); x1[m] = t1; t2 = fma2(r2, t2, x2[m]); x2[m] = t2; }
+}
+
 // how a thread reaches element j of its window (two lines at once) inside a ring slot
 template <bool XD>
 struct TileAcc;
@@ -370,10 +418,9 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
           }
         }
         if constexpr (CYC) {
-          pair_solve_cyclic<L>(r, g.cy2, lane, nc);
+          pair_solve_cyclic2<L>(r, g.cy2, x, g.cy1, lane, nc);
           X3D_UNROLL
           for (int m = 0; m < L; ++m) r[m] = g.cy2.scale * r[m];
-          pair_solve_cyclic<L>(x, g.cy1, lane, nc);
           const double k1 = g.cy1.scale;
           X3D_UNROLL
           for (int m = 0; m < L; ++m) {

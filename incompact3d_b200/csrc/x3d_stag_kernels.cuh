@@ -88,8 +88,60 @@ __device__ __forceinline__ void pair_solve_cyclic_ks(dd2 (&x)[L], const StagCyc 
   for (int m = L - 1; m >= 0; --m) { t = fma2(rho, t, x[m]); x[m] = t; }
 }
 
+// two independent solves interleaved (see pair_solve_cyclic2: four dependent chains per thread instead of two)
+template <int L>
+__device__ __forceinline__ void pair_solve_cyclic_ks2(dd2 (&x1)[L], const StagCyc &c1, dd2 (&x2)[L], const StagCyc &c2, int lane, int nc) {
+  const double r1 = c1.rho, r2 = c2.rho;
+  const bool last = lane == nc - 1;
+  const double e1s = last ? c1.esc : 1.0, g1 = last ? c1.gamma : 0.0, d1 = last ? c1.delta : 0.0;
+  const double e2s = last ? c2.esc : 1.0, g2 = last ? c2.gamma : 0.0, d2 = last ? c2.delta : 0.0;
+  int up[5], dn[5];
+  X3D_UNROLL
+  for (int lev = 0; lev < 5; ++lev) {
+    int s = lane - (1 << lev);
+    while (s < 0) s += nc;
+    up[lev] = s;
+    s = lane + (1 << lev);
+    while (s >= nc) s -= nc;
+    dn[lev] = s;
+  }
+  dd2 e1 = x1[0], e2 = x2[0];
+  X3D_UNROLL
+  for (int m = 1; m < L; ++m) { e1 = fma2(r1, e1, x1[m]); e2 = fma2(r2, e2, x2[m]); }
+  e1 = e1s * e1; e2 = e2s * e2;
+  X3D_UNROLL
+  for (int lev = 0; lev < 5; ++lev) {
+    const dd2 o1 = shfl2(e1, up[lev]), o2 = shfl2(e2, up[lev]);
+    e1 = fma2(__ldg(c1.scan + lev * 32 + lane), o1, e1);
+    e2 = fma2(__ldg(c2.scan + lev * 32 + lane), o2, e2);
+  }
+  int prev = lane - 1;
+  prev += prev < 0 ? nc : 0;
+  dd2 t1 = shfl2(e1, prev), t2 = shfl2(e2, prev);
+  X3D_UNROLL
+  for (int m = 0; m < L; ++m) { t1 = fma2(r1, t1, x1[m]); x1[m] = t1; t2 = fma2(r2, t2, x2[m]); x2[m] = t2; }
+  const dd2 y1 = e1s * t1, y2 = e2s * t2;
+  dd2 b1 = x1[L - 1], b2 = x2[L - 1];
+  X3D_UNROLL
+  for (int m = L - 2; m >= 0; --m) { b1 = fma2(r1, b1, x1[m]); b2 = fma2(r2, b2, x2[m]); }
+  b1 = fma2(-g1, y1, b1); b2 = fma2(-g2, y2, b2);
+  X3D_UNROLL
+  for (int lev = 0; lev < 5; ++lev) {
+    const dd2 o1 = shfl2(b1, dn[lev]), o2 = shfl2(b2, dn[lev]);
+    b1 = fma2(__ldg(c1.scan + (5 + lev) * 32 + lane), o1, b1);
+    b2 = fma2(__ldg(c2.scan + (5 + lev) * 32 + lane), o2, b2);
+  }
+  int next = lane + 1;
+  next -= next >= nc ? nc : 0;
+  t1 = e1s * fma2(-d1, y1, shfl2(b1, next));
+  t2 = e2s * fma2(-d2, y2, shfl2(b2, next));
+  X3D_UNROLL
+  for (int m = L - 1; m >= 0; --m) { t1 = fma2(r1, t1, x1[m]); x1[m] = t1; t2 = fma2(r2, t2, x2[m]); x2[m] = t2; }
+}
+
+// 288 threads per CTA, one CTA per SM: up to 224 registers per thread (a launch bound alone makes ptxas stop at 168)
 template <int KA, int KB, int MODE, int L>
-__global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
+__global__ void __maxnreg__(224)
     k_stag(const __grid_constant__ DevOp opA, const __grid_constant__ DevOp opB, const __grid_constant__ StagMaps maps,
            const __grid_constant__ StagGeom g) {
   constexpr int NWIN = L + 2 * HALO;
@@ -186,7 +238,6 @@ __global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(done + slot0);   // B has been read: its slot is free
-      pair_solve_cyclic_ks<L>(y, g.b, lane, nc);
       dd2 x[L];
       mbar_wait(full + slot1, par1);          // A
       {
@@ -201,7 +252,7 @@ __global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
           x[m].y = ok ? v.y : 0.0;
         }
       }
-      pair_solve_cyclic_ks<L>(x, g.a, lane, nc);
+      pair_solve_cyclic_ks2<L>(x, g.a, y, g.b, lane, nc);
       __syncwarp();  // every lane has read its window of A
       if (live) {
         X3D_UNROLL
@@ -232,7 +283,7 @@ __global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
           y[m].y = ok ? vb.y : 0.0;
         }
       }
-      pair_solve_cyclic_ks<L>(x, g.a, lane, nc);
+      pair_solve_cyclic_ks2<L>(x, g.a, y, g.b, lane, nc);
       __syncwarp();  // every lane has read its window
       if (live) {
         X3D_UNROLL
@@ -242,7 +293,6 @@ __global__ void __launch_bounds__(32 * (PAIR_WARPS + 1), 1)
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(done + slot0);
-      pair_solve_cyclic_ks<L>(y, g.b, lane, nc);
       mbar_wait(full + slot1, par1);          // S: free slot handed over by the producer
       if (live) {
         X3D_UNROLL
