@@ -88,6 +88,24 @@ bool mom_cyclic_ok(double alpha, int n, int L) {
   return make_cyc(alpha, n, L, 1.0, cy);
 }
 
+// Overlap-save segments for a periodic line of ntot rows (MomGeom::ntot ...): tile rows T = S + 2 H <= 544.
+// nseg = 1 when the whole line fits a tile.  False when no segmentation works (line extents, decay of the two operators).
+bool mom_segments(int ntot, double alpha1, double alpha2, int &S, int &H, int &nseg) {
+  if (ntot <= 544) { S = ntot; H = 0; nseg = 1; return true; }
+  double rmax = 0.0;
+  for (double a : {alpha1, alpha2}) {
+    if (!(std::fabs(a) < 0.5) || std::fabs(a) < 1e-3) return false;
+    rmax = std::max(rmax, std::fabs((-1.0 + std::sqrt(1.0 - 4.0 * a * a)) / (2.0 * a)));
+  }
+  for (int h : {48, 64, 96, 128}) {
+    if (ntot % h) continue;
+    if (std::pow(rmax, h - 4) > 1e-17) continue;   // the 4 stencil rows next to the artificial wrap carry O(1) errors
+    for (int s = ((544 - 2 * h) / h) * h; s >= h; s -= h)
+      if (ntot % s == 0) { S = s; H = h; nseg = ntot / s; return true; }
+  }
+  return false;
+}
+
 bool mom_pair_plan(int n, int L, MomGeom &g, size_t &smem) {
   if (L != 17 && L != 9) return false;
   if ((n & 7) || n < 64) return false;
@@ -141,14 +159,19 @@ void launch_mom_pair(Ctx &ctx, int axis, const DevOp &op1, const DevOp &op2, con
                      long long souter, bool add, bool cyclic) {
   MomGeom g{};
   size_t smem = 0;
-  const int L = pick_L_contig(nline);
+  int segS, segH, nseg;
+  if (!mom_segments(nline, op1.alpha, op2.alpha, segS, segH, nseg) || (nseg > 1 && !cyclic)) throw Error("fused momentum kernel: ineligible call");
+  const int T = segS + 2 * segH;                  // rows of a tile (= nline when the line is not segmented)
+  const int L = pick_L_contig(T);
   if (!cyclic && (!M1.ok || !M2.ok || M1.L != M2.L || M1.L != L)) throw Error("fused momentum kernel: ineligible call");
-  if (!mom_pair_plan(nline, L, g, smem)) throw Error("fused momentum kernel: ineligible call");
-  g.rem = nline - (g.nc - 1) * L;
-  if (cyclic && !(make_cyc(op1.alpha, nline, L, -0.5, g.cy1) && make_cyc(op2.alpha, nline, L, xnu, g.cy2)))
+  if (!mom_pair_plan(T, L, g, smem)) throw Error("fused momentum kernel: ineligible call");
+  g.ntot = nline; g.seg_S = segS; g.seg_H = segH; g.nseg = nseg;
+  if (nseg > 1) { g.br = segH; g.nbox = T / segH; }   // boxes of seg_H rows never straddle the end of the line
+  g.rem = T - (g.nc - 1) * L;
+  if (cyclic && !(make_cyc(op1.alpha, T, L, -0.5, g.cy1) && make_cyc(op2.alpha, T, L, xnu, g.cy2)))
     throw Error("fused momentum kernel: cyclic solves are not possible for this scheme");
   g.nbx = static_cast<int>((n1 + 15) / 16);
-  g.npos = static_cast<long long>(g.nbx) * nouter;
+  g.npos = static_cast<long long>(g.nbx) * nouter * nseg;
   g.ia = axis; g.ic1 = (axis + 1) % 3; g.ic2 = (axis + 2) % 3;
   g.xnu = xnu;
   g.add = add ? 1 : 0;
@@ -183,12 +206,17 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
                   const double *const f[3], double *const out[3], int n, long long nlines, bool add, bool cyclic, const MomIntt *intt) {
   MomGeom g{};
   size_t smem = 0;
-  const int L = pick_L_contig(n);
+  int segS, segH, nseg;
+  if (!mom_segments(n, op1.alpha, op2.alpha, segS, segH, nseg) || (nseg > 1 && !cyclic)) throw Error("fused x momentum kernel: ineligible call");
+  const int T = segS + 2 * segH;
+  const int L = pick_L_contig(T);
   if (!cyclic && (!M1.ok || !M2.ok || M1.L != M2.L || M1.L != L)) throw Error("fused x momentum kernel: ineligible call");
-  if (!mom_x_plan(n, L, g, smem)) throw Error("fused x momentum kernel: ineligible call");
-  g.rem = n - (g.nc - 1) * L;
-  if (cyclic && !(make_cyc(op1.alpha, n, L, -0.5, g.cy1) && make_cyc(op2.alpha, n, L, xnu, g.cy2)))
+  if (!mom_x_plan(T, L, g, smem)) throw Error("fused x momentum kernel: ineligible call");
+  g.ntot = n; g.seg_S = segS; g.seg_H = segH; g.nseg = nseg;
+  g.rem = T - (g.nc - 1) * L;
+  if (cyclic && !(make_cyc(op1.alpha, T, L, -0.5, g.cy1) && make_cyc(op2.alpha, T, L, xnu, g.cy2)))
     throw Error("fused x momentum kernel: cyclic solves are not possible for this scheme");
+  if (intt && nseg > 1 && intt->u_out[0] == intt->u[0]) throw Error("fused x momentum kernel: a segmented line needs a separate output velocity");
   if (intt && !cyclic) throw Error("fused x momentum kernel: the folded time integration needs the cyclic solves");
   for (int q = 0; q < 3; ++q) {
     if ((reinterpret_cast<uintptr_t>(f[q]) | (intt ? 0 : reinterpret_cast<uintptr_t>(out[q]))) & 15u) throw Error("fused x momentum kernel: unaligned field");
@@ -197,16 +225,16 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
   if (intt) {
     for (int q = 0; q < 3; ++q) {
       g.isum[q] = intt->sum[q]; g.iextra[q] = intt->has_extra ? intt->extra[q] : nullptr; g.iold_in[q] = intt->use_old ? intt->old_in[q] : nullptr;
-      g.iu[q] = intt->u[q]; g.iold_out[q] = intt->store_old ? intt->old_out[q] : nullptr;
+      g.iu[q] = intt->u[q]; g.iu_out[q] = intt->u_out[q]; g.iold_out[q] = intt->store_old ? intt->old_out[q] : nullptr;
       const uintptr_t all = reinterpret_cast<uintptr_t>(g.isum[q]) | reinterpret_cast<uintptr_t>(g.iextra[q]) | reinterpret_cast<uintptr_t>(g.iold_in[q]) |
-                            reinterpret_cast<uintptr_t>(g.iu[q]) | reinterpret_cast<uintptr_t>(g.iold_out[q]);
+                            reinterpret_cast<uintptr_t>(g.iu[q]) | reinterpret_cast<uintptr_t>(g.iu_out[q]) | reinterpret_cast<uintptr_t>(g.iold_out[q]);
       if (all & 15u) throw Error("fused x momentum kernel: unaligned field");
     }
     g.ca = intt->ca; g.cb = intt->cb;
     g.use_old = intt->use_old; g.store_old = intt->store_old; g.has_extra = intt->has_extra;
   }
   g.nlines = nlines;
-  g.npos = (nlines + 15) / 16;
+  g.npos = ((nlines + 15) / 16) * nseg;
   g.nbx = 1;
   g.ia = 0; g.ic1 = 1; g.ic2 = 2;
   g.xnu = xnu;

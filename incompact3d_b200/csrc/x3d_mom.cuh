@@ -15,10 +15,13 @@ struct MomTable {        // compressed coefficient table of one periodic operato
 bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M);
 // table-free cyclic solves (pair_solve_cyclic, x3d_mom_kernels.cuh) are possible for this scheme and chunking
 bool mom_cyclic_ok(double alpha, int n, int L);
+// overlap-save segmentation of a periodic line of ntot rows for the fused kernels (nseg = 1: the line fits a tile)
+bool mom_segments(int ntot, double alpha1, double alpha2, int &S, int &H, int &nseg);
 // time integration folded into the x kernel: N = sum (+ extra) + r_x ; u <- ca N + cb old_in + u ; old_out <- N
 struct MomIntt {
   const double *sum[3], *extra[3], *old_in[3];
   double *u[3], *old_out[3];
+  double *u_out[3];       // = u, or a separate array when the x lines are segmented (neighbouring tiles read the old u)
   double ca, cb;
   bool use_old, store_old, has_extra;
 };

@@ -50,6 +50,14 @@ struct MomGeom {
     int K;              // chunks of look-back: |rho|^(K L) < 1e-18
   } cy1, cy2;
   int rem;              // rows of the last chunk
+  // ---- long lines by overlap-save segments ----
+  // A line of ntot > 544 rows does not fit a tile.  The cyclic recurrences forget their past geometrically (|rho|^k), so a
+  // tile of n = seg_S + 2 seg_H consecutive rows (wrapping at the ends of the line), solved as if IT were periodic, is
+  // exact to double precision on its inner seg_S rows once |rho|^(seg_H - 4) < 1e-17: what the artificial wrap and the
+  // stencil rows next to it get wrong has decayed before it reaches them.  nseg tiles per line; only the inner rows
+  // are stored.  nseg = 1: seg_S = n = ntot, seg_H = 0 (the whole line, truly periodic).
+  int ntot, seg_S, seg_H, nseg;
+  double *iu_out[3];    // INTT: where the new velocity goes (= iu unless the line is segmented: neighbours still read the old one)
   // ---- time integration folded into the x kernel (INTT), src/time_integrators.f90:71-74,151-157 ----
   //   N = sum (+ extra) + r_x ;  u <- ca N + cb old + u ;  old <- N (when store_old)
   const double *isum[3], *iextra[3], *iold_in[3];
@@ -304,20 +312,35 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
       const long long pos = first + p * step;
       const int slot = static_cast<int>((p + 1 + q) % 3);
       unsigned char *dst = smem_raw + slot * slot_bytes;
+      const int seg = static_cast<int>(pos % g.nseg);
+      const long long blk = pos / g.nseg;
+      int row0 = seg * g.seg_S - g.seg_H;           // first row of the tile in the line (wraps)
+      row0 += row0 < 0 ? g.ntot : 0;
       if constexpr (XD) {
-        const long long line0 = pos * 16;
+        const long long line0 = blk * 16;
         const int nl = static_cast<int>(g.nlines - line0 < 16 ? g.nlines - line0 : 16);
-        const double *src = g.fin[fld[q]] + line0 * n;
+        const double *src = g.fin[fld[q]] + line0 * g.ntot;
         mbar_expect_tx(full + slot, static_cast<unsigned>(nl) * n * 8u);
-        for (int l = 0; l < nl; ++l)
-          bulk_g2s(dst + (l * g.pitch + HALO) * 8, src + static_cast<long long>(l) * n, static_cast<unsigned>(n) * 8u, full + slot);
+        const int n1 = g.ntot - row0 < n ? g.ntot - row0 : n;   // rows up to the end of the line, then from its start
+        for (int l = 0; l < nl; ++l) {
+          const double *ls = src + static_cast<long long>(l) * g.ntot;
+          bulk_g2s(dst + (l * g.pitch + HALO) * 8, ls + row0, static_cast<unsigned>(n1) * 8u, full + slot);
+          if (n1 < n) bulk_g2s(dst + (l * g.pitch + HALO + n1) * 8, ls, static_cast<unsigned>(n - n1) * 8u, full + slot);
+        }
       } else {
-        const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
+        const int bx = static_cast<int>(blk % g.nbx), by = static_cast<int>(blk / g.nbx);
         const CUtensorMap *tm = &maps.in[fld[q]], *th = &maps.halo[fld[q]];
         mbar_expect_tx(full + slot, (static_cast<unsigned>(g.nbox) * g.br + 16u) * 128u);
-        for (int b = 0; b < g.nbox; ++b) tma_load_3d(dst + (8 + b * g.br) * 128, tm, bx * 16, b * g.br, by, full + slot);
-        tma_load_3d(dst, th, bx * 16, n - 8, by, full + slot);
-        tma_load_3d(dst + (8 + n) * 128, th, bx * 16, 0, by, full + slot);
+        for (int b = 0; b < g.nbox; ++b) {            // boxes never straddle the end of the line (ntot, row0 are multiples of br)
+          int r = row0 + b * g.br;
+          r -= r >= g.ntot ? g.ntot : 0;
+          tma_load_3d(dst + (8 + b * g.br) * 128, tm, bx * 16, r, by, full + slot);
+        }
+        int rp = row0 - 8, rn = row0 + n;             // the 8 rows before and after the tile: the solver's own wrap ghosts
+        rp += rp < 0 ? g.ntot : 0;
+        rn -= rn >= g.ntot ? g.ntot : 0;
+        tma_load_3d(dst, th, bx * 16, rp, by, full + slot);
+        tma_load_3d(dst + (8 + n) * 128, th, bx * 16, rn, by, full + slot);
       }
     };
     if (mine > 0) { load(0, 2); load(0, 0); load(0, 1); }
@@ -331,25 +354,31 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
           // the consumers have written their results to global memory themselves: the slot is free
           (void)src;
         } else if constexpr (XD) {
-          const long long line0 = pos * 16;
+          const int seg = static_cast<int>(pos % g.nseg);
+          const long long line0 = (pos / g.nseg) * 16;
           const int nl = static_cast<int>(g.nlines - line0 < 16 ? g.nlines - line0 : 16);
-          double *dst = g.fout[fld[q]] + line0 * n;
+          double *dst = g.fout[fld[q]] + line0 * g.ntot + seg * g.seg_S;     // the inner seg_S rows of the tile
+          const unsigned bytes = static_cast<unsigned>(g.seg_S) * 8u;
           if (g.add == 0) {
             for (int l = 0; l < nl; ++l)
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * n),
-                           "r"(smem_u32(src + (l * g.pitch + HALO) * 8)), "r"(static_cast<unsigned>(n) * 8u)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * g.ntot),
+                           "r"(smem_u32(src + (l * g.pitch + HALO + g.seg_H) * 8)), "r"(bytes)
                            : "memory");
           } else {
             for (int l = 0; l < nl; ++l)
-              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * n),
-                           "r"(smem_u32(src + (l * g.pitch + HALO) * 8)), "r"(static_cast<unsigned>(n) * 8u)
+              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst + static_cast<long long>(l) * g.ntot),
+                           "r"(smem_u32(src + (l * g.pitch + HALO + g.seg_H) * 8)), "r"(bytes)
                            : "memory");
           }
         } else {
-          const int bx = static_cast<int>(pos % g.nbx), by = static_cast<int>(pos / g.nbx);
+          const int seg = static_cast<int>(pos % g.nseg);
+          const long long blk = pos / g.nseg;
+          const int bx = static_cast<int>(blk % g.nbx), by = static_cast<int>(blk / g.nbx);
           const CUtensorMap *tm = &maps.out[fld[q]];
-          if (g.add == 0) for (int b = 0; b < g.nbox; ++b) tma_store_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
-          else for (int b = 0; b < g.nbox; ++b) tma_red_add_3d(tm, bx * 16, b * g.br, by, src + (8 + b * g.br) * 128);
+          const int nbs = g.seg_S / g.br;              // the inner seg_S rows of the tile
+          const unsigned char *s0 = src + (8 + g.seg_H) * 128;
+          if (g.add == 0) for (int b = 0; b < nbs; ++b) tma_store_3d(tm, bx * 16, seg * g.seg_S + b * g.br, by, s0 + b * g.br * 128);
+          else for (int b = 0; b < nbs; ++b) tma_red_add_3d(tm, bx * 16, seg * g.seg_S + b * g.br, by, s0 + b * g.br * 128);
         }
         bulk_commit();
         if (p + 1 < mine) {
@@ -488,7 +517,9 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
         //   N = sum (+ extra) + r ;  u <- ca N + cb old + u ;  old <- N
         __syncwarp();
         const int f = fld[q];
-        const long long line0 = (first + p * step) * 16 + 2 * jw;
+        const long long posq = first + p * step;
+        const int seg = static_cast<int>(posq % g.nseg);
+        const long long line0 = (posq / g.nseg) * 16 + 2 * jw;
         const double ca = g.ca, cb = g.cb;
         // all loads of a batch (8 x 32 lanes x 16 bytes per array) are issued before the first use: the warp has
         // nothing else to overlap the HBM latency with, so it needs the bytes in flight (the solve's registers are dead here)
@@ -496,14 +527,15 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
           if (line0 + l >= g.nlines) break;
-          const double2 *rs = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(bufC) + (2 * jw + l) * g.pitch + HALO);
-          const long long gb = (line0 + l) * static_cast<long long>(n) / 2;
+          const double2 *rs = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(bufC) + (2 * jw + l) * g.pitch + HALO + g.seg_H);
+          const long long gb = ((line0 + l) * static_cast<long long>(g.ntot) + seg * g.seg_S) / 2;   // the inner seg_S rows
           const double2 *gs = reinterpret_cast<const double2 *>(g.isum[f]) + gb;
           const double2 *ge = reinterpret_cast<const double2 *>(g.iextra[f]) + gb;
           const double2 *go = reinterpret_cast<const double2 *>(g.iold_in[f]) + gb;
-          double2 *gu = reinterpret_cast<double2 *>(g.iu[f]) + gb;
+          const double2 *gu = reinterpret_cast<const double2 *>(g.iu[f]) + gb;
+          double2 *gw = reinterpret_cast<double2 *>(g.iu_out[f]) + gb;
           double2 *gn = reinterpret_cast<double2 *>(g.iold_out[f]) + gb;
-          const int nh = n / 2;
+          const int nh = g.seg_S / 2;
 #pragma unroll 1
           for (int i0 = 0; i0 < nh; i0 += 32 * NBT) {
             double2 Sv[NBT], Uv[NBT], Ov[NBT];
@@ -545,7 +577,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 1)
                 double2 U = Uv[t];
                 U.x = ca * N.x + cb * Ov[t].x + U.x;
                 U.y = ca * N.y + cb * Ov[t].y + U.y;
-                gu[i] = U;
+                gw[i] = U;
                 if (g.store_old) __stcs(gn + i, N);
               }
             }

@@ -170,6 +170,8 @@ struct SolverImpl : SolverState {
   MomTable mt1[3], mt2[3];
   bool fused[3] = {false, false, false};
   bool cyclic[3] = {false, false, false};   // table-free cyclic solves in the fused kernels (X3D_MOM_CYC=0: tables)
+  bool segmented[3] = {false, false, false};   // long lines (n > 544) run the fused kernels by overlap-save segments
+  DevBuf unew[3];                           // segmented x lines: the fused time integration writes the new velocity here
   bool stag[3] = {false, false, false};     // fused pairs of staggered operators on periodic y / z lines (X3D_FUSE_STAG=0: off)
   bool fuse_intt = true;                    // time integration folded into the x momentum kernel (X3D_FUSE_INTT=0: k_map pass)
   // several ranks, X3D_OVERLAP=1: the y -> z transposes of the velocity run on `aux` while the x and y momentum
@@ -342,17 +344,23 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
     const char *e = getenv("X3D_FUSED");
     const bool want = !(e && atoi(e) == 0);
     for (int a = 0; a < 3 && want; ++a) {
-      const int n = nn[a];
-      const int L = pick_L_contig(n);
       const long long lanes = (a == 1) ? p.nx : static_cast<long long>(p.nx) * nyl;
-      if (!S->A[a].periodic || L <= 0 || (p.nx & 1)) continue;
-      if (a == 0 ? !mom_x_eligible(n, L) : (!mom_pair_eligible(n, L) || (lanes & 1))) continue;
+      if (!S->A[a].periodic || (p.nx & 1)) continue;
       const PreOp &o1 = S->d1[a][0], &o2 = S->d2[a][0];
-      const TriTable &T1 = get_tri(ctx, o1.call.f, o1.call.s, o1.call.w, n, L, true, o1.op.alpha, nullptr);
-      const TriTable &T2 = get_tri(ctx, o2.call.f, o2.call.s, o2.call.w, n, L, true, o2.op.alpha, nullptr);
+      int segS, segH, nseg;
+      if (!mom_segments(nn[a], o1.op.alpha, o2.op.alpha, segS, segH, nseg)) continue;
+      const int n = segS + 2 * segH;           // rows of a tile: the line, or one overlap-save segment of a long line
+      const int L = pick_L_contig(n);
+      if (L <= 0) continue;
+      if (a == 0 ? !mom_x_eligible(n, L) : (!mom_pair_eligible(n, L) || (lanes & 1))) continue;
       const char *ec = getenv("X3D_MOM_CYC");
       S->cyclic[a] = !(ec && atoi(ec) == 0) && mom_cyclic_ok(o1.op.alpha, n, L) && mom_cyclic_ok(o2.op.alpha, n, L);
-      S->fused[a] = S->cyclic[a] || (build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]));
+      S->segmented[a] = nseg > 1;
+      if (S->cyclic[a]) { S->fused[a] = true; continue; }
+      if (nseg > 1) continue;                  // segments need the table-free solves
+      const TriTable &T1 = get_tri(ctx, o1.call.f, o1.call.s, o1.call.w, n, L, true, o1.op.alpha, nullptr);
+      const TriTable &T2 = get_tri(ctx, o2.call.f, o2.call.s, o2.call.w, n, L, true, o2.op.alpha, nullptr);
+      S->fused[a] = build_mom_table(ctx, T1, S->mt1[a]) && build_mom_table(ctx, T2, S->mt2[a]);
     }
     if (const char *e2 = getenv("X3D_FUSE_INTT")) S->fuse_intt = atoi(e2) != 0;
   }
@@ -680,8 +688,13 @@ static bool momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
     I.store_old = rk3 && itr < S.iadvance;   // the last sub-step's right-hand side is never read (bdt(1) = 0)
     I.ca = (!rk3 || itr == 1) ? S.gdt[0] : S.adt[itr - 1];
     I.cb = I.use_old ? S.bdt[itr - 1] : 0.0;
-    for (int c = 0; c < 3; ++c) { I.sum[c] = sum[c]; I.extra[c] = extra[c]; I.old_in[c] = old[c]; I.u[c] = vel[c]; I.old_out[c] = old[c]; }
+    for (int c = 0; c < 3; ++c) { I.sum[c] = sum[c]; I.extra[c] = extra[c]; I.old_in[c] = old[c]; I.u[c] = vel[c]; I.u_out[c] = vel[c]; I.old_out[c] = old[c]; }
+    DevBuf *vb[3] = {&S.ux, &S.uy, &S.uz};
+    if (S.segmented[0])   // neighbouring tiles of a segmented line still read the old velocity: write the new one elsewhere, then swap
+      for (int c = 0; c < 3; ++c) { S.unew[c].reserve(vb[c]->bytes); I.u_out[c] = B(S.unew[c]); }
     launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true, true, &I);
+    if (S.segmented[0])
+      for (int c = 0; c < 3; ++c) { std::swap(vb[c]->p, S.unew[c].p); std::swap(vb[c]->bytes, S.unew[c].bytes); }
     folded = true;
   } else if (S.fused[0]) {
     launch_mom_x(ctx, S.d1[0][0].op, S.d2[0][0].op, S.mt1[0], S.mt2[0], xnu, f, sum, nx, static_cast<long long>(ny) * S.nzl, true, S.cyclic[0]);

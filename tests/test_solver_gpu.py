@@ -39,7 +39,10 @@ def test_tgv_65_free_slip_matches_reference_golden(golden_dir):
 
 @pytest.mark.parametrize("nn,ncl", [((64, 64, 64), (0,) * 6), ((48, 40, 56), (0,) * 6), ((33, 33, 40), (1, 1, 1, 1, 0, 0)),
                                     # line lengths for which the fused momentum kernels run (y: L=9, z: L=17; ragged lane blocks)
-                                    ((40, 168, 304), (0,) * 6), ((24, 304, 176), (0,) * 6), ((170, 176, 168), (0,) * 6)])
+                                    ((40, 168, 304), (0,) * 6), ((24, 304, 176), (0,) * 6), ((170, 176, 168), (0,) * 6),
+                                    # long lines (BASELINE config #5 has 1536 points per direction): the fused kernels run them as
+                                    # overlap-save segments (4 x 384 rows + 48-row halos; 768 = 2 x 384)
+                                    ((24, 1536, 168), (0,) * 6), ((24, 176, 1536), (0,) * 6), ((768, 168, 176), (0,) * 6)])
 def test_solver_matches_oracle(nn, ncl):
     _solver_vs_oracle(nn, ncl, 5, 3)
 
