@@ -127,7 +127,7 @@ void launch_stag_pair(Ctx &ctx, int mode, int axis, const DevOp &opA, const DevO
     X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     long long blocks = ctx.sm_count;
     if (blocks > g.npos) blocks = g.npos;
-    kern<<<static_cast<unsigned>(blocks), 32 * (PAIR_WARPS + 1), smem, ctx.stream>>>(opA, opB, maps, g);
+    kern<<<static_cast<unsigned>(blocks), MOM_THREADS, smem, ctx.stream>>>(opA, opB, maps, g);
     X3D_CUDA(cudaGetLastError());
     ctx.launches++;
   };

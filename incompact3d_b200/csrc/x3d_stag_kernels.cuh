@@ -139,9 +139,10 @@ __device__ __forceinline__ void pair_solve_cyclic_ks2(dd2 (&x1)[L], const StagCy
   for (int m = L - 1; m >= 0; --m) { t1 = fma2(r1, t1, x1[m]); x1[m] = t1; t2 = fma2(r2, t2, x2[m]); x2[m] = t2; }
 }
 
-// 288 threads per CTA, one CTA per SM: up to 224 registers per thread (a launch bound alone makes ptxas stop at 168)
+// 8 consumer warps + one producer warpgroup (one active thread), registers rebalanced with setmaxnreg as in k_mom_pair:
+// a ninth full-size warp would put three warps on one SM sub-partition and cap every thread at 168 registers
 template <int KA, int KB, int MODE, int L>
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(MOM_THREADS, 1)
     k_stag(const __grid_constant__ DevOp opA, const __grid_constant__ DevOp opB, const __grid_constant__ StagMaps maps,
            const __grid_constant__ StagGeom g) {
   constexpr int NWIN = L + 2 * HALO;
@@ -169,9 +170,10 @@ __global__ void __maxnreg__(224)
   // MODE 0: s = 0 -> B (load inB, no store), s = 1 -> A (load inA, store outA)
   // MODE 1: s = 0 -> A (load inA, store outA), s = 1 -> S (no load, store outB)
 
-  if (warp == PAIR_WARPS) {
+  if (warp >= PAIR_WARPS) {
     // ---------------- TMA producer ----------------
-    if (lane != 0) return;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp != PAIR_WARPS || lane != 0) return;
     const unsigned in_bytes = (static_cast<unsigned>(g.nbox) * g.br + 16u) * 128u;
     auto fill = [&](long long q) {   // make slot q % 3 ready for use q: load its input, or just hand it over
       const long long pos = first + (q >> 1) * step;
@@ -209,6 +211,7 @@ __global__ void __maxnreg__(224)
   }
 
   // ---------------- consumers: warp = lane pair, thread = chunk ----------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
   const int jw = warp;
   const int cl = lane < nc ? lane : nc - 1;
   const bool live = lane < nc;
