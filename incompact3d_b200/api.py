@@ -487,13 +487,14 @@ def _decomp_stats(self):
     return a.value, b.value
 
 
-def _transpose_selftest(self, decomp_id=0, whiches=(0, 1, 2, 3), modes=(-1, 0, 1, 2)):
-    """bit-exactness of the production transposes between library-owned pencils (collective); -> number of wrong elements"""
+def _transpose_selftest(self, decomp_id=0, whiches=(0, 1, 2, 3), modes=(-1, 0, 1, 2), kinds=(0, 1)):
+    """bit-exactness of the production transposes between library-owned pencils (collective); -> number of wrong elements.
+    kinds: 0 real, 1 complex"""
     fn = self._L.x3d_transpose_selftest
     fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     bad = 0
     for which in whiches:
-        for cplx in (0, 1):
+        for cplx in kinds:
             for mode in modes:
                 m = C.c_longlong()
                 self._check(fn(self._h, int(which), int(decomp_id), cplx, int(mode), C.byref(m)))

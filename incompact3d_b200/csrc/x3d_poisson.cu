@@ -40,7 +40,7 @@ struct PoissonImpl : PoissonState {
   cufftHandle plan_r2c = 0, plan_c2r = 0, plan_xy = 0;
   // poisson_000: the x-y transforms and the spectral factor run plane-chunk by plane-chunk (forward FFT, factor, inverse
   // FFT of fft_chunk planes before the next chunk) so that a chunk stays in the 126 MB L2 between the three passes and
-  // the spectral array crosses HBM once in each direction instead of three times.  X3D_FFT_CHUNK=0 turns it off.
+  // the spectral array crosses HBM once in each direction instead of three times.  Opt-in (X3D_FFT_CHUNK=k): it measured slower.
   cufftHandle plan_xy_chunk = 0, plan_xy_rem = 0;
   int fft_chunk = 0;
   bool plans = false;
@@ -667,10 +667,11 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   int nyx[2] = {ny, nx};
   if (nzhl > 0) { X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, nzhl, &ws)); wmax = std::max(wmax, ws); }
   if (!(p.bcx || p.bcy || p.bcz) && P->spec_real && nzhl > 0) {
-    int ch = 8;
-    // a chunk must fit the L2 with room to spare: at most ~48 MB of complex planes
+    // Off by default: measured at 512^3 (profiles/r2g_fft_chunk_sweep.txt) the three whole-array passes take 1.83 ms, the
+    // chunked form 2.0-4.7 ms for chunks of 64 ... 2 planes -- cuFFT's 2-D transforms lose more on small batches than the
+    // L2 residency saves.  X3D_FFT_CHUNK=k turns it on.
+    int ch = 0;
     const long long plane_bytes = static_cast<long long>(nx) * ny * 16;
-    while (ch > 1 && ch * plane_bytes > (48ll << 20)) ch /= 2;
     if (const char *e = getenv("X3D_FFT_CHUNK")) ch = atoi(e);
     if (ch > 0 && ch < nzhl && plane_bytes <= (48ll << 20)) {
       P->fft_chunk = ch;
