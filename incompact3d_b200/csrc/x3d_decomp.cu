@@ -844,9 +844,17 @@ long long transpose_selftest(Ctx &ctx, int which, int id, int elem, int mode) {
   }
   const long long ns = static_cast<long long>(ssz[0]) * ssz[1] * ssz[2], nd = static_cast<long long>(dsz[0]) * dsz[1] * dsz[2];
   DevBuf &src = D.self_src, &dst = D.self_dst, &cnt = D.self_cnt;
-  // fixed-size, symmetric allocations (every rank reserves the same way, so the peer-pointer cache stays collective)
-  src.reserve(std::max<long long>(ns, 1) * elem * sizeof(double));
-  dst.reserve(std::max<long long>(nd, 1) * elem * sizeof(double));
+  // Symmetric allocations: every rank reserves the size of the LARGEST pencil any rank holds in this decomposition (the
+  // last mod(n, p) members of a group hold one more), not its own.  With per-rank sizes an uneven split (257 spectral
+  // planes over 2 ranks) made one rank reallocate -- a new buffer generation, i.e. a collective pointer exchange -- while
+  // the other hit its cache and went on to the flag barrier: a dead-lock.
+  {
+    auto cdiv = [](long long a, long long b) { return (a + b - 1) / b; };
+    const long long g0 = D.gdims[id][0], g1 = D.gdims[id][1], g2 = D.gdims[id][2], pr = D.p_row, pc = D.p_col;
+    const long long big = std::max({g0 * cdiv(g1, pr) * cdiv(g2, pc), cdiv(g0, pr) * g1 * cdiv(g2, pc), cdiv(g0, pr) * cdiv(g1, pc) * g2, 1LL});
+    src.reserve(big * elem * sizeof(double));
+    dst.reserve(big * elem * sizeof(double));
+  }
   cnt.reserve(sizeof(unsigned long long));
   X3D_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), ctx.stream));
   X3D_CUDA(cudaMemsetAsync(dst.p, 0xff, std::max<long long>(nd, 1) * elem * sizeof(double), ctx.stream));

@@ -41,6 +41,11 @@ def main():
         info = decomp_compute(nx, ny, nz, p_row, p_col, rank)
         # the production data plane: peer stores / block copies / copy engines between library-owned pencils
         assert x.transpose_selftest() == 0, ("selftest", p_row, p_col, rank)
+        # what bench.py does on the spectral decomposition: a second decomposition that splits unevenly (ranks hold pencils of
+        # different sizes: their self-test buffers must still be (re)allocated by all ranks together), complex first, y<->z only
+        sp = x.decomp_info_init(nx, ny, nz // 2 + 1)
+        assert x.transpose_selftest(sp, whiches=(1, 2), kinds=(1,)) == 0, ("selftest sp", p_row, p_col, rank)
+        assert x.transpose_selftest(0, whiches=(1, 2), kinds=(0,)) == 0, ("selftest after sp", p_row, p_col, rank)
         for arr, cplx in ((G, False), (Gc, True)):
             tdt = torch.complex128 if cplx else torch.float64
             for name, s, d in (("transpose_x_to_y", "x", "y"), ("transpose_y_to_z", "y", "z"),
