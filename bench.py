@@ -242,6 +242,8 @@ def alg_bytes(name, npts, nsp):
         return 16.0 * npts                      # read u, write t
     if name.startswith("accumulate_"):
         return 24.0 * npts                      # read u, read-modify-write t
+    if name.startswith("momentum_z_face"):
+        return None                             # k_zfix: rows next to the slab faces only
     if name.startswith("momentum_fused"):
         # 3 velocities in, 3 results out.  With the time integration folded in: u, v, w and the running sum in, the stored
         # right-hand side in (2 of 3 RK3 sub-steps), u, v, w out, the stored right-hand side out (2 of 3) = 104 B on average
@@ -369,7 +371,7 @@ def run_b200(args):
     for r in roof:
         ab = alg_bytes(r["name"], npl, nspl)
         r["alg_bytes_per_launch"] = ab
-        r["frac_of_hbm_peak"] = (ab / (r["avg_ms"] * 1e-3) / 1e9 / peak) if (ab and r["avg_ms"] > 0 and not r["name"].startswith("transpose_p2p")) else None
+        r["frac_of_hbm_peak"] = (ab / (r["avg_ms"] * 1e-3) / 1e9 / peak) if (ab and r["avg_ms"] > 0 and not r["name"].startswith("transpose_p2p") and not r["name"].startswith("slab_ring")) else None
     tot_ms = sum(r["total_ms"] for r in roof)
     # dominant KERNEL: classes are per direction / role; group them by the kernel that runs (the name in parentheses)
     def kern(r):
@@ -400,12 +402,12 @@ def run_b200(args):
                 "launches_per_step": k["count"], "share_of_step": k["total_ms"] / tot_ms, "classes": roof}
     nvlink = None
     if world > 1:
-        tms = sum(r["total_ms"] for r in roof if r["name"].startswith("transpose_"))
+        tms = sum(r["total_ms"] for r in roof if r["name"].startswith("transpose_") or r["name"].startswith("slab_ring_exchange"))
         gbs = nv_bytes / (tms * 1e-3) / 1e9 if tms > 0 else None
         nvlink = {"bytes_per_gpu_per_step": nv_bytes, "ms": tms, "gbs_per_direction": gbs, "frac_of_900": gbs / 900.0 if gbs else None,
                   "share_of_step": tms / tot_ms,
-                  "note": "bytes each GPU stores into its peers' pencils per step (transposes) / device time of the transpose scopes "
-                          "(between their two flag barriers) in the instrumented step; 900 GB/s = NVLink 5 per direction"}
+                  "note": "bytes each GPU stores into its peers' pencils per step (transposes, and the halo / carry planes of the slab z kernels) / device "
+                          "time of those scopes (between their two flag barriers) in the instrumented step; 900 GB/s = NVLink 5 per direction"}
 
     # ---- e2e: host jobs through the C ABI, H2D + D2H of every step inside the timed region ---------------------
     e2e = None

@@ -10,6 +10,15 @@ void register_alloc(void *p, size_t n);
 void unregister_alloc(void *p);
 bool find_alloc(const void *q, void **base, size_t *size, unsigned long long *gen = nullptr);
 
+// one item of a ring exchange between neighbouring z slabs (x3d_decomp.cu: ring_exchange)
+struct RingCopy {
+  const void *src;   // this rank's data
+  void *dst;         // base pointer of a library-owned buffer allocated the same way on every rank
+  size_t dst_off;    // byte offset inside the neighbour's buffer
+  size_t bytes;
+  int dir;           // +1: to the next rank of the ring, -1: to the previous one
+};
+
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;

@@ -803,6 +803,48 @@ void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_
   group_barrier(ctx, G);
 }
 
+// ---- ring exchange of planes between neighbouring z slabs (column group) --------------------------------------
+// Every item copies `bytes` from this rank's `src` into the buffer `dst` (a library-owned buffer that every rank allocates
+// the same way) of the member `dir` places further along the ring (+1 next, -1 previous; periodic), at byte offset
+// `dst_off`, with peer stores over NVLink between the same two flag barriers as the transposes.  All items of a call share
+// one barrier pair.  False when the group has no peer-to-peer path (the caller then uses the transposes).
+bool ring_exchange(Ctx &ctx, int n, const RingCopy *items) {
+  DecompImpl &D = DEC(ctx);
+  DecompImpl::Group &G = D.grp_col;
+  if (!D.p2p || !D.have_nccl || G.np < 2 || n < 1 || n > P2P_MAX_MEMBERS) return false;
+  X3D_CUDA(cudaSetDevice(ctx.device));
+  std::vector<const std::vector<void *> *> hosts(n, nullptr);
+  for (int q = 0; q < n; ++q)
+    if (!p2p_dst(ctx, D, G, items[q].dst, &hosts[q])) return false;   // collective on a first use; all members agree
+  BlockCopies bc;
+  unsigned long long total = 0;
+  for (int q = 0; q < n; ++q) {
+    const int m = ((G.me + items[q].dir) % G.np + G.np) % G.np;
+    BlockCopy &b = bc.b[q];
+    b.src = static_cast<const char *>(items[q].src);
+    b.dst = static_cast<char *>((*hosts[q])[m]) + items[q].dst_off;
+    b.width = b.spitch = b.dpitch = items[q].bytes;
+    b.height = 1;
+    if ((b.width | reinterpret_cast<uintptr_t>(b.src) | reinterpret_cast<uintptr_t>(b.dst)) & 15u) throw Error("ring exchange: unaligned item");
+    total += items[q].bytes;
+  }
+  D.stat_remote_bytes += total;
+  group_barrier(ctx, G);   // the neighbours have finished reading what these stores overwrite
+  {
+    ProfScope ps(ctx, "slab_ring_exchange(k_p2p_blocks)");
+    int gx = (8 * ctx.sm_count + n - 1) / n;
+    k_p2p_blocks<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n)), 256, 0, ctx.stream>>>(bc);
+    X3D_CUDA(cudaGetLastError());
+    ctx.launches++;
+  }
+  group_barrier(ctx, G);   // the neighbours' stores into my buffers have landed
+  return true;
+}
+bool ring_available(Ctx &ctx) {
+  auto *D = dynamic_cast<DecompImpl *>(ctx.decomp.get());
+  return D && D->p2p && D->have_nccl && D->grp_col.np >= 2 && D->p_row == 1;
+}
+
 // ---- self-test of the production data plane --------------------------------------------------------------
 // Fills a library-owned source pencil with the global linear index of every element (exact in a double), runs the
 // transpose through the path the solver takes (peer stores / block copies / copy engines between library-owned

@@ -3,6 +3,7 @@
 #include <cmath>
 #include "x3d_mom.cuh"
 #include "x3d_mom_kernels.cuh"
+#include "x3d_slab_kernels.cuh"
 #include "x3d_ops_inst.cuh"
 
 namespace x3d {
@@ -62,7 +63,7 @@ bool build_mom_table(Ctx &ctx, const TriTable &T, MomTable &M) {
 }
 
 // parameters of pair_solve_cyclic for the periodic system tri(alpha, 1, alpha); scale_num / c multiplies the solution
-static bool make_cyc(double alpha, int n, int L, double scale_num, MomGeom::Cyc &cy) {
+static bool make_cyc(double alpha, int n, int L, double scale_num, MomGeom::Cyc &cy, bool open = false) {
   if (!(std::fabs(alpha) < 0.5) || std::fabs(alpha) < 1e-3) return false;
   const int nc = (n + L - 1) / L, rem = n - (nc - 1) * L;
   const double rho = (-1.0 + std::sqrt(1.0 - 4.0 * alpha * alpha)) / (2.0 * alpha);
@@ -70,7 +71,7 @@ static bool make_cyc(double alpha, int n, int L, double scale_num, MomGeom::Cyc 
   int K = 1;
   while (std::pow(std::fabs(rho), static_cast<double>(K) * L) >= 1e-18 && K < 16) ++K;
   if (rem != L) ++K;     // one of the K chunks may be the short last one
-  if (K > 8 || K > nc - 1) return false;
+  if (K > 8 || (!open && K > nc - 1)) return false;   // open (slab) lines: the look-back stops at the face
   cy.rho = rho;
   cy.rhoL = std::pow(rho, L);
   cy.rhoR = std::pow(rho, rem);
@@ -261,6 +262,110 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
     if (L == 17) { if (nt4) launch(k_mom_pair<17, 4, true, false, false>); else launch(k_mom_pair<17, 2, true, false, false>); }
     else { if (nt4) launch(k_mom_pair<9, 4, true, false, false>); else launch(k_mom_pair<9, 2, true, false, false>); }
   }
+}
+
+
+// ---- z part of the momentum right-hand side on slabs, without transposes (x3d_slab_kernels.cuh) -----------------------
+namespace {
+double root_of(double alpha) { return (-1.0 + std::sqrt(1.0 - 4.0 * alpha * alpha)) / (2.0 * alpha); }
+
+bool slab_plan(long long nlanes, int n, SlabGeom &g, size_t &smem) {
+  constexpr int L = 9;
+  if ((n & 7) || n < 64 || n > 288 || (nlanes & 1)) return false;
+  if (!pair_boxes(n, true, g.nbox, g.br)) return false;
+  g.n = n;
+  g.nc = (n + L - 1) / L;
+  g.rem = n - (g.nc - 1) * L;
+  g.nbx = static_cast<int>((nlanes + 15) / 16);
+  g.ntiles = g.nbx;
+  g.gshift = g.nc <= 8 ? 2 : (g.nc <= 16 ? 1 : 0);
+  while (g.gshift > 0 && (g.ntiles % (1 << g.gshift)) != 0) --g.gshift;
+  g.npos = g.ntiles >> g.gshift;
+  g.sub_bytes = (8 + n + 8) * 128;
+  g.slot_bytes = g.sub_bytes << g.gshift;
+  if (static_cast<long long>(g.nc * L + 8 + HALO - (n + 16)) * 128 > 512 * 8) return false;
+  smem = static_cast<size_t>(3) * g.slot_bytes + 512 * 8 + 2 * 3 * 8;
+  return smem <= 227 * 1024;
+}
+}  // namespace
+
+// rows of a slab line: both recurrences must forget a whole slab (|rho|^n < 1e-17), see x3d_slab_kernels.cuh
+bool mom_slab_eligible(double alpha1, double alpha2, long long nlanes, int n) {
+  SlabGeom g{};
+  size_t smem;
+  if (!slab_plan(nlanes, n, g, smem)) return false;
+  MomGeom::Cyc cy{};
+  for (double a : {alpha1, alpha2}) {
+    if (!make_cyc(a, n, 9, 1.0, cy, true)) return false;
+    if (std::pow(std::fabs(root_of(a)), n) > 1e-17) return false;
+  }
+  return true;
+}
+
+void launch_mom_slab(Ctx &ctx, const DevOp &op1, const DevOp &op2, double xnu, const double *const f[3], const double *const halo[3],
+                     double *const out[3], long long nlanes, int n, bool add, double *carry) {
+  SlabGeom g{};
+  size_t smem = 0;
+  if (!slab_plan(nlanes, n, g, smem) || !make_cyc(op1.alpha, n, 9, -0.5, g.cy1, true) || !make_cyc(op2.alpha, n, 9, xnu, g.cy2, true))
+    throw Error("slab momentum kernel: ineligible call");
+  g.ia = 2; g.ic1 = 0; g.ic2 = 1;
+  g.add = add ? 1 : 0;
+  g.carry = carry;
+  g.nlanes = nlanes;
+  MomMaps maps;
+  for (int q = 0; q < 3; ++q) {
+    if ((reinterpret_cast<uintptr_t>(f[q]) | reinterpret_cast<uintptr_t>(halo[q]) | reinterpret_cast<uintptr_t>(out[q])) & 15u)
+      throw Error("slab momentum kernel: unaligned field");
+    maps.in[q] = make_line_map(f[q], nlanes, n, 1, nlanes, nlanes * n, 16, g.br, true);
+    maps.halo[q] = make_line_map(halo[q], nlanes, 16, 1, nlanes, nlanes * 16, 16, 8, true);
+    maps.out[q] = make_line_map(out[q], nlanes, n, 1, nlanes, nlanes * n, 16, g.br, true);
+  }
+  const bool nt4 = op2.c[2] != 0.0 || op2.c[3] != 0.0;
+  auto launch = [&](auto kern) {
+    X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    long long blocks = ctx.sm_count;
+    if (blocks > g.npos) blocks = g.npos;
+    kern<<<static_cast<unsigned>(blocks), MOM_THREADS, smem, ctx.stream>>>(op1, op2, maps, g);
+    X3D_CUDA(cudaGetLastError());
+    ctx.launches++;
+  };
+  ProfScope ps(ctx, "momentum_fused_z_slab(k_mom_slab)");
+  if (nt4) launch(k_mom_slab<9, 4>); else launch(k_mom_slab<9, 2>);
+}
+
+// tables A(i), B(i) of the face corrections for the two operators, and the band width W
+void build_zfix(Ctx &ctx, const DevOp &op1, const DevOp &op2, double xnu, int n, ZFix &Z) {
+  const double r1 = root_of(op1.alpha), r2 = root_of(op2.alpha);
+  std::vector<double> h(static_cast<size_t>(4) * n);
+  for (int i = 0; i < n; ++i) {
+    h[i] = std::pow(r1, i + 1) * (1.0 - std::pow(r1, 2.0 * (n - i))) / (1.0 - r1 * r1);
+    h[n + i] = std::pow(r1, n - i);
+    h[2 * n + i] = std::pow(r2, i + 1) * (1.0 - std::pow(r2, 2.0 * (n - i))) / (1.0 - r2 * r2);
+    h[3 * n + i] = std::pow(r2, n - i);
+  }
+  const double rmax = std::max(std::fabs(r1), std::fabs(r2));
+  int W = 1;
+  while (W < n && std::pow(rmax, W) > 1e-19) ++W;
+  Z.tab.reserve(h.size() * sizeof(double));
+  X3D_CUDA(cudaMemcpyAsync(Z.tab.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  X3D_CUDA(cudaStreamSynchronize(ctx.stream));
+  Z.n = n; Z.W = W;
+  Z.k1 = -0.5 / (-op1.alpha / r1);
+  Z.k2 = xnu / (-op2.alpha / r2);
+}
+
+void launch_zfix(Ctx &ctx, const ZFix &Z, const double *yin, const double *z0n, const double *yout, double *const sum[3], const double *a,
+                 long long nlanes) {
+  ZFixArgs z{};
+  z.yin = yin; z.z0n = z0n; z.yout = yout;
+  for (int q = 0; q < 3; ++q) z.sum[q] = sum[q];
+  z.a = a;
+  z.tab = static_cast<const double *>(Z.tab.p);
+  z.nl = nlanes; z.n = Z.n; z.W = Z.W; z.k1 = Z.k1; z.k2 = Z.k2;
+  ProfScope ps(ctx, "momentum_z_face_corrections(k_zfix)");
+  k_zfix<<<static_cast<unsigned>((nlanes + 255) / 256), 256, 0, ctx.stream>>>(z);
+  X3D_CUDA(cudaGetLastError());
+  ctx.launches++;
 }
 
 }  // namespace x3d

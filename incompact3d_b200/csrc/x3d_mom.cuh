@@ -36,6 +36,21 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
                   const MomIntt *intt = nullptr);
 bool mom_x_eligible(int n, int L);
 
+// z lines of slabs without transposes (x3d_slab_kernels.cuh): zero-carry solves of the slab's own rows + carry planes, then the
+// face corrections.  f / out: the slab (nlanes, n rows); halo[c]: (nlanes, 16) with rows 4..7 = the 4 planes below, 8..11 = above;
+// carry: [18][nlanes] (Yout of the 9 systems, then Z0)
+bool mom_slab_eligible(double alpha1, double alpha2, long long nlanes, int n);
+void launch_mom_slab(Ctx &ctx, const DevOp &op1, const DevOp &op2, double xnu, const double *const f[3], const double *const halo[3],
+                     double *const out[3], long long nlanes, int n, bool add, double *carry);
+struct ZFix {
+  DevBuf tab;     // [4][n]: A (D1), B (D1), A (D2), B (D2)
+  int n = 0, W = 0;
+  double k1 = 0.0, k2 = 0.0;
+};
+void build_zfix(Ctx &ctx, const DevOp &op1, const DevOp &op2, double xnu, int n, ZFix &Z);
+void launch_zfix(Ctx &ctx, const ZFix &Z, const double *yin, const double *z0n, const double *yout, double *const sum[3], const double *a,
+                 long long nlanes);
+
 // fused pairs of periodic staggered operators on y / z lines (x3d_stag_kernels.cuh, x3d_stag.cu)
 //   mode 0: outA = opA(inA) + opB(inB), (opA, opB) = (inter?vp, der?vp);  mode 1: outA = opA(inA), outB = opB(inA), (inter?pv, der?pv)
 bool stag_pair_eligible(Ctx &ctx, const DevOp &opA, const DevOp &opB, long long n1, int nline, long long sline, long long souter, long long nouter);

@@ -20,6 +20,8 @@ void transpose_device(Ctx &ctx, int which, const double *d_src, double *d_dst, i
 void transpose_device_multi(Ctx &ctx, int which, int nf, const double *const *d_src, double *const *d_dst, int id, int elem);
 void allreduce(Ctx &ctx, double *d_buf, int n, bool is_max);
 void decomp_shape(Ctx &ctx, int *p_row, int *p_col, int *rank, int *nranks);
+bool ring_exchange(Ctx &ctx, int n, const RingCopy *items);
+bool ring_available(Ctx &ctx);
 
 namespace {
 
@@ -174,6 +176,15 @@ struct SolverImpl : SolverState {
   DevBuf unew[3];                           // segmented x lines: the fused time integration writes the new velocity here
   bool stag[3] = {false, false, false};     // fused pairs of staggered operators on periodic y / z lines (X3D_FUSE_STAG=0: off)
   bool fuse_intt = true;                    // time integration folded into the x momentum kernel (X3D_FUSE_INTT=0: k_map pass)
+  // z part of the momentum terms on the slabs themselves (x3d_slab_kernels.cuh): no y <-> z transposes of the velocity and of
+  // its right-hand side; neighbouring ranks exchange 4 halo planes per component and 18 carry planes.  X3D_SLABZ=0: transposes.
+  // slab_nv > 1 on ONE rank (X3D_SLABZ_EMULATE=P): the rank's planes are treated as P virtual slabs with local copies for
+  // the exchanges -- the same kernels and arithmetic as P ranks, testable on one GPU.
+  bool slabz = false;
+  int slab_nv = 1;
+  DevBuf zhalo[3];                          // [slab_nv][16 planes]
+  DevBuf zcarry_out, zcarry_in;             // [slab_nv][18 planes]: Yout | Z0 of this rank;  Yout of the previous | Z0 of the next rank
+  ZFix zfix;
   // several ranks, X3D_OVERLAP=1: the y -> z transposes of the velocity run on `aux` while the x and y momentum
   // kernels compute.  Off by default: on 2 B200 it gave 42.4 ms per 512^3 step against 42.3 ms on one stream (the
   // hidden copies are paid back by slower kernels beside them and by the extra array intt then reads).
@@ -382,6 +393,26 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   S->ipv_x_sub = S->ipv[0]; S->ipv_x_sub.op.store_mode = 2;
   if (const char *e = getenv("X3D_FUSE_SUMS")) S->fuse_sums = atoi(e) != 0;
   if (const char *e = getenv("X3D_OVERLAP")) S->overlap = atoi(e);
+  {
+    // slab z kernels: periodic z, the fused kernels with table-free solves in all three directions, equal slabs
+    const char *e = getenv("X3D_SLABZ"), *em = getenv("X3D_SLABZ_EMULATE");
+    int nv = 1;
+    bool want = !(e && atoi(e) == 0);
+    if (S->nranks == 1) { nv = em ? atoi(em) : 1; want = want && nv > 1; }
+    else want = want && ring_available(ctx);
+    const long long plane = static_cast<long long>(p.nx) * p.ny;
+    if (want && S->fused[1] && S->fused[2] && S->cyclic[2] && p.nz % (S->nranks * nv) == 0 && nzl * S->nranks == p.nz &&
+        mom_slab_eligible(S->d1[2][0].op.alpha, S->d2[2][0].op.alpha, plane, nzl / nv)) {
+      S->slabz = true;
+      S->slab_nv = nv;
+      for (auto &b : S->zhalo) { b.reserve(static_cast<size_t>(nv) * 16 * plane * sizeof(double)); X3D_CUDA(cudaMemsetAsync(b.p, 0, b.bytes, ctx.stream)); }
+      S->zcarry_out.reserve(static_cast<size_t>(nv) * 18 * plane * sizeof(double));
+      S->zcarry_in.reserve(static_cast<size_t>(nv) * 18 * plane * sizeof(double));
+      X3D_CUDA(cudaMemsetAsync(S->zcarry_out.p, 0, S->zcarry_out.bytes, ctx.stream));
+      X3D_CUDA(cudaMemsetAsync(S->zcarry_in.p, 0, S->zcarry_in.bytes, ctx.stream));
+      build_zfix(ctx, S->d1[2][0].op, S->d2[2][0].op, S->xnu, nzl / nv, S->zfix);
+    }
+  }
   x3d_poisson_params pp{};
   pp.nx = p.nx; pp.ny = p.ny; pp.nz = p.nz;
   pp.bcx = S->A[0].periodic ? 0 : 1; pp.bcy = S->A[1].periodic ? 0 : 1; pp.bcz = S->A[2].periodic ? 0 : 1;
@@ -631,7 +662,45 @@ static bool momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
   const long long lanes = static_cast<long long>(nx) * S.nyl;
   extra[0] = extra[1] = extra[2] = nullptr;
   bool z_first = true;
-  if (!alias) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
+  const bool slab = S.slabz;
+  const long long plane = static_cast<long long>(nx) * ny;
+  const int nv = S.slab_nv, nzv = S.nzl / (nv > 0 ? nv : 1);
+  if (slab) {
+    // transeq.f90:236-320 without the transposes: every rank differentiates its own planes of the z lines (zero-carry solves),
+    // the face corrections follow once the carries of the neighbours are there (x3d_slab_kernels.cuh)
+    double *hz[3] = {B(S.zhalo[0]), B(S.zhalo[1]), B(S.zhalo[2])};
+    double *co = B(S.zcarry_out);
+    const size_t pb = static_cast<size_t>(plane) * sizeof(double);
+    if (S.nranks > 1) {
+      RingCopy rc[6];
+      for (int c = 0; c < 3; ++c) {
+        rc[2 * c] = RingCopy{f[c] + static_cast<long long>(S.nzl - 4) * plane, hz[c], 4 * pb, 4 * pb, +1};   // my last planes: below the next slab
+        rc[2 * c + 1] = RingCopy{f[c], hz[c], 8 * pb, 4 * pb, -1};                                            // my first planes: above the previous slab
+      }
+      if (!ring_exchange(ctx, 6, rc)) throw Error("solver: slab z kernels without a peer-to-peer path");
+    } else {
+      for (int v = 0; v < nv; ++v)
+        for (int c = 0; c < 3; ++c) {
+          const int vp = (v + nv - 1) % nv, vn = (v + 1) % nv;
+          double *h = hz[c] + static_cast<long long>(v) * 16 * plane;
+          X3D_CUDA(cudaMemcpyAsync(h + 4 * plane, f[c] + (static_cast<long long>(vp) * nzv + nzv - 4) * plane, 4 * pb, cudaMemcpyDeviceToDevice, ctx.stream));
+          X3D_CUDA(cudaMemcpyAsync(h + 8 * plane, f[c] + static_cast<long long>(vn) * nzv * plane, 4 * pb, cudaMemcpyDeviceToDevice, ctx.stream));
+        }
+    }
+    for (int v = 0; v < nv; ++v) {
+      const long long o = static_cast<long long>(v) * nzv * plane;
+      const double *fv[3] = {f[0] + o, f[1] + o, f[2] + o};
+      const double *hv[3] = {hz[0] + static_cast<long long>(v) * 16 * plane, hz[1] + static_cast<long long>(v) * 16 * plane, hz[2] + static_cast<long long>(v) * 16 * plane};
+      double *ov[3] = {sum[0] + o, sum[1] + o, sum[2] + o};
+      launch_mom_slab(ctx, S.d1[2][0].op, S.d2[2][0].op, xnu, fv, hv, ov, plane, nzv, false, co + static_cast<long long>(v) * 18 * plane);
+    }
+    if (S.nranks > 1) {
+      RingCopy rc[2] = {RingCopy{co, B(S.zcarry_in), 0, 9 * pb, +1},                    // Yout -> Yin of the next slab
+                        RingCopy{co + 9 * plane, B(S.zcarry_in), 9 * pb, 9 * pb, -1}};  // Z0 -> the previous slab
+      if (!ring_exchange(ctx, 2, rc)) throw Error("solver: slab z kernels without a peer-to-peer path");
+    }
+  }
+  if (!alias && !slab) {  // transpose_y_to_z of the three components, one barrier pair (transeq.f90:236-238)
     if (S.overlap) {
       if (!S.aux) {
         int lo = 0, hi = 0;
@@ -667,9 +736,19 @@ static bool momentum_rhs_fused(Ctx &ctx, SolverImpl &S, double *sum[3], double *
       }
     }
   };
-  if (z_first) z_dir(true);
+  if (z_first && !slab) z_dir(true);
   // ---- y, transeq.f90:188-219,336-338
   launch_mom_pair(ctx, 1, S.d1[1][0].op, S.d2[1][0].op, S.mt1[1], S.mt2[1], xnu, f, sum, nx, ny, S.nzl, nx, static_cast<long long>(nx) * ny, z_first, S.cyclic[1]);
+  if (slab) {   // face corrections of the z part: A Yin + B Zin on the rows next to the slab faces
+    const double *co = B(S.zcarry_out), *ci = B(S.zcarry_in);
+    for (int v = 0; v < nv; ++v) {
+      const long long o = static_cast<long long>(v) * nzv * plane;
+      const double *yin = S.nranks > 1 ? ci : co + static_cast<long long>((v + nv - 1) % nv) * 18 * plane;
+      const double *z0n = S.nranks > 1 ? ci + 9 * plane : co + (static_cast<long long>((v + 1) % nv) * 18 + 9) * plane;
+      double *sv[3] = {sum[0] + o, sum[1] + o, sum[2] + o};
+      launch_zfix(ctx, S.zfix, yin, z0n, co + static_cast<long long>(v) * 18 * plane, sv, w + o, plane);
+    }
+  }
   bool z_pending = !z_first;
   if (z_pending && S.overlap == 2) {   // the forward transposes ran beside the y kernel: z now, x (+ intt) last
     X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));

@@ -62,12 +62,19 @@ def main():
     # ---- slab-decomposed solver vs the single-rank oracle -----------------------------------------
     import oracle_lib as ol
     from test_oracle_tgv import make_solver
+    # torch.distributed.run exports OMP_NUM_THREADS=1: give the oracle this rank's share of the host cores instead
+    Lo = ol.lib()
+    Lo.x3do_set_threads.argtypes = [C.c_int]
+    Lo.x3do_set_threads(max(1, len(os.sched_getaffinity(0)) // world))
     # the last case has line lengths for which the fused momentum kernels (and their reduce-add accumulation across
     # the z -> y transposes) run
     # X3D_P2P_MODE (read by x3d_decomp_init): the block copies of the y<->z transposes through the vector-copy kernel
     # (what these small pencils take by default) and through the copy engines (what 512^3 pencils take)
     for nn, ncl, p2p_mode, overlap in (((32, 24, 40), (0,) * 6, None, "0"), ((33, 25, 33), (1,) * 6, "1", "0"), ((24, 176, 168), (0,) * 6, None, "0"),
-                                       ((24, 176, 168), (0,) * 6, "1", "1"), ((176, 176, 168), (0,) * 6, None, "2")):
+                                       ((24, 176, 168), (0,) * 6, "1", "1"), ((176, 176, 168), (0,) * 6, None, "2"),
+                                       # equal slabs of >= 64 planes: the z part of the momentum terms runs on the slabs themselves
+                                       # (k_mom_slab + k_zfix, halo and carry planes through ring_exchange) instead of through transposes
+                                       ((32, 168, 256), (0,) * 6, None, "0"), ((176, 168, 256), (0,) * 6, None, "0")):
         length = 2 * np.pi
         if p2p_mode is None:
             os.environ.pop("X3D_P2P_MODE", None)
@@ -100,7 +107,10 @@ def main():
         assert abs(d["divmax"]) < 1e-11
         if nn[1] >= 168 and os.environ.get("X3D_FUSED", "1") != "0":
             names = {r["name"] for r in x.profile_step(1)}
-            assert "momentum_fused_y(k_mom_pair)" in names and "momentum_fused_z(k_mom_pair)" in names, names
+            slab = nn[2] % world == 0 and (nn[2] // world) % 8 == 0 and 64 <= nn[2] // world <= 288 and os.environ.get("X3D_SLABZ", "1") != "0"
+            zname = "momentum_fused_z_slab(k_mom_slab)" if slab else "momentum_fused_z(k_mom_pair)"
+            assert "momentum_fused_y(k_mom_pair)" in names and zname in names, names
+            assert ("slab_ring_exchange(k_p2p_blocks)" in names) == slab, names
         x.close()
         dist.barrier()
     if rank == 0:

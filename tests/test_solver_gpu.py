@@ -47,6 +47,18 @@ def test_solver_matches_oracle(nn, ncl):
     _solver_vs_oracle(nn, ncl, 5, 3)
 
 
+# z part of the momentum terms solved slab by slab (x3d_slab_kernels.cuh: zero-carry solves, carry planes, face corrections)
+# instead of through y <-> z transposes -- what several GPUs do; here ONE rank treats its planes as P virtual slabs
+# (X3D_SLABZ_EMULATE), same kernels and arithmetic.  64-row slabs: 4 lines per warp; 128: 2; 256: 1.
+@pytest.mark.parametrize("nn,nslab,scheme", [((32, 168, 192), 3, 5), ((32, 168, 256), 4, 5), ((24, 176, 256), 2, 5), ((24, 176, 512), 2, 5),
+                                             ((176, 168, 256), 2, 5), ((32, 168, 192), 3, 3), ((30, 168, 256), 2, 1)])
+def test_slab_z_momentum_matches_oracle(nn, nslab, scheme, monkeypatch):
+    monkeypatch.setenv("X3D_SLABZ_EMULATE", str(nslab))
+    names = _solver_vs_oracle(nn, (0,) * 6, scheme, 3)
+    assert "momentum_fused_z_slab(k_mom_slab)" in names and "momentum_z_face_corrections(k_zfix)" in names, names
+    assert "momentum_fused_z(k_mom_pair)" not in names, names
+
+
 # Euler / AB2 / AB3 (time_integrators.f90:71-100, variables.f90:1343-1374): four steps so that AB3 passes through
 # its Euler and AB2 start-up steps; unfused and fused momentum paths
 @pytest.mark.parametrize("scheme", [1, 2, 3])
@@ -90,12 +102,14 @@ def _solver_vs_oracle(nn, ncl, scheme, nsteps):
     assert np.abs(got / np.array(out[:]) - 1).max() < 1e-10
     dmax, dmean = x.solver_divergence()
     assert abs(dmax) < 1e-11 and dmean < 1e-12
-    if min(nn[1], nn[2]) >= 168 and os.environ.get("X3D_FUSED", "1") != "0":
-        names = {r["name"] for r in x.profile_step(1)}   # the fused momentum kernels were the ones that ran
+    names = {r["name"] for r in x.profile_step(1)}
+    if min(nn[1], nn[2]) >= 168 and os.environ.get("X3D_FUSED", "1") != "0" and "X3D_SLABZ_EMULATE" not in os.environ:
+        # the fused momentum kernels were the ones that ran
         assert "momentum_fused_y(k_mom_pair)" in names and "momentum_fused_z(k_mom_pair)" in names, names
         assert any(nm.startswith("momentum_fused_x") for nm in names) == (nn[0] >= 168), names
     Ls.x3do_solver_destroy(s)
     x.close()
+    return names
 
 
 @pytest.mark.parametrize("nn,istret,second", [((32, 33, 16), 0, 4), ((32, 33, 16), 2, 5), ((24, 41, 20), 1, 4), ((16, 33, 12), 3, 4)])
