@@ -269,9 +269,12 @@ void launch_mom_x(Ctx &ctx, const DevOp &op1, const DevOp &op2, const MomTable &
 namespace {
 double root_of(double alpha) { return (-1.0 + std::sqrt(1.0 - 4.0 * alpha * alpha)) / (2.0 * alpha); }
 
+// chunks of 17 rows from 128 rows on (8 .. 17 chunks per line: 2 or 4 lines per warp), of 9 rows below (64 rows: 8 chunks)
+int slab_L(int n) { return n >= 128 ? 17 : 9; }
+
 bool slab_plan(long long nlanes, int n, SlabGeom &g, size_t &smem) {
-  constexpr int L = 9;
-  if ((n & 7) || n < 64 || n > 288 || (nlanes & 1)) return false;
+  const int L = slab_L(n);
+  if ((n & 7) || n < 64 || n > 544 || (nlanes & 1)) return false;
   if (!pair_boxes(n, true, g.nbox, g.br)) return false;
   g.n = n;
   g.nc = (n + L - 1) / L;
@@ -296,7 +299,7 @@ bool mom_slab_eligible(double alpha1, double alpha2, long long nlanes, int n) {
   if (!slab_plan(nlanes, n, g, smem)) return false;
   MomGeom::Cyc cy{};
   for (double a : {alpha1, alpha2}) {
-    if (!make_cyc(a, n, 9, 1.0, cy, true)) return false;
+    if (!make_cyc(a, n, slab_L(n), 1.0, cy, true)) return false;
     if (std::pow(std::fabs(root_of(a)), n) > 1e-17) return false;
   }
   return true;
@@ -306,7 +309,8 @@ void launch_mom_slab(Ctx &ctx, const DevOp &op1, const DevOp &op2, double xnu, c
                      double *const out[3], long long nlanes, int n, bool add, double *carry) {
   SlabGeom g{};
   size_t smem = 0;
-  if (!slab_plan(nlanes, n, g, smem) || !make_cyc(op1.alpha, n, 9, -0.5, g.cy1, true) || !make_cyc(op2.alpha, n, 9, xnu, g.cy2, true))
+  const int L = slab_L(n);
+  if (!slab_plan(nlanes, n, g, smem) || !make_cyc(op1.alpha, n, L, -0.5, g.cy1, true) || !make_cyc(op2.alpha, n, L, xnu, g.cy2, true))
     throw Error("slab momentum kernel: ineligible call");
   g.ia = 2; g.ic1 = 0; g.ic2 = 1;
   g.add = add ? 1 : 0;
@@ -330,7 +334,8 @@ void launch_mom_slab(Ctx &ctx, const DevOp &op1, const DevOp &op2, double xnu, c
     ctx.launches++;
   };
   ProfScope ps(ctx, "momentum_fused_z_slab(k_mom_slab)");
-  if (nt4) launch(k_mom_slab<9, 4>); else launch(k_mom_slab<9, 2>);
+  if (L == 17) { if (nt4) launch(k_mom_slab<17, 4>); else launch(k_mom_slab<17, 2>); }
+  else { if (nt4) launch(k_mom_slab<9, 4>); else launch(k_mom_slab<9, 2>); }
 }
 
 // tables A(i), B(i) of the face corrections for the two operators, and the band width W

@@ -107,7 +107,7 @@ def main():
         assert abs(d["divmax"]) < 1e-11
         if nn[1] >= 168 and os.environ.get("X3D_FUSED", "1") != "0":
             names = {r["name"] for r in x.profile_step(1)}
-            slab = nn[2] % world == 0 and (nn[2] // world) % 8 == 0 and 64 <= nn[2] // world <= 288 and os.environ.get("X3D_SLABZ", "1") != "0"
+            slab = nn[2] % world == 0 and (nn[2] // world) % 8 == 0 and 64 <= nn[2] // world <= 544 and os.environ.get("X3D_SLABZ", "1") != "0"
             zname = "momentum_fused_z_slab(k_mom_slab)" if slab else "momentum_fused_z(k_mom_pair)"
             assert "momentum_fused_y(k_mom_pair)" in names and zname in names, names
             assert ("slab_ring_exchange(k_p2p_blocks)" in names) == slab, names
