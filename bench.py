@@ -514,13 +514,16 @@ def run_b200(args):
                   "max_du_over_max_u": err, "tol": PARITY_TOL, "diagnostics_rel_err": drel, "gpu_divmax": gd.get("divmax") if gd else None,
                   "ok": bool(ok)}
 
+    free_b, total_b = torch.cuda.mem_get_info()
+    hbm_used = round(allmax((total_b - free_b) / 1e9), 2)   # memory budget: device memory in use on the fullest GPU at the end of the run
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["name"],
-                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), transposes = peer stores into the owners' pencils over NVLink (CUDA IPC) between device-side flag barriers"),
+                   "parallelism": f"{world} GPU" + ("" if world == 1 else f", 2-D pencil decomposition p_row=1 x p_col={world} (slabs), transposes = peer stores into the owners' pencils over NVLink (CUDA IPC) between device-side flag barriers; z part of the momentum terms on the slabs themselves (halo + carry planes) when the slabs are equal and >= 64 planes"),
                    "l2": "fields are far larger than the 126 MB L2 (1 GiB each at 512^3); no flush needed" if npts >= 2 ** 26 else "fields fit the 126 MB L2: an L2-resident, launch-bound configuration",
+                   "hbm_gb_in_use_per_gpu": hbm_used,
                    "diagnostics_after_run": diag},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "transposes_bit_exact": bit_exact, "nvlink": nvlink,

@@ -74,7 +74,8 @@ def main():
                                        ((24, 176, 168), (0,) * 6, "1", "1"), ((176, 176, 168), (0,) * 6, None, "2"),
                                        # equal slabs of >= 64 planes: the z part of the momentum terms runs on the slabs themselves
                                        # (k_mom_slab + k_zfix, halo and carry planes through ring_exchange) instead of through transposes
-                                       ((32, 168, 256), (0,) * 6, None, "0"), ((176, 168, 256), (0,) * 6, None, "0")):
+                                       ((32, 168, 256), (0,) * 6, None, "0"), ((176, 168, 256), (0,) * 6, None, "0"),
+                                       ((32, 168, 512), (0,) * 6, None, "0")):   # slabs of 256 / 128 / 64 planes on 2 / 4 / 8 ranks
         length = 2 * np.pi
         if p2p_mode is None:
             os.environ.pop("X3D_P2P_MODE", None)
