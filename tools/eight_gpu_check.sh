@@ -4,10 +4,11 @@
 tag=$1
 out=gpurun_out/$tag
 mkdir -p $out
-run() { n=$1; name=$2; shift 2; (time timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n "$@") > $out/$name.json 2> $out/$name.err; tail -c 900 $out/$name.json; tail -3 $out/$name.err; }
-(time timeout 420 python -m pytest tests/test_transpose_gpu.py -x -q -k "multi_gpu and 8") > $out/pytest.log 2>&1; tail -15 $out/pytest.log
-run 8 bench8 --steps 20 --warmup 5 --no-e2e
+run() { n=$1; name=$2; shift 2; (time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n "$@") > $out/$name.json 2> $out/$name.err; tail -c 900 $out/$name.json; tail -3 $out/$name.err; }
+export X3D_BARRIER_TIMEOUT_S=20   # a rank that never arrives is reported after 20 s instead of 120
+(time timeout 250 python -m pytest tests/test_transpose_gpu.py -x -q -k "multi_gpu and 8") > $out/pytest.log 2>&1; tail -15 $out/pytest.log
+grep -q "1 passed" $out/pytest.log || { echo "worker test failed: not running the benches"; exit 1; }
+run 8 bench8 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline
 run 4 bench4 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline
-X3D_SLABZ=0 run 8 bench8_transposes --steps 20 --warmup 5 --no-e2e --no-cpu-baseline
 run 8 bench8_1536 --n 1536 --steps 3 --warmup 1 --no-e2e --no-cpu-baseline
 nvidia-smi --query-gpu=memory.used --format=csv | head -3
