@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--case", default="tgv", choices=["tgv", "channel", "cylinder"])
-    ap.add_argument("--n", type=int, default=512, help="nodes per direction (periodic TGV)")
+    # --size: the same under torch.distributed.run, whose own parser takes "--n" for an abbreviation of --nnodes / --nproc-per-node
+    ap.add_argument("--n", "--size", dest="n", type=int, default=512, help="nodes per direction (periodic TGV)")
     ap.add_argument("--parity-n", type=int, default=256, help="box size of the in-bench GPU-vs-oracle parity run (also the "
                     "bounded CPU sample of cpu_baseline)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock budget of the reference arm's timed steps")
@@ -456,6 +457,8 @@ def run_b200(args):
                        "turn (job j reads and writes member j mod 3), so the copies run on their own streams beside the kernels of the "
                        "neighbouring jobs; wall clock between barriers, max over ranks"}
         del sets
+    free_b, total_b = torch.cuda.mem_get_info()
+    hbm_used = round(allmax((total_b - free_b) / 1e9), 2)   # memory budget: device memory in use on the fullest GPU while the solver exists
     x.close()
 
     # ---- parity + cpu_baseline: GPU solver (same rank layout) vs the oracle from the same state, bounded size ----
@@ -514,8 +517,6 @@ def run_b200(args):
                   "max_du_over_max_u": err, "tol": PARITY_TOL, "diagnostics_rel_err": drel, "gpu_divmax": gd.get("divmax") if gd else None,
                   "ok": bool(ok)}
 
-    free_b, total_b = torch.cuda.mem_get_info()
-    hbm_used = round(allmax((total_b - free_b) / 1e9), 2)   # memory budget: device memory in use on the fullest GPU at the end of the run
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

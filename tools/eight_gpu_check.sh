@@ -10,5 +10,5 @@ export X3D_BARRIER_TIMEOUT_S=20   # a rank that never arrives is reported after 
 grep -q "1 passed" $out/pytest.log || { echo "worker test failed: not running the benches"; exit 1; }
 run 8 bench8 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline
 run 4 bench4 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline
-run 8 bench8_1536 --n 1536 --steps 3 --warmup 1 --no-e2e --no-cpu-baseline
+run 8 bench8_1536 --size 1536 --steps 3 --warmup 1 --no-e2e --no-cpu-baseline
 nvidia-smi --query-gpu=memory.used --format=csv | head -3
