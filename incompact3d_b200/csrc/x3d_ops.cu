@@ -18,8 +18,10 @@ void launch_kind_IPV(Ctx &, const DevOp &, const LineGeom &, const TriTable &, c
 
 Ctx::Ctx() {}
 void stag_release(Ctx *ctx);
+void fft_release(Ctx *ctx);
 Ctx::~Ctx() {
   stag_release(this);
+  fft_release(this);
   tri_cache.clear();
   if (stream) cudaStreamDestroy(stream);
 }

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <algorithm>
 #include "x3d_state.cuh"
+#include "x3d_fft.cuh"
+#include "x3d_fft_kernels.cuh"
 
 namespace x3d {
 
@@ -51,6 +53,9 @@ struct PoissonImpl : PoissonState {
   double *d_ax = nullptr, *d_bx = nullptr, *d_ay = nullptr, *d_by = nullptr, *d_az = nullptr, *d_bz = nullptr;
   double *d_xk2 = nullptr, *d_yk2 = nullptr, *d_zk2 = nullptr, *d_tx = nullptr, *d_ty = nullptr, *d_tz = nullptr;
   // stretched y mesh (matrice_refinement + inversion5_v1/v2): pre-eliminated pentadiagonal systems
+  // poisson_000 on power-of-two meshes: the hand-written FFT passes of x3d_fft_kernels.cuh instead of the cuFFT plans (z real
+  // transforms, y transforms, and ONE x pass that does forward transform + spectral factor + inverse transform).  X3D_FFT=0: cuFFT.
+  bool own_fft = false;
   bool spec_real = false;   // poisson_000 with identical (re,im) z tables: the spectral step is one real factor per mode
   int istret = 0;
   int pen_nsys = 0, pen_rows = 0;     // istret 1,2: two systems (odd / even modes) of ny/2 rows; istret 3: one of nym rows
@@ -657,15 +662,20 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   int inembed[1] = {nz}, onembed[1] = {nzh};
   const int nxyl = nx * nyl;
   size_t ws = 0, wmax = 0;
+  {
+    const char *e = getenv("X3D_FFT");
+    P->own_fft = !(e && atoi(e) == 0) && !(p.bcx || p.bcy || p.bcz) && P->spec_real && fft_real_ok(nz) && fft_complex_ok(ny) && fft_complex_ok(nx) &&
+                 !getenv("X3D_FFT_CHUNK");
+  }
   X3D_CUFFT(cufftCreate(&P->plan_r2c)); X3D_CUFFT(cufftCreate(&P->plan_c2r)); X3D_CUFFT(cufftCreate(&P->plan_xy));
   P->plans = true;
   X3D_CUFFT(cufftSetAutoAllocation(P->plan_r2c, 0)); X3D_CUFFT(cufftSetAutoAllocation(P->plan_c2r, 0)); X3D_CUFFT(cufftSetAutoAllocation(P->plan_xy, 0));
-  if (nxyl > 0) {
+  if (nxyl > 0 && !P->own_fft) {
     X3D_CUFFT(cufftMakePlanMany(P->plan_r2c, 1, nzv, inembed, nxyl, 1, onembed, nxyl, 1, CUFFT_D2Z, nxyl, &ws)); wmax = std::max(wmax, ws);
     X3D_CUFFT(cufftMakePlanMany(P->plan_c2r, 1, nzv, onembed, nxyl, 1, inembed, nxyl, 1, CUFFT_Z2D, nxyl, &ws)); wmax = std::max(wmax, ws);
   }
   int nyx[2] = {ny, nx};
-  if (nzhl > 0) { X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, nzhl, &ws)); wmax = std::max(wmax, ws); }
+  if (nzhl > 0 && !P->own_fft) { X3D_CUFFT(cufftMakePlanMany(P->plan_xy, 2, nyx, nullptr, 1, nx * ny, nullptr, 1, nx * ny, CUFFT_Z2Z, nzhl, &ws)); wmax = std::max(wmax, ws); }
   if (!(p.bcx || p.bcy || p.bcz) && P->spec_real && nzhl > 0) {
     // Off by default: measured at 512^3 (profiles/r2g_fft_chunk_sweep.txt) the three whole-array passes take 1.83 ms, the
     // chunked form 2.0-4.7 ms for chunks of 64 ... 2 planes -- cuFFT's 2-D transforms lose more on small batches than the
@@ -688,8 +698,10 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   P->fftwork.reserve(wmax ? wmax : 16);
   for (cufftHandle h : {P->plan_xy_chunk, P->plan_xy_rem})
     if (h) { X3D_CUFFT(cufftSetWorkArea(h, P->fftwork.p)); X3D_CUFFT(cufftSetStream(h, ctx.stream)); }
-  X3D_CUFFT(cufftSetWorkArea(P->plan_r2c, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_c2r, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_xy, P->fftwork.p));
-  X3D_CUFFT(cufftSetStream(P->plan_r2c, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_c2r, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_xy, ctx.stream));
+  if (!P->own_fft) {
+    X3D_CUFFT(cufftSetWorkArea(P->plan_r2c, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_c2r, P->fftwork.p)); X3D_CUFFT(cufftSetWorkArea(P->plan_xy, P->fftwork.p));
+    X3D_CUFFT(cufftSetStream(P->plan_r2c, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_c2r, ctx.stream)); X3D_CUFFT(cufftSetStream(P->plan_xy, ctx.stream));
+  }
   const size_t nsp_y = static_cast<size_t>(nx) * ny * std::max(nzhl, 1);       // spectral y-pencil
   const size_t nsp_z = static_cast<size_t>(nx) * std::max(nyl, 1) * nzh;       // spectral z-pencil
   const size_t nr_z = static_cast<size_t>(nx) * std::max(nyl, 1) * nz;         // physical z-pencil
@@ -743,6 +755,28 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     }
     fft_in = const_cast<double *>(cur);
     (void)ident_y; (void)ident_z;
+  }
+  if (P->own_fft) {
+    // poisson_000 with the hand-written passes: z r2c | (transpose) | y forward | x forward + spectral factor + x inverse |
+    // y inverse | (transpose) | z c2r -- the spectral array crosses HBM five times instead of seven
+    const long long lanes_z = static_cast<long long>(nx) * nyl;
+    if (lanes_z > 0) {
+      ProfScope ps(ctx, "fft_z_r2c(k_fft_z_r2c)");
+      fft_z_r2c(ctx, fft_in, cwz, nz, lanes_z, lanes_z);
+    }
+    if (multi) transpose_device(ctx, 2, reinterpret_cast<double *>(cwz), reinterpret_cast<double *>(cw), P->id_sp, 2);  // z -> y
+    if (nzhl > 0) {
+      FftSpec sp{ny, P->k0, -a.inv_norm, EPS, a.ax, a.bx, a.ay, a.by, a.az, a.bz, a.xk2, a.yk2, a.zk2, a.tx, a.ty, a.tz};
+      { ProfScope ps(ctx, "fft_y(k_fft_strided)"); fft_strided(ctx, cw, ny, nx, static_cast<long long>(nx) * ny, nx, nzhl, false); }
+      { ProfScope ps(ctx, "fft_x_fwd+spectral+fft_x_inv(k_fft_x_spec)"); fft_x_spec(ctx, cw, nx, static_cast<long long>(ny) * nzhl, &sp, 0); }
+      { ProfScope ps(ctx, "fft_y(k_fft_strided)"); fft_strided(ctx, cw, ny, nx, static_cast<long long>(nx) * ny, nx, nzhl, true); }
+    }
+    if (multi) transpose_device(ctx, 1, reinterpret_cast<double *>(cw), reinterpret_cast<double *>(cwz), P->id_sp, 2);  // y -> z
+    if (lanes_z > 0) {
+      ProfScope ps(ctx, "fft_z_c2r(k_fft_z_c2r)");
+      fft_z_c2r(ctx, cwz, d_rhs, nz, lanes_z, lanes_z);
+    }
+    return;
   }
   if (static_cast<long long>(nx) * nyl > 0) {
     ProfScope ps(ctx, "fft_z_r2c(cuFFT)");

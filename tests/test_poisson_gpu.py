@@ -31,7 +31,21 @@ CASES = [
     ((17, 13, 21), (1, 1, 1, 1, 1, 1)),   # poisson_11x, bcz=1 (TGV tests/ configuration)
     ((33, 65, 17), (2, 1, 1, 2, 2, 2)),
     ((64, 64, 64), (0, 0, 0, 0, 0, 0)),
+    # power-of-two periodic meshes: the hand-written FFT passes (x3d_fft_kernels.cuh): radices 8.8, 8.8.2, 8.8.4, 8.8.8 for the
+    # complex lines, half-length transforms 8.4, 8.8, 8.8.2, 8.8.4 for the real ones
+    ((128, 256, 64), (0, 0, 0, 0, 0, 0)),
+    ((256, 64, 128), (0, 0, 0, 0, 0, 0)),
+    ((64, 128, 256), (0, 0, 0, 0, 0, 0)),
+    ((512, 64, 64), (0, 0, 0, 0, 0, 0)),
+    ((64, 512, 64), (0, 0, 0, 0, 0, 0)),
+    ((64, 64, 512), (0, 0, 0, 0, 0, 0)),
 ]
+
+
+def test_poisson_000_cufft_path_matches_oracle(monkeypatch):
+    """X3D_FFT=0: the library FFT plans + k_spec_000s instead of the hand-written passes"""
+    monkeypatch.setenv("X3D_FFT", "0")
+    test_poisson_matches_oracle((64, 64, 64), (0, 0, 0, 0, 0, 0))
 
 
 STRETCHED = [  # (nodes, ncl, istret): matrice_refinement + inversion5_v1/v2 (src/poisson.f90:1814, src/tools.f90:1225)
