@@ -16,24 +16,54 @@ struct TwCache {
 };
 std::map<Ctx *, std::unique_ptr<TwCache>> g_tw;   // per context: device memory belongs to its device
 
-// W[m] = exp(-2 pi i m / n), evaluated in long double and by octant symmetry so that the table is exact to the last bit or two
-const double2 *twiddles(Ctx &ctx, int n) {
+// stages = false: the single table W[m] = exp(-2 pi i m / n); stages = true: the per-stage tables of an n-point transform
+// (FftTw<n>: TW_s[t-1][b] = exp(-2 pi i t (b mod NS) / (NS R)), stages 2 ..).  Angles in long double.
+template <int N>
+void build_stage_tables(std::vector<double> &h) {
+  using F = FftRadix<N>;
+  const long double pi = 3.141592653589793238462643383279502884L;
+  const int R[4] = {F::R1, F::R2, F::R3, F::R4};
+  int NS = R[0];
+  for (int s = 1; s < 4 && R[s]; ++s) {
+    for (int t = 1; t < R[s]; ++t)
+      for (int b = 0; b < N / R[s]; ++b) {
+        const long double a = -2.0L * pi * static_cast<long double>(t) * (b % NS) / (static_cast<long double>(NS) * R[s]);
+        h.push_back(static_cast<double>(cosl(a)));
+        h.push_back(static_cast<double>(sinl(a)));
+      }
+    NS *= R[s];
+  }
+}
+
+const double2 *twiddles(Ctx &ctx, int n, bool stages) {
   auto &slot = g_tw[&ctx];
   if (!slot) slot = std::make_unique<TwCache>();
-  auto it = slot->m.find(n);
+  const int key = stages ? -n : n;
+  auto it = slot->m.find(key);
   if (it != slot->m.end()) return reinterpret_cast<const double2 *>(it->second);
-  std::vector<double> h(2 * static_cast<size_t>(n));
-  const long double pi = 3.141592653589793238462643383279502884L;
-  for (int m = 0; m < n; ++m) {
-    const long double a = -2.0L * pi * static_cast<long double>(m) / static_cast<long double>(n);
-    h[2 * m] = static_cast<double>(cosl(a));
-    h[2 * m + 1] = static_cast<double>(sinl(a));
+  std::vector<double> h;
+  if (stages) {
+    switch (n) {
+      case 64: build_stage_tables<64>(h); break;
+      case 128: build_stage_tables<128>(h); break;
+      case 256: build_stage_tables<256>(h); break;
+      case 512: build_stage_tables<512>(h); break;
+      case 1024: build_stage_tables<1024>(h); break;
+      default: throw Error("hand-written FFT: unsupported length");
+    }
+  } else {
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int m = 0; m < n; ++m) {
+      const long double a = -2.0L * pi * static_cast<long double>(m) / static_cast<long double>(n);
+      h.push_back(static_cast<double>(cosl(a)));
+      h.push_back(static_cast<double>(sinl(a)));
+    }
   }
   double *d = nullptr;
   X3D_CUDA(cudaMalloc(&d, h.size() * sizeof(double)));
   X3D_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   X3D_CUDA(cudaStreamSynchronize(ctx.stream));
-  slot->m[n] = d;
+  slot->m[key] = d;
   return reinterpret_cast<const double2 *>(d);
 }
 
@@ -64,8 +94,12 @@ bool fft_real_ok(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || 
     default: throw Error("hand-written FFT: unsupported length");  \
   }
 
+static size_t tw_bytes(int n) {   // sum over the stages after the first of (R - 1) n / R entries: below 3 n for up to four stages
+  return static_cast<size_t>(3) * n * 16;
+}
+
 void fft_strided(Ctx &ctx, double2 *data, int n, long long stride, long long ostride, int lanes, long long nouter, bool inverse) {
-  const double2 *W = twiddles(ctx, n);
+  const double2 *W = twiddles(ctx, n, false);
   const long long ntiles = static_cast<long long>((lanes + 7) / 8) * nouter;
   const size_t smem = static_cast<size_t>(n) * 16 * 9;
 #define CALL(N)                                                                                                             \
@@ -76,7 +110,7 @@ void fft_strided(Ctx &ctx, double2 *data, int n, long long stride, long long ost
 }
 
 void fft_z_r2c(Ctx &ctx, const double *in, double2 *out, int n, long long plane, long long lanes) {
-  const double2 *W = twiddles(ctx, n);
+  const double2 *W = twiddles(ctx, n, false);
   const long long ntiles = (lanes + 15) / 16;
   const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(n / 2 + 1) * 16 * 16;
 #define CALL(N) launch(ctx, k_fft_z_r2c<N>, N, smem, ntiles, N <= 512 ? 2 : 1, in, out, plane, lanes, ntiles, W)
@@ -85,7 +119,7 @@ void fft_z_r2c(Ctx &ctx, const double *in, double2 *out, int n, long long plane,
 }
 
 void fft_z_c2r(Ctx &ctx, const double2 *in, double *out, int n, long long plane, long long lanes) {
-  const double2 *W = twiddles(ctx, n);
+  const double2 *W = twiddles(ctx, n, false);
   const long long ntiles = (lanes + 15) / 16;
   const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(n / 2 + 1) * 16 * 16;
 #define CALL(N) launch(ctx, k_fft_z_c2r<N>, N, smem, ntiles, N <= 512 ? 2 : 1, in, out, plane, lanes, ntiles, W)
@@ -94,9 +128,9 @@ void fft_z_c2r(Ctx &ctx, const double2 *in, double *out, int n, long long plane,
 }
 
 void fft_x_spec(Ctx &ctx, double2 *data, int n, long long nlines, const FftSpec *sp, int inverse_only) {
-  const double2 *W = twiddles(ctx, n);
+  const double2 *W = twiddles(ctx, n, true);
   const long long ntiles = (nlines + 7) / 8;
-  const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(8) * (n + n / 8 + 1) * 16 + (sp ? static_cast<size_t>(3) * n * 8 : 0);
+  const size_t smem = tw_bytes(n) + static_cast<size_t>(8) * (n + n / 8 + 1) * 16 + (sp ? static_cast<size_t>(3) * n * 8 + 8 * 4 * 8 : 0);
   FftSpec none{};
 #define CALL(N)                                                                                                   \
   if (sp) launch(ctx, k_fft_x_spec<N, true>, N, smem, ntiles, N <= 512 ? 2 : 1, data, nlines, W, *sp, 0);            \

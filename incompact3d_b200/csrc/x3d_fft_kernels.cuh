@@ -79,8 +79,25 @@ template <> struct FftRadix<256>  { static constexpr int R1 = 8, R2 = 8, R3 = 4,
 template <> struct FftRadix<512>  { static constexpr int R1 = 8, R2 = 8, R3 = 8, R4 = 0; };
 template <> struct FftRadix<1024> { static constexpr int R1 = 8, R2 = 8, R3 = 8, R4 = 2; };
 
-// One Stockham stage on the 8 points of a thread (points j + m N/8 on entry).  NS = product of the earlier radices; WS = stride of
-// this transform's twiddles in the table W (the table may belong to a longer transform).  row[m] = where point m goes.
+// Twiddles.  Two table forms:
+//  * strided passes (threads of a quarter-warp share the butterfly index): ONE table W[m] = exp(-2 pi i m / NW), NW = WS N, read at
+//    m = t (b mod NS) N / (NS R) WS -- a broadcast within the quarter-warp;
+//  * contiguous pass (neighbouring threads = neighbouring butterflies): one table per stage after the first,
+//    TW_s[t-1][b] = exp(-2 pi i t (b mod NS) / (NS R)), b = 0 .. N/R-1, so that neighbouring threads read neighbouring entries.  With
+//    the single table the second stage read with a stride of 128 bytes: an 8-way bank conflict, 52 % of that kernel's
+//    shared-memory wavefronts (ncu, profiles/r2o_fft_ncu_summary.txt).
+// Measured and dropped: taking only w from the table and its powers by multiplication (fewer shared-memory reads, but the
+// dependent FP64 chains cost more: y pass 0.44 -> 0.51 ms at 512^3).
+template <int N> struct FftTw {
+  using F = FftRadix<N>;
+  static constexpr int n2 = F::R2 ? (F::R2 - 1) * (N / F::R2) : 0;
+  static constexpr int n3 = F::R3 ? (F::R3 - 1) * (N / F::R3) : 0;
+  static constexpr int n4 = F::R4 ? (F::R4 - 1) * (N / F::R4) : 0;
+  static constexpr int off2 = 0, off3 = n2, off4 = n2 + n3, total = n2 + n3 + n4;
+};
+
+// One Stockham stage on the 8 points of a thread (points j + m N/8 on entry).  NS = product of the earlier radices.
+// WS > 0: W is the single table of a transform of length WS N; WS = 0: W is this stage's own table.  row[m] = where point m goes.
 template <int N, int R, int NS, int WS, bool INV>
 __device__ __forceinline__ void fft_stage(double2 (&v)[8], int (&row)[8], int j, const double2 *__restrict__ W) {
   constexpr int T = N / 8, Q = 8 / R;
@@ -90,7 +107,10 @@ __device__ __forceinline__ void fft_stage(double2 (&v)[8], int (&row)[8], int j,
     const int k = b & (NS - 1);
     if (NS > 1) {
 #pragma unroll
-      for (int t = 1; t < R; ++t) v[u + t * Q] = cmulw<INV>(v[u + t * Q], W[t * k * (N / (NS * R)) * WS]);
+      for (int t = 1; t < R; ++t) {
+        const double2 w = WS > 0 ? W[t * k * (N / (NS * R)) * WS] : W[(t - 1) * (N / R) + b];
+        v[u + t * Q] = cmulw<INV>(v[u + t * Q], w);
+      }
     }
     if (R == 8) bfly8<INV>(v[u], v[u + Q], v[u + 2 * Q], v[u + 3 * Q], v[u + 4 * Q], v[u + 5 * Q], v[u + 6 * Q], v[u + 7 * Q]);
     else if (R == 4) bfly4<INV>(v[u], v[u + Q], v[u + 2 * Q], v[u + 3 * Q]);
@@ -131,18 +151,19 @@ __device__ __forceinline__ void fft_exchange(double2 (&v)[8], const int (&row)[8
 template <int N, int WS, bool INV, class Acc>
 __device__ __forceinline__ void fft_run(double2 (&v)[8], int (&row)[8], int j, const double2 *__restrict__ W, const Acc &acc) {
   using F = FftRadix<N>;
+  using TW = FftTw<N>;
   fft_stage<N, F::R1, 1, WS, INV>(v, row, j, W);
   if constexpr (F::R2 != 0) {
     fft_exchange<N>(v, row, j, acc);
-    fft_stage<N, F::R2, F::R1, WS, INV>(v, row, j, W);
+    fft_stage<N, F::R2, F::R1, WS, INV>(v, row, j, W + (WS > 0 ? 0 : TW::off2));
   }
   if constexpr (F::R3 != 0) {
     fft_exchange<N>(v, row, j, acc);
-    fft_stage<N, F::R3, F::R1 * F::R2, WS, INV>(v, row, j, W);
+    fft_stage<N, F::R3, F::R1 * F::R2, WS, INV>(v, row, j, W + (WS > 0 ? 0 : TW::off3));
   }
   if constexpr (F::R4 != 0) {
     fft_exchange<N>(v, row, j, acc);
-    fft_stage<N, F::R4, F::R1 * F::R2 * F::R3, WS, INV>(v, row, j, W);
+    fft_stage<N, F::R4, F::R1 * F::R2 * F::R3, WS, INV>(v, row, j, W + (WS > 0 ? 0 : TW::off4));
   }
 }
 
@@ -185,7 +206,8 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
                 const double2 *__restrict__ Wg) {
   constexpr int M = N / 2, T = M / 8, LX = 16;
   extern __shared__ __align__(16) unsigned char fft_smem[];
-  double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N] table of the real length
+  double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N] table of the real length (the M-point transform reads every second entry)
+  double2 *U = W;
   double2 *tile = W + N;                                // [M][LX]
   for (int i = threadIdx.x; i < N; i += blockDim.x) W[i] = Wg[i];
   __syncthreads();
@@ -216,7 +238,7 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
       const double2 E = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
       const double2 D = csub(a, b);
       const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);
-      const double2 X = cadd(E, cmulw<false>(O, W[k]));
+      const double2 X = cadd(E, cmulw<false>(O, U[k]));
       if (ok) {
         q[static_cast<long long>(k) * plane] = X;
         if (k == 0) q[static_cast<long long>(M) * plane] = make_double2(E.x - O.x, 0.0);
@@ -233,7 +255,8 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
                 const double2 *__restrict__ Wg) {
   constexpr int M = N / 2, T = M / 8, LX = 16;
   extern __shared__ __align__(16) unsigned char fft_smem[];
-  double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N]
+  double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N] table of the real length
+  double2 *U = W;
   double2 *tile = W + N;                                // [M + 1][LX]
   for (int i = threadIdx.x; i < N; i += blockDim.x) W[i] = Wg[i];
   __syncthreads();
@@ -259,7 +282,7 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
       const double2 a = acc.ld(k), bq = acc.ld(M - k);
       const double2 b = make_double2(bq.x, -bq.y);
       const double2 Ze = cadd(a, b);
-      const double2 Zo = cmulw<true>(csub(a, b), W[k]);
+      const double2 Zo = cmulw<true>(csub(a, b), U[k]);
       v[m] = make_double2(Ze.x - Zo.y, Ze.y + Zo.x);
     }
     __syncthreads();
@@ -289,11 +312,11 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
     k_fft_x_spec(double2 *__restrict__ data, long long nlines, const double2 *__restrict__ Wg, const __grid_constant__ FftSpec sp, int inverse_only) {
   constexpr int T = N / 8, LL = 8, PITCH = N + N / 8 + 1;
   extern __shared__ __align__(16) unsigned char fft_smem[];
-  double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N]
-  double2 *tile = W + N;                                // [LL][PITCH]
+  double2 *W = reinterpret_cast<double2 *>(fft_smem);   // stage tables of the N-point transform
+  double2 *tile = W + FftTw<N>::total;                  // [LL][PITCH]
   double *xt = reinterpret_cast<double *>(tile + LL * PITCH);   // [3][N]: x-dependent parts of the spectral factor
+  for (int i = threadIdx.x; i < FftTw<N>::total; i += blockDim.x) W[i] = Wg[i];
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    W[i] = Wg[i];
     if constexpr (SPEC) {
       const double f = sp.tx[i];
       xt[i] = sp.xk2[i];
@@ -314,27 +337,37 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
 #pragma unroll
     for (int m = 0; m < 8; ++m) v[m] = ok ? p[j + m * T] : make_double2(0.0, 0.0);
     if constexpr (SPEC) {
-      fft_run<N, 1, false>(v, row, j, W, acc);
-      fft_exchange<N>(v, row, j, acc);       // natural order back into the read pattern: v[m] is mode i = j + m T
-      const int jy = static_cast<int>(line % sp.ny), kl = static_cast<int>(line / sp.ny), k = kl + sp.k0;
+      fft_run<N, 0, false>(v, row, j, W, acc);
+      // the last Stockham stage leaves point row[m] = j + m T in slot m: exactly the read pattern of a first stage, so the inverse
+      // transform starts from the registers as they are (v[m] is mode i = j + m T); the forward transform's last exchange ended
+      // with a barrier, so the inverse one may write shared memory at once
       if (ok) {
+        // the (y, z)-dependent parts of the factor (every thread of the line: passing them through shared memory measured slower)
+        const int jy = static_cast<int>(line % sp.ny), k = static_cast<int>(line / sp.ny) + sp.k0;
         const double fy = sp.ty[jy], fz = sp.tz[2 * k];
         const double A = (fy * fz) * (fy * fz);
         const double BC = sp.yk2[jy] * (fz * fz) + sp.zk2[2 * k] * (fy * fy);
-        const double wzy = (sp.az[k] * sp.az[k] + sp.bz[k] * sp.bz[k]) * (sp.ay[jy] * sp.ay[jy] + sp.by[jy] * sp.by[jy]);
+        const double wzy = sp.neg_inv_norm * ((sp.az[k] * sp.az[k] + sp.bz[k] * sp.bz[k]) * (sp.ay[jy] * sp.ay[jy] + sp.by[jy] * sp.by[jy]));
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
           const int i = j + m * T;
           const double kk = fma(xt[i], A, xt[N + i] * BC);
-          const double g = kk < sp.eps ? 0.0 : (sp.neg_inv_norm * (wzy * xt[2 * N + i])) / kk;   // src/poisson.f90:366 and k_spec_000s
+          // src/poisson.f90:366 and k_spec_000s; kk is a sum of positive terms well inside the normal range, so the division is a
+          // reciprocal seed + two Newton steps (correctly rounded but for the last bit) instead of the IEEE division's slow path
+          double rc;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(kk));
+          rc = fma(fma(-kk, rc, 1.0), rc, rc);
+          rc = fma(fma(-kk, rc, 1.0), rc, rc);
+          rc = fma(fma(-kk, rc, 1.0), rc, rc);
+          const double g = kk < sp.eps ? 0.0 : (wzy * xt[2 * N + i]) * rc;
           v[m].x *= g;
           v[m].y *= g;
         }
       }
-      fft_run<N, 1, true>(v, row, j, W, acc);
+      fft_run<N, 0, true>(v, row, j, W, acc);
     } else {
-      if (inverse_only) fft_run<N, 1, true>(v, row, j, W, acc);
-      else fft_run<N, 1, false>(v, row, j, W, acc);
+      if (inverse_only) fft_run<N, 0, true>(v, row, j, W, acc);
+      else fft_run<N, 0, false>(v, row, j, W, acc);
     }
     if (ok) {
 #pragma unroll

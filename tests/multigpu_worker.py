@@ -70,7 +70,8 @@ def main():
     # the z -> y transposes) run
     # X3D_P2P_MODE (read by x3d_decomp_init): the block copies of the y<->z transposes through the vector-copy kernel
     # (what these small pencils take by default) and through the copy engines (what 512^3 pencils take)
-    for nn, ncl, p2p_mode, overlap in (((32, 24, 40), (0,) * 6, None, "0"), ((33, 25, 33), (1,) * 6, "1", "0"), ((24, 176, 168), (0,) * 6, None, "0"),
+    for nn, ncl, p2p_mode, overlap in (((32, 24, 40), (0,) * 6, None, "0"),
+                                       ((64, 64, 128), (0,) * 6, None, "0"),   # power-of-two periodic mesh: the hand-written FFT passes, 65 spectral planes split unevenly ((33, 25, 33), (1,) * 6, "1", "0"), ((24, 176, 168), (0,) * 6, None, "0"),
                                        ((24, 176, 168), (0,) * 6, "1", "1"), ((176, 176, 168), (0,) * 6, None, "2"),
                                        # equal slabs of >= 64 planes: the z part of the momentum terms runs on the slabs themselves
                                        # (k_mom_slab + k_zfix, halo and carry planes through ring_exchange) instead of through transposes
