@@ -255,6 +255,10 @@ def alg_bytes(name, npts, nsp):
         return 104.0 * npts                     # intt of RK3: 13 array passes on average over the sub-steps
     if name.startswith("fft_z"):
         return 8.0 * npts + 16.0 * nsp
+    if name.startswith("fft_y(") or name.startswith("fft_x_fwd+spectral"):
+        return 32.0 * nsp                       # one read + one write of the spectral array (the x pass does two transforms and the factor)
+    if name.startswith("fft_y_fwd+fft_x_fwd") or name.startswith("fft_x_inv+fft_y_inv"):
+        return 64.0 * nsp                       # two passes
     if name.startswith("fft_xy") or name.startswith("poisson_spectral"):
         return 32.0 * nsp
     if name.startswith("transpose"):

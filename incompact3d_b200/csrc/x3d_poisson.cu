@@ -5,8 +5,10 @@
 //   -> fused spectral kernels: normalise, half-sample phase rotations / DCT post-processing with
 //      the mirrored partner, division by the modified wavenumbers, inverse post-processing
 //   -> inverse FFTs -> inverse reorder.
-// The 1-D FFT passes are cuFFT plans (library code, like calling cuBLAS); everything around
-// them is hand written.  kxyz (src/poisson.f90:1733-1738,1787-1800) is NOT stored: it is
+// The 1-D FFT passes are hand written too (x3d_fft_kernels.cuh) when the Poisson mesh has power-of-two extents
+// (64 .. 1024): real z transforms, strided y transforms, contiguous x transforms -- for poisson_000 the forward x
+// transform, the spectral factor and the inverse x transform are ONE kernel.  Other extents (768, 1536, odd) and
+// X3D_FFT=0 use cuFFT plans (library code, like calling cuBLAS) between the hand-written kernels.  kxyz (src/poisson.f90:1733-1738,1787-1800) is NOT stored: it is
 // rebuilt per mode from three 1-D tables (squared modified wavenumbers and interpolator
 // transfer functions), which removes a 16 B/mode read and 1 GB of HBM at 512^3.
 #include <cufft.h>
@@ -56,6 +58,7 @@ struct PoissonImpl : PoissonState {
   // poisson_000 on power-of-two meshes: the hand-written FFT passes of x3d_fft_kernels.cuh instead of the cuFFT plans (z real
   // transforms, y transforms, and ONE x pass that does forward transform + spectral factor + inverse transform).  X3D_FFT=0: cuFFT.
   bool own_fft = false;
+  bool own_spec = false;   // poisson_000: the spectral factor inside the x pass
   bool spec_real = false;   // poisson_000 with identical (re,im) z tables: the spectral step is one real factor per mode
   int istret = 0;
   int pen_nsys = 0, pen_rows = 0;     // istret 1,2: two systems (odd / even modes) of ny/2 rows; istret 3: one of nym rows
@@ -664,8 +667,9 @@ void poisson_init(Ctx &ctx, const x3d_poisson_params &p) {
   size_t ws = 0, wmax = 0;
   {
     const char *e = getenv("X3D_FFT");
-    P->own_fft = !(e && atoi(e) == 0) && !(p.bcx || p.bcy || p.bcz) && P->spec_real && fft_real_ok(nz) && fft_complex_ok(ny) && fft_complex_ok(nx) &&
-                 !getenv("X3D_FFT_CHUNK");
+    // nx, ny, nz are the extents of the Poisson mesh (nxm ...: 64^3 for the 65^3 free-slip TGV, 256 x 128 x 128 for the channel)
+    P->own_fft = !(e && atoi(e) == 0) && fft_real_ok(nz) && fft_complex_ok(ny) && fft_complex_ok(nx) && !getenv("X3D_FFT_CHUNK");
+    P->own_spec = P->own_fft && !(p.bcx || p.bcy || p.bcz) && P->spec_real;
   }
   X3D_CUFFT(cufftCreate(&P->plan_r2c)); X3D_CUFFT(cufftCreate(&P->plan_c2r)); X3D_CUFFT(cufftCreate(&P->plan_xy));
   P->plans = true;
@@ -756,10 +760,10 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     fft_in = const_cast<double *>(cur);
     (void)ident_y; (void)ident_z;
   }
-  if (P->own_fft) {
+  if (P->own_spec) {
     // poisson_000 with the hand-written passes: z r2c | (transpose) | y forward | x forward + spectral factor + x inverse |
     // y inverse | (transpose) | z c2r -- the spectral array crosses HBM five times instead of seven
-    const long long lanes_z = static_cast<long long>(nx) * nyl;
+    const long long lanes_z = static_cast<long long>(nx) * nyl;   // (this block returns)
     if (lanes_z > 0) {
       ProfScope ps(ctx, "fft_z_r2c(k_fft_z_r2c)");
       fft_z_r2c(ctx, fft_in, cwz, nz, lanes_z, lanes_z);
@@ -778,7 +782,24 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     }
     return;
   }
-  if (static_cast<long long>(nx) * nyl > 0) {
+  const long long lanes_z = static_cast<long long>(nx) * nyl;
+  // the x-y transforms of the variants whose spectral step is not the single real factor: hand-written y and x passes, or the 2-D plan
+  auto fft_xy = [&](bool inverse) {
+    if (nzhl <= 0) return;
+    if (P->own_fft) {
+      ProfScope ps(ctx, inverse ? "fft_x_inv+fft_y_inv(k_fft_x_spec, k_fft_strided)" : "fft_y_fwd+fft_x_fwd(k_fft_strided, k_fft_x_spec)");
+      if (!inverse) fft_strided(ctx, cw, ny, nx, static_cast<long long>(nx) * ny, nx, nzhl, false);
+      fft_x_spec(ctx, cw, nx, static_cast<long long>(ny) * nzhl, nullptr, inverse ? 1 : 0);
+      if (inverse) fft_strided(ctx, cw, ny, nx, static_cast<long long>(nx) * ny, nx, nzhl, true);
+    } else {
+      ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
+      X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    }
+  };
+  if (lanes_z > 0 && P->own_fft) {
+    ProfScope ps(ctx, "fft_z_r2c(k_fft_z_r2c)");
+    fft_z_r2c(ctx, fft_in, cwz, nz, lanes_z, lanes_z);
+  } else if (lanes_z > 0) {
     ProfScope ps(ctx, "fft_z_r2c(cuFFT)");
     X3D_CUFFT(cufftExecD2Z(P->plan_r2c, fft_in, reinterpret_cast<cufftDoubleComplex *>(cwz)));
   }
@@ -798,10 +819,7 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
       X3D_CUFFT(cufftExecZ2Z(h, pc, pc, CUFFT_INVERSE));
     }
   }
-  if (nzhl > 0 && !chunked) {
-    ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
-    X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_FORWARD));
-  }
+  if (!chunked) fft_xy(false);
   auto stage = [&](unsigned mode, const double2 *in, double2 *out) {
     if (nsp == 0) return;
     ProfScope ps(ctx, "poisson_spectral(k_spec)");
@@ -839,13 +857,13 @@ void poisson_solve_device(Ctx &ctx, double *d_rhs) {
     stage(S_PREX, cw, cwb);
     stage(S_PREY | S_ROTZ_B, cwb, cw);
   }
-  if (nzhl > 0 && !chunked) {
-    ProfScope ps(ctx, "fft_xy_c2c(cuFFT)");
-    X3D_CUFFT(cufftExecZ2Z(P->plan_xy, reinterpret_cast<cufftDoubleComplex *>(cw), reinterpret_cast<cufftDoubleComplex *>(cw), CUFFT_INVERSE));
-  }
+  if (!chunked) fft_xy(true);
   if (multi) transpose_device(ctx, 1, reinterpret_cast<double *>(cw), reinterpret_cast<double *>(cwz), P->id_sp, 2);  // y -> z
   double *fft_out = any ? rw : d_rhs;
-  if (static_cast<long long>(nx) * nyl > 0) {
+  if (lanes_z > 0 && P->own_fft) {
+    ProfScope ps(ctx, "fft_z_c2r(k_fft_z_c2r)");
+    fft_z_c2r(ctx, cwz, fft_out, nz, lanes_z, lanes_z);
+  } else if (lanes_z > 0) {
     ProfScope ps(ctx, "fft_z_c2r(cuFFT)");
     X3D_CUFFT(cufftExecZ2D(P->plan_c2r, reinterpret_cast<cufftDoubleComplex *>(cwz), fft_out));
   }
