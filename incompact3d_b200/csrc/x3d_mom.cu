@@ -368,7 +368,10 @@ void launch_zfix(Ctx &ctx, const ZFix &Z, const double *yin, const double *z0n, 
   z.tab = static_cast<const double *>(Z.tab.p);
   z.nl = nlanes; z.n = Z.n; z.W = Z.W; z.k1 = Z.k1; z.k2 = Z.k2;
   ProfScope ps(ctx, "momentum_z_face_corrections(k_zfix)");
-  k_zfix<<<static_cast<unsigned>((nlanes + 255) / 256), 256, 0, ctx.stream>>>(z);
+  if ((nlanes & 1) || ((reinterpret_cast<uintptr_t>(yin) | reinterpret_cast<uintptr_t>(z0n) | reinterpret_cast<uintptr_t>(yout) | reinterpret_cast<uintptr_t>(a) |
+                       reinterpret_cast<uintptr_t>(sum[0]) | reinterpret_cast<uintptr_t>(sum[1]) | reinterpret_cast<uintptr_t>(sum[2])) & 15u))
+    throw Error("slab face corrections: unaligned field");
+  k_zfix<<<static_cast<unsigned>((nlanes / 2 + 255) / 256), 256, 0, ctx.stream>>>(z);
   X3D_CUDA(cudaGetLastError());
   ctx.launches++;
 }

@@ -327,27 +327,51 @@ struct ZFixArgs {
   double k1, k2;                    // -1/2 / c (D1), xnu / c (D2)
 };
 __global__ void __launch_bounds__(256) k_zfix(const __grid_constant__ ZFixArgs z) {
-  const long long l = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  // two neighbouring lines per thread (16-byte accesses), four rows in flight
+  const long long l = 2 * (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x);
   if (l >= z.nl) return;
-  double Y[9], Z[9];
+  double2 Y[9], Z[9];
   const double A01 = z.tab[0], A02 = z.tab[2 * z.n];
   X3D_UNROLL
   for (int s = 0; s < 9; ++s) {
-    Y[s] = z.yin[s * z.nl + l];
-    Z[s] = fma((s % 3 == 0) ? A02 : A01, z.yout[s * z.nl + l], z.z0n[s * z.nl + l]);
+    Y[s] = *reinterpret_cast<const double2 *>(z.yin + s * z.nl + l);
+    const double2 yo = *reinterpret_cast<const double2 *>(z.yout + s * z.nl + l), z0 = *reinterpret_cast<const double2 *>(z.z0n + s * z.nl + l);
+    const double a0 = (s % 3 == 0) ? A02 : A01;
+    Z[s] = make_double2(fma(a0, yo.x, z0.x), fma(a0, yo.y, z0.y));
   }
   const int n = z.n, W = z.W;
-  for (int i = 0; i < n; ++i) {
-    if (i == W && n - W > W) i = n - W;
-    const double a1 = z.tab[i], b1 = z.tab[n + i], a2 = z.tab[2 * n + i], b2 = z.tab[3 * n + i];
-    const long long o = static_cast<long long>(i) * z.nl + l;
-    const double av = z.a[o];
+  const int nrows = (n - W > W) ? 2 * W : n;          // rows 0 .. W-1 and n-W .. n-1 (all rows when the bands meet)
+  constexpr int NB = 4;
+  for (int r0 = 0; r0 < nrows; r0 += NB) {
+    double2 av[NB], sv[NB][3];
+    int row[NB];
     X3D_UNROLL
-    for (int q = 0; q < 3; ++q) {
-      const double d0 = fma(a2, Y[3 * q], b2 * Z[3 * q]);
-      const double d1 = fma(a1, Y[3 * q + 1], b1 * Z[3 * q + 1]);
-      const double d2 = fma(a1, Y[3 * q + 2], b1 * Z[3 * q + 2]);
-      z.sum[q][o] += z.k2 * d0 + z.k1 * fma(av, d1, d2);
+    for (int q = 0; q < NB; ++q) {
+      const int r = r0 + q;
+      row[q] = (nrows == n || r < W) ? r : n - 2 * W + r;
+      if (r < nrows) {
+        const long long o = static_cast<long long>(row[q]) * z.nl + l;
+        av[q] = *reinterpret_cast<const double2 *>(z.a + o);
+        X3D_UNROLL
+        for (int c = 0; c < 3; ++c) sv[q][c] = *reinterpret_cast<const double2 *>(z.sum[c] + o);
+      }
+    }
+    X3D_UNROLL
+    for (int q = 0; q < NB; ++q) {
+      if (r0 + q >= nrows) break;
+      const int i = row[q];
+      const double a1 = z.tab[i], b1 = z.tab[n + i], a2 = z.tab[2 * n + i], b2 = z.tab[3 * n + i];
+      const long long o = static_cast<long long>(i) * z.nl + l;
+      X3D_UNROLL
+      for (int c = 0; c < 3; ++c) {
+        const double d0x = fma(a2, Y[3 * c].x, b2 * Z[3 * c].x), d0y = fma(a2, Y[3 * c].y, b2 * Z[3 * c].y);
+        const double d1x = fma(a1, Y[3 * c + 1].x, b1 * Z[3 * c + 1].x), d1y = fma(a1, Y[3 * c + 1].y, b1 * Z[3 * c + 1].y);
+        const double d2x = fma(a1, Y[3 * c + 2].x, b1 * Z[3 * c + 2].x), d2y = fma(a1, Y[3 * c + 2].y, b1 * Z[3 * c + 2].y);
+        double2 sN = sv[q][c];
+        sN.x += z.k2 * d0x + z.k1 * fma(av[q].x, d1x, d2x);
+        sN.y += z.k2 * d0y + z.k1 * fma(av[q].y, d1y, d2y);
+        *reinterpret_cast<double2 *>(z.sum[c] + o) = sN;
+      }
     }
   }
 }
