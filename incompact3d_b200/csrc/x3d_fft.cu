@@ -111,30 +111,33 @@ void fft_strided(Ctx &ctx, double2 *data, int n, long long stride, long long ost
 
 void fft_z_r2c(Ctx &ctx, const double *in, double2 *out, int n, long long plane, long long lanes) {
   const double2 *W = twiddles(ctx, n, false);
-  const long long ntiles = (lanes + 15) / 16;
-  const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(n / 2 + 1) * 16 * 16;
-#define CALL(N) launch(ctx, k_fft_z_r2c<N>, N, smem, ntiles, N <= 512 ? 2 : 1, in, out, plane, lanes, ntiles, W)
+  const int lx = 16;   // FftZLanes
+  const long long ntiles = (lanes + lx - 1) / lx;
+  const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(n / 2 + 1) * lx * 16;
+#define CALL(N) launch(ctx, k_fft_z_r2c<N>, FftZLanes<N>::LX * N / 16, smem, ntiles, FftZLanes<N>::MINB, in, out, plane, lanes, ntiles, W)
   X3D_FFT_SWITCH(n, CALL)
 #undef CALL
 }
 
 void fft_z_c2r(Ctx &ctx, const double2 *in, double *out, int n, long long plane, long long lanes) {
   const double2 *W = twiddles(ctx, n, false);
-  const long long ntiles = (lanes + 15) / 16;
-  const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(n / 2 + 1) * 16 * 16;
-#define CALL(N) launch(ctx, k_fft_z_c2r<N>, N, smem, ntiles, N <= 512 ? 2 : 1, in, out, plane, lanes, ntiles, W)
+  const int lx = 16;   // FftZLanes
+  const long long ntiles = (lanes + lx - 1) / lx;
+  const size_t smem = static_cast<size_t>(n) * 16 + static_cast<size_t>(n / 2 + 1) * lx * 16;
+#define CALL(N) launch(ctx, k_fft_z_c2r<N>, FftZLanes<N>::LX * N / 16, smem, ntiles, FftZLanes<N>::MINB, in, out, plane, lanes, ntiles, W)
   X3D_FFT_SWITCH(n, CALL)
 #undef CALL
 }
 
 void fft_x_spec(Ctx &ctx, double2 *data, int n, long long nlines, const FftSpec *sp, int inverse_only) {
   const double2 *W = twiddles(ctx, n, true);
-  const long long ntiles = (nlines + 7) / 8;
-  const size_t smem = tw_bytes(n) + static_cast<size_t>(8) * (n + n / 8 + 1) * 16 + (sp ? static_cast<size_t>(3) * n * 8 + 8 * 4 * 8 : 0);
+  const int ll = n <= 512 ? 4 : 8;   // FftXLines
+  const long long ntiles = (nlines + ll - 1) / ll;
+  const size_t smem = tw_bytes(n) + static_cast<size_t>(ll) * (n + n / 8 + 1) * 16 + (sp ? static_cast<size_t>(3) * n * 8 : 0);
   FftSpec none{};
-#define CALL(N)                                                                                                   \
-  if (sp) launch(ctx, k_fft_x_spec<N, true>, N, smem, ntiles, N <= 512 ? 2 : 1, data, nlines, W, *sp, 0);            \
-  else launch(ctx, k_fft_x_spec<N, false>, N, smem, ntiles, N <= 512 ? 2 : 1, data, nlines, W, none, inverse_only)
+#define CALL(N)                                                                                                                              \
+  if (sp) launch(ctx, k_fft_x_spec<N, true>, FftXLines<N>::LL * N / 8, smem, ntiles, FftXLines<N>::MINB, data, nlines, W, *sp, 0);            \
+  else launch(ctx, k_fft_x_spec<N, false>, FftXLines<N>::LL * N / 8, smem, ntiles, FftXLines<N>::MINB, data, nlines, W, none, inverse_only)
   X3D_FFT_SWITCH(n, CALL)
 #undef CALL
 }

@@ -198,20 +198,23 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
   }
 }
 
+// lanes per CTA of the real transforms: 16 (128 B of reals, 256 B of complex per row; N threads, two CTAs per SM up to N = 512).
+// Measured: 8 lanes (64-byte rows, N/2 threads, three CTAs per SM) take 0.59 instead of 0.47 / 0.53 ms at 512^3.
+template <int N> struct FftZLanes { static constexpr int LX = 16, SH = 4, MINB = N <= 512 ? 2 : 1; };
 // ---- real z lines -> complex half spectrum ---------------------------------------------------------------------------
 // in: (lanes, N rows) real with row stride `plane`; out: (lanes, N/2+1 rows) complex with the same row stride.  M = N/2.
 template <int N>
-__global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
+__global__ void __launch_bounds__(FftZLanes<N>::LX * N / 16, FftZLanes<N>::MINB)
     k_fft_z_r2c(const double *__restrict__ in, double2 *__restrict__ out, long long plane, long long lanes, long long ntiles,
                 const double2 *__restrict__ Wg) {
-  constexpr int M = N / 2, T = M / 8, LX = 16;
+  constexpr int M = N / 2, T = M / 8, LX = FftZLanes<N>::LX;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N] table of the real length (the M-point transform reads every second entry)
   double2 *U = W;
   double2 *tile = W + N;                                // [M][LX]
   for (int i = threadIdx.x; i < N; i += blockDim.x) W[i] = Wg[i];
   __syncthreads();
-  const int l = threadIdx.x & (LX - 1), j = threadIdx.x >> 4;
+  const int l = threadIdx.x & (LX - 1), j = threadIdx.x >> FftZLanes<N>::SH;
   const AccStrided acc{tile + l, LX};
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long long lane = t * LX + l;
@@ -250,17 +253,17 @@ __global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
 
 // ---- complex half spectrum -> real z lines (unnormalised inverse) ---------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
+__global__ void __launch_bounds__(FftZLanes<N>::LX * N / 16, FftZLanes<N>::MINB)
     k_fft_z_c2r(const double2 *__restrict__ in, double *__restrict__ out, long long plane, long long lanes, long long ntiles,
                 const double2 *__restrict__ Wg) {
-  constexpr int M = N / 2, T = M / 8, LX = 16;
+  constexpr int M = N / 2, T = M / 8, LX = FftZLanes<N>::LX;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   double2 *W = reinterpret_cast<double2 *>(fft_smem);   // [N] table of the real length
   double2 *U = W;
   double2 *tile = W + N;                                // [M + 1][LX]
   for (int i = threadIdx.x; i < N; i += blockDim.x) W[i] = Wg[i];
   __syncthreads();
-  const int l = threadIdx.x & (LX - 1), j = threadIdx.x >> 4;
+  const int l = threadIdx.x & (LX - 1), j = threadIdx.x >> FftZLanes<N>::SH;
   const AccStrided acc{tile + l, LX};
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long long lane = t * LX + l;
@@ -307,10 +310,12 @@ struct FftSpec {
   double eps;
   const double *ax, *bx, *ay, *by, *az, *bz, *xk2, *yk2, *zk2, *tx, *ty, *tz;   // tables of waves() / abxyz(), as SpecArgs
 };
+// lines per CTA: 4 up to N = 512 (256 threads, three CTAs per SM: no register spills at 85 registers, smaller barrier groups), 8 above
+template <int N> struct FftXLines { static constexpr int LL = N <= 512 ? 4 : 8, MINB = N <= 512 ? 3 : 1; };
 template <int N, bool SPEC>
-__global__ void __launch_bounds__(N, (N <= 512 ? 2 : 1))
+__global__ void __launch_bounds__(FftXLines<N>::LL * N / 8, FftXLines<N>::MINB)
     k_fft_x_spec(double2 *__restrict__ data, long long nlines, const double2 *__restrict__ Wg, const __grid_constant__ FftSpec sp, int inverse_only) {
-  constexpr int T = N / 8, LL = 8, PITCH = N + N / 8 + 1;
+  constexpr int T = N / 8, LL = FftXLines<N>::LL, PITCH = N + N / 8 + 1;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   double2 *W = reinterpret_cast<double2 *>(fft_smem);   // stage tables of the N-point transform
   double2 *tile = W + FftTw<N>::total;                  // [LL][PITCH]
