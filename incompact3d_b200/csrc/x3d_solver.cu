@@ -180,6 +180,9 @@ struct SolverImpl : SolverState {
   // its right-hand side; neighbouring ranks exchange 4 halo planes per component and 18 carry planes.  X3D_SLABZ=0: transposes.
   // slab_nv > 1 on ONE rank (X3D_SLABZ_EMULATE=P): the rank's planes are treated as P virtual slabs with local copies for
   // the exchanges -- the same kernels and arithmetic as P ranks, testable on one GPU.
+  // several ranks: the two fields that divergence / gradp transpose are ready at different times; the transpose of the first one
+  // runs on `aux` beside the kernels that produce (divergence) or consume (gradp) the other one.  X3D_OVERLAP_DIV=0: one scope.
+  bool overlap_div = true;
   bool slabz = false;
   int slab_nv = 1;
   DevBuf zhalo[3];                          // [slab_nv][16 planes]
@@ -393,6 +396,7 @@ void solver_init(Ctx &ctx, const x3d_solver_params &p) {
   S->ipv_x_sub = S->ipv[0]; S->ipv_x_sub.op.store_mode = 2;
   if (const char *e = getenv("X3D_FUSE_SUMS")) S->fuse_sums = atoi(e) != 0;
   if (const char *e = getenv("X3D_OVERLAP")) S->overlap = atoi(e);
+  if (const char *e = getenv("X3D_OVERLAP_DIV")) S->overlap_div = atoi(e) != 0;
   {
     // slab z kernels: periodic z, the fused kernels with table-free solves in all three directions, equal slabs
     const char *e = getenv("X3D_SLABZ"), *em = getenv("X3D_SLABZ_EMULATE");
@@ -640,6 +644,23 @@ static void momentum_rhs(Ctx &ctx, SolverImpl &S, double *dux1, double *duy1, do
       map(ctx, n, [=] __device__(long long q) { dux1[q] = dux1[q] - wr * v[q]; duy1[q] = duy1[q] + wr * u[q]; });
     }
   }
+}
+
+static void ensure_aux(SolverImpl &S) {
+  if (S.aux) return;
+  int lo = 0, hi = 0;
+  X3D_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  X3D_CUDA(cudaStreamCreateWithPriority(&S.aux, cudaStreamNonBlocking, hi));
+  X3D_CUDA(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+  X3D_CUDA(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
+}
+// run f with ctx.stream = S.aux (the transposes take their stream from the context)
+template <class F>
+static void on_aux(Ctx &ctx, SolverImpl &S, F f) {
+  cudaStream_t main_stream = ctx.stream;
+  ctx.stream = S.aux;
+  try { f(); } catch (...) { ctx.stream = main_stream; throw; }
+  ctx.stream = main_stream;
 }
 
 // Fused form of momentum_rhs for periodic y and z: per direction one kernel forms
@@ -983,10 +1004,35 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
     });
     ta1 = a; tb1 = b; tc1 = c;
   }
+  const bool ovl = S.nranks > 1 && S.overlap_div && S.stag[1];
   run(ctx, S.dvp[0], ta1, pp1);    // :297
   run(ctx, S.ivp[0], tb1, pgy1);   // :313
-  run(ctx, S.ivp[0], tc1, pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
+  if (!ovl) run(ctx, S.ivp[0], tc1, pgz1);   // :314   (transpose_x_to_y :316-318 is local: p_row = 1)
   const long long nxm_ = S.nxm;
+  if (ovl) {
+    // duy is complete before the x and y interpolations of uz have started: its transpose (:329) runs on the second stream
+    // beside them, the transpose of their result (:330) follows on the same stream (one order of the group barriers on all ranks)
+    ensure_aux(S);
+    launch_stag_pair(ctx, 0, 1, S.ivp[1].op, S.dvp[1].op, pp1, pgy1, duy, nullptr, nxm_, S.p.ny, S.nzl, nxm_, nxm_ * S.p.ny);
+    X3D_CUDA(cudaEventRecord(S.ev_fork, ctx.stream));
+    X3D_CUDA(cudaStreamWaitEvent(S.aux, S.ev_fork, 0));
+    on_aux(ctx, S, [&] { transpose_device(ctx, 1, duy, t1, S.id_p3, 1); });
+    run(ctx, S.ivp[0], tc1, pgz1);       // :314
+    run(ctx, S.ivp[1], pgz1, upi2);      // :327
+    X3D_CUDA(cudaEventRecord(S.ev_fork, ctx.stream));
+    X3D_CUDA(cudaStreamWaitEvent(S.aux, S.ev_fork, 0));
+    on_aux(ctx, S, [&] { transpose_device(ctx, 1, upi2, t2, S.id_p3, 1); });
+    X3D_CUDA(cudaEventRecord(S.ev_join, S.aux));
+    X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));
+    const long long n3o = static_cast<long long>(S.n3);
+    if (nlock != 2 && S.stag[2] && n3o > 0) {
+      launch_stag_pair(ctx, 0, 2, S.ivp[2].op, S.dvp[2].op, t1, t2, out, nullptr, nxm_ * S.nyml, S.p.nz, 1, nxm_ * S.nyml, 0);
+      return;
+    }
+  }
+  const double *duy3 = duy, *uzp3 = upi2;
+  if (ovl) { duy3 = t1; uzp3 = t2; }
+  else {
   if (S.stag[1]) {                     // :321-325 in one kernel: duy = interyvp(pp1) + deryvp(pgy1)
     launch_stag_pair(ctx, 0, 1, S.ivp[1].op, S.dvp[1].op, pp1, pgy1, duy, nullptr, nxm_, S.p.ny, S.nzl, nxm_, nxm_ * S.p.ny);
   } else {
@@ -1000,12 +1046,12 @@ static void divergence(Ctx &ctx, SolverImpl &S, double *out, int nlock) {
   }
   }
   run(ctx, S.ivp[1], pgz1, upi2);      // :327
-  const double *duy3 = duy, *uzp3 = upi2;
   if (S.nranks > 1) {  // :329-330, both fields between one pair of barriers
     const double *src[2] = {duy, upi2};
     double *dst[2] = {t1, t2};
     transpose_device_multi(ctx, 1, 2, src, dst, S.id_p3, 1);
     duy3 = t1; uzp3 = t2;
+  }
   }
   const long long n3 = static_cast<long long>(S.n3);
   if (nlock != 2 && S.stag[2] && n3 > 0) {   // :333-339 in one kernel: out = interzvp(duy3) + derzvp(uzp3)
@@ -1048,7 +1094,17 @@ static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
     run(ctx, S.dpv[2], pp3, pgz3);   // :406
   }
   const double *pgz2 = pgz3, *pp2 = ppi3;
-  if (S.nranks > 1) {  // :410-411
+  const bool ovl = S.nranks > 1 && S.overlap_div && S.stag[1];
+  if (ovl) {
+    // ppi3 first (:411), then pgz3 (:410) on the second stream beside the y operators of ppi3
+    ensure_aux(S);
+    transpose_device(ctx, 2, ppi3, t2, S.id_p3, 1);
+    X3D_CUDA(cudaEventRecord(S.ev_fork, ctx.stream));
+    X3D_CUDA(cudaStreamWaitEvent(S.aux, S.ev_fork, 0));
+    on_aux(ctx, S, [&] { transpose_device(ctx, 2, pgz3, t1, S.id_p3, 1); });
+    X3D_CUDA(cudaEventRecord(S.ev_join, S.aux));
+    pgz2 = t1; pp2 = t2;
+  } else if (S.nranks > 1) {  // :410-411
     const double *src[2] = {pgz3, ppi3};
     double *dst[2] = {t1, t2};
     transpose_device_multi(ctx, 2, 2, src, dst, S.id_p3, 1);
@@ -1056,6 +1112,7 @@ static void gradp(Ctx &ctx, SolverImpl &S, const double *pp3, int itr) {
   }
   if (S.stag[1]) {                 // :413-415 in one kernel: one read of pp2
     launch_stag_pair(ctx, 1, 1, S.ipv[1].op, S.dpv[1].op, pp2, nullptr, ppi2, pgy2, nxm_, S.p.ny, S.nzl, nxm_, nxm_ * S.p.ny);
+    if (ovl) X3D_CUDA(cudaStreamWaitEvent(ctx.stream, S.ev_join, 0));
   } else {
     run(ctx, S.ipv[1], pp2, ppi2);   // :413
     run(ctx, S.dpv[1], pp2, pgy2);   // :415
