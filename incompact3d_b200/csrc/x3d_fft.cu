@@ -67,8 +67,8 @@ const double2 *twiddles(Ctx &ctx, int n, bool stages) {
   return reinterpret_cast<const double2 *>(d);
 }
 
-template <class K>
-void launch(Ctx &ctx, K kern, int threads, size_t smem, long long ntiles, int per_sm, auto... args) {
+template <class K, class... A>
+void launch(Ctx &ctx, K kern, int threads, size_t smem, long long ntiles, int per_sm, A... args) {
   X3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   long long blocks = static_cast<long long>(ctx.sm_count) * per_sm;
   if (blocks > ntiles) blocks = ntiles;
